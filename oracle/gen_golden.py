@@ -1,0 +1,237 @@
+"""Generate tests/golden/* by RUNNING THE UNMODIFIED REFERENCE (builder container only).
+
+TEST INFRASTRUCTURE.  Usage:  python oracle/gen_golden.py  [--out tests/golden]
+
+The reference has no tests or golden vectors for the ODE head, so the pin
+for the oracle is the reference itself, run here on CPU from /root/reference.  Weights, inputs and
+noise are produced by the name-keyed recipes in ``oracle/sf_oracle.py`` (``recipe_state_dict``,
+``recipe_array``), so the fixtures only hold the reference's OUTPUTS plus the recipe parameters;
+the same recipes regenerate the operands on the GPU box, where /root/reference does not exist.
+
+Fixtures written:
+  sched.json           step schedules traced from the reference's own control flow (variable / fixed step,
+                       euler / midpoint, jittered stamps incl. 1-ulp micro-steps and gap<delta_t cases) and
+                       the path-selection result per target.
+  tiny_full_c8.npz     FuturePredictionODE.forward, C=8, B=2, 16x16 BEV, jittered stamps, fp64 + fp32 runs.
+  c64_latent_*.npz     NNFOwithBayesianJumps.forward, C=64, 32x32 BEV (8x8 latent): per-event latent states,
+                       selected states, decoded frames; one file per solver / step-mode / impute variant.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import _refimport as ri  # noqa: E402
+from oracle import sf_oracle as so  # noqa: E402
+
+CANON_CAM = [-1.0, -0.5, 0.0]
+CANON_LIDAR = [-0.8, -0.6, -0.4, -0.2, 0.0]
+CANON_TARGETS = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+
+
+class Tracer:
+    """Wraps ode_step / gru_obs of a reference NNFOwithBayesianJumps instance and srvp_decode to expose the
+    event sequence, per-event states and which recorded state each target selected."""
+
+    def __init__(self, nnfo):
+        self.n = nnfo
+        self.events = []          # (kind, dt, t_after)
+        self.states = []
+        self.selected = None
+        self._ode, self._obs, self._dec = nnfo.ode_step, nnfo.gru_obs.forward, nnfo.srvp_decode
+
+    def __enter__(self):
+        def ode_step(state, inp, delta_t, current_time):
+            out = self._ode(state, inp, delta_t, current_time)
+            t_after = out[2].item() if isinstance(out[2], torch.Tensor) else float(out[2])
+            self.events.append(("step", float(delta_t), t_after))
+            self.states.append(out[0].detach().clone())
+            return out
+
+        def gru_obs(state, p, x_obs):
+            out = self._obs(state, p, x_obs)
+            self.events.append(("jump", 0.0, float("nan")))
+            self.states.append(out[0].detach().clone())
+            return out
+
+        def srvp_decode(x, skip=None):
+            self.selected = x.detach().clone()
+            return self._dec(x, skip)
+
+        self.n.ode_step, self.n.gru_obs.forward, self.n.srvp_decode = ode_step, gru_obs, srvp_decode
+        return self
+
+    def __exit__(self, *a):
+        self.n.ode_step, self.n.gru_obs.forward, self.n.srvp_decode = self._ode, self._obs, self._dec
+        return False
+
+    def selected_event_indices(self):
+        idx = []
+        for t in range(self.selected.shape[1]):
+            hits = [i for i, s in enumerate(self.states) if torch.equal(s, self.selected[:, t])]
+            idx.append(hits[-1] if hits else -1)   # latest identical state (states never repeat in practice)
+        return idx
+
+
+def build_nnfo(ref, C, solver, variable, impute, seed, gain, dtype):
+    m = ref.tob.NNFOwithBayesianJumps(C, C, ri.make_cfg(C, impute=impute, solver=solver, variable=variable)).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = so.recipe_state_dict(shapes, seed=seed, gain=gain, dtype=dtype)
+    m.to(dtype).load_state_dict(sd, strict=True)
+    return m, shapes
+
+
+def gen_schedules(ref, out_dir):
+    C, HW = 8, 8
+    cases = []
+    rng = np.random.RandomState(1234)
+
+    def run_case(times, targets, variable, solver, tag):
+        m, _ = build_nnfo(ref, C, solver, variable, True, 3, 1.0, torch.float32)
+        obs = torch.zeros(1, len(times), C, HW, HW)
+        inp = torch.zeros(1, 1, C, HW, HW)
+        with torch.no_grad(), Tracer(m) as tr:
+            m(times=torch.tensor(times, dtype=torch.float64), input=inp, obs=obs, delta_t=0.05,
+              T=torch.tensor(targets, dtype=torch.float64))
+        cases.append(dict(tag=tag, times=[float(t) for t in times], targets=[float(t) for t in targets],
+                          variable=variable, solver=solver, delta_t=0.05,
+                          kinds=[e[0] for e in tr.events], dts=[e[1] for e in tr.events],
+                          t_after=[None if e[0] == "jump" else e[2] for e in tr.events],
+                          selected=tr.selected_event_indices()))
+        return tr
+
+    canon = sorted(CANON_CAM + CANON_LIDAR)
+    for variable in (True, False):
+        for solver in ("euler", "midpoint"):
+            run_case(canon, CANON_TARGETS, variable, solver, f"canon_var{int(variable)}_{solver}")
+    run_case(CANON_CAM, [0.5, 1.0, 1.5, 2.0], True, "euler", "config1_cam_only")
+    run_case(canon, CANON_TARGETS[:3] + [0.05 * i for i in range(1, 41)], True, "euler", "streaming_40")
+    run_case(canon, CANON_TARGETS[:3] + [0.5 * i for i in range(1, 17)], True, "euler", "long_8s")
+    # jittered stamps: keep a spread of step counts, every micro-step case and every gap<delta_t case found
+    n_micro = n_gap = n_plain = 0
+    for trial in range(400):
+        cam = [t + rng.uniform(-0.02, 0.02) for t in CANON_CAM]
+        cam[-1] -= rng.uniform(0, 0.03)
+        lid = [t + rng.uniform(-0.02, 0.02) for t in CANON_LIDAR]
+        tg = [t + rng.uniform(-0.02, 0.02) for t in CANON_TARGETS]
+        times = sorted(cam + lid)
+        sch = so.build_schedule(times, tg, 0.05, True)
+        micro = any(e.kind == "step" and e.dt < 1e-9 for e in sch.events)
+        gaps = sum(1 for a, b in zip(times[:-1], times[1:]) if b - a < 0.05)
+        keep = (micro and n_micro < 6) or (gaps >= 2 and n_gap < 4) or (not micro and n_plain < 6)
+        if not keep:
+            continue
+        n_micro += micro
+        n_gap += (gaps >= 2 and not micro)
+        n_plain += (not micro)
+        run_case(times, tg, True, "euler", f"jitter_{trial}{'_micro' if micro else ''}")
+    # a fixed-step case with jitter (many steps, window selection matters)
+    cam = [-1.003, -0.512, -0.004]
+    run_case(sorted(cam + [-0.79, -0.61, -0.4, -0.21, 0.0]), [-1.0, -0.5, 0.0, 0.26, 0.5, 0.74, 1.0], False, "euler",
+             "fixed_jitter")
+    with open(os.path.join(out_dir, "sched.json"), "w") as f:
+        json.dump(dict(generator="oracle/gen_golden.py::gen_schedules (reference NNFOwithBayesianJumps.forward traced)",
+                       cases=cases), f)
+    print(f"sched.json: {len(cases)} cases, {n_micro} with micro-steps")
+
+
+def gen_tiny_full(ref, out_dir):
+    C, H, B, seed, gain = 8, 16, 2, 11, 1.0
+    ct = torch.tensor([[-1.0, -0.5, 0.0], [-1.013, -0.492, -0.004]], dtype=torch.float64)
+    lt = torch.tensor([[-0.8, -0.6, -0.4, -0.2, 0.0], [-0.81, -0.6, -0.418, -0.2, 0.011]], dtype=torch.float64)
+    tt = torch.tensor([CANON_TARGETS, [-1.0, -0.5, 0.0, 0.49, 1.0, 1.52, 2.0]], dtype=torch.float64)
+    outs = {}
+    n_eps = None
+    for name, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+        m = ref.FuturePredictionODE(C, C, 4, ri.make_cfg(C)).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.to(dtype).load_state_dict(so.recipe_state_dict(shapes, seed, gain, dtype), strict=True)
+        cam = so.recipe_array("cam", (B, 3, C, H, H), seed, dtype)
+        lid = so.recipe_array("lidar", (B, 5, C, H, H), seed, dtype)
+        eps = [so.recipe_array(f"eps{i}", (1, C, H // 4, H // 4), seed, dtype) for i in range(64)]
+        with torch.no_grad(), ri.EpsTape(replay=eps) as tape:
+            x, aux = m(torch.zeros(B, 1, C, H, H, dtype=dtype), cam, lid, ct, lt, tt)
+        assert aux == 0
+        n_eps = len(tape.tape)
+        if name == "f64":
+            outs["x_f64"] = x.numpy()
+            x64 = x
+        else:
+            outs["ref_f32_x_err"] = float((x.double() - x64).abs().max() / x64.abs().max())
+        # B>1 == sequential B=1 on one noise stream
+        if name == "f64":
+            xs = []
+            with torch.no_grad(), ri.EpsTape(replay=eps):
+                for b in range(B):
+                    xs.append(m(torch.zeros(1, 1, C, H, H, dtype=dtype), cam[b:b + 1], lid[b:b + 1], ct[b:b + 1],
+                                lt[b:b + 1], tt[b:b + 1])[0])
+            assert torch.equal(torch.cat(xs, 0), x), "reference: batched != sequential"
+        if name == "f64":
+            outs["shapes_keys"] = np.array(list(shapes.keys()))
+            outs["shapes_vals"] = np.array([",".join(map(str, v)) for v in shapes.values()])
+    np.savez_compressed(os.path.join(out_dir, "tiny_full_c8.npz"), C=C, H=H, B=B, seed=seed, gain=gain, n_eps=n_eps,
+                        camera_timestamp=ct.numpy(), lidar_timestamp=lt.numpy(), target_timestamp=tt.numpy(), **outs)
+    print("tiny_full_c8.npz: x", outs["x_f64"].shape, "n_eps", n_eps)
+
+
+def gen_c64_latent(ref, out_dir):
+    C, H, seed, gain = 64, 32, 7, 1.0
+    canon = sorted(CANON_CAM + CANON_LIDAR)
+    variants = [
+        ("euler_var", "euler", True, True, canon, CANON_TARGETS),
+        ("midpoint_var", "midpoint", True, True, canon, [-1.0, 0.0, 0.5, 1.0]),
+        ("euler_fixed", "euler", False, True, CANON_CAM, [0.0, 0.25, 0.5]),
+        ("euler_var_noimpute", "euler", True, False, canon, [-0.5, 0.0, 1.0, 2.0]),
+        ("euler_var_jitter", "euler", True, True,
+         sorted([-1.013, -0.492, -0.004, -0.81, -0.6, -0.418, -0.2, 0.011]), [-1.0, -0.5, 0.0, 0.49, 1.0, 1.52, 2.0]),
+    ]
+    for tag, solver, variable, impute, times, targets in variants:
+        res = {}
+        for name, dtype in (("f64", torch.float64), ("f32", torch.float32)):
+            m, shapes = build_nnfo(ref, C, solver, variable, impute, seed, gain, dtype)
+            obs = so.recipe_array("obs", (1, len(times), C, H, H), seed, dtype)
+            eps = [so.recipe_array(f"eps{i}", (1, C, H // 4, H // 4), seed, dtype) for i in range(256)]
+            with torch.no_grad(), ri.EpsTape(replay=eps) as tape, Tracer(m) as tr:
+                state, loss, x = m(times=torch.tensor(times, dtype=torch.float64),
+                                   input=torch.zeros(1, 1, C, H, H, dtype=dtype), obs=obs, delta_t=0.05,
+                                   T=torch.tensor(targets, dtype=torch.float64))
+            assert loss == 0
+            if name == "f64":       # ground truth, stored as fp32 (6e-8 relative)
+                res["states_f64"] = torch.cat(tr.states, 0).to(torch.float32).numpy()
+                res["final_f64"] = state.to(torch.float32).numpy()
+                res["x_f64"] = x[:, [0, -1]].to(torch.float32).numpy()
+                st64, x64 = torch.cat(tr.states, 0), x
+            else:                   # the reference's own fp32 run: keep only its distance to fp64
+                res["ref_f32_state_err"] = float((torch.cat(tr.states, 0).double() - st64).abs().max() / st64.abs().max())
+                res["ref_f32_x_err"] = float((x.double() - x64).abs().max() / x64.abs().max())
+            if name == "f64":
+                res["selected"] = np.array(tr.selected_event_indices())
+                res["kinds"] = np.array([e[0] for e in tr.events])
+                res["dts"] = np.array([e[1] for e in tr.events])
+                res["n_eps"] = len(tape.tape)
+                res["encoded_f64"] = m.srvp_encoder(obs[0]).detach().to(torch.float32).numpy()
+        np.savez_compressed(os.path.join(out_dir, f"c64_latent_{tag}.npz"), C=C, H=H, seed=seed, gain=gain, solver=solver,
+                            variable=variable, impute=impute, times=np.array(times), targets=np.array(targets), **res)
+        print(f"c64_latent_{tag}.npz: events {len(res['kinds'])}, n_eps {res['n_eps']}, "
+              f"ref f32-vs-f64 state {res['ref_f32_state_err']:.2e} x {res['ref_f32_x_err']:.2e}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                  "tests", "golden"))
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = ri.import_reference()
+    gen_schedules(ref, args.out)
+    gen_tiny_full(ref, args.out)
+    gen_c64_latent(ref, args.out)
+
+
+if __name__ == "__main__":
+    main()
