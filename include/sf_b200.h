@@ -1,0 +1,155 @@
+/*
+ * sf_b200.h -- C ABI of libsf_b200.so: the B200 (sm_100a) implementation of StreamingFlow's
+ * GRU-ODE-Bayes BEV integration path.
+ *
+ * The reference has NO native code on this path: every FLOP is a torch.nn call made from Python
+ *   streamingflow/layers/temporal_ode_bayes.py:92-161   DualGRUODECell.forward  (derivative)
+ *   streamingflow/layers/temporal_ode_bayes.py:239-305  DualGRUCell.forward     (observation jump)
+ *   streamingflow/layers/temporal_ode_bayes.py:436-477  ode_step / infer_state
+ *   streamingflow/layers/res_models.py:150-180          SELayer / ConvNet (= p_model)
+ *   streamingflow/layers/convolutions.py:283-380        LayerNorm(channels_first) / Bottleblock
+ * so the "FFI" a maintainer binds is this header, loaded with ctypes from the Python module that
+ * keeps the reference's nn.Module interface.  Plain pointers and sizes only; no
+ * torch types cross this boundary.  All device pointers are owned by the caller (torch allocator);
+ * the library allocates no persistent device memory.  Every call returns 0 on success or a negative
+ * sf_status; sf_last_error() gives the message for the calling thread's last failure.
+ *
+ * Data layout: every activation is NHWC ("pixel-major"): [image][y][x][channel], channel fastest,
+ * stored as bf16 (optionally a second bf16 plane holding the rounding residual: split mode).
+ * The master copy of the ODE state and the two GRU branch outputs stay fp32 NHWC.
+ */
+#ifndef SF_B200_H_
+#define SF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SF_ABI_VERSION 1
+
+typedef enum {
+  SF_OK = 0,
+  SF_ERR_INVALID = -1,      /* bad argument / unsupported shape  (reference: Python assert, temporal_ode_bayes.py:101,249,386) */
+  SF_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+  SF_ERR_STATE = -3,        /* plan not finalised, buffer not bound, ... */
+  SF_ERR_UNSUPPORTED = -4   /* device is not sm_100 */
+} sf_status;
+
+/* precision modes of the tensor-core operands (accumulation is always fp32 in TMEM) */
+#define SF_PREC_BF16 0      /* bf16 operands: rel 1e-2 contract                              */
+#define SF_PREC_BF16X3 1    /* hi/lo split bf16, 3 products: fp32-class, rel 1e-4 contract   */
+
+/* fused epilogues (one per conv stage of an event; SURVEY.md 7.4 kernel map) */
+typedef enum {
+  SF_EPI_GATES = 0,     /* sigmoid gates: writes u1,u2,(1-r1)*s,(1-r2)*s            temporal_ode_bayes.py:135-140,150-155 */
+  SF_EPI_PROPOSE = 1,   /* proposal + GRU blend: a = (1-u1)s+u1*s~1, h = (1-u2)s+u2*s~2          :143-146,158-161 */
+  SF_EPI_DECODE = 2,    /* b = conv_decoder_2(h) + bias                                            :121 */
+  SF_EPI_LNGELU = 3,    /* LayerNorm(C)+GELU (7x7 trunk conv, then the 1x1)                 convolutions.py:356-361 */
+  SF_EPI_MIX = 4,       /* LN+GELU, +GELU(proj), 1x1->2, softmax, mix, Euler / jump update   :362-380, tob:124-131,446 */
+  SF_EPI_BIAS_LRELU = 5,/* folded-BN bias + LeakyReLU(0.1)                                   res_models.py:42-49 */
+  SF_EPI_RES_PROJ = 6,  /* LReLU(acc0+b0) + (acc1+b1): ResBlock with 1x1 projection           res_models.py:75-79 */
+  SF_EPI_RES_ID = 7,    /* LReLU(acc+b) + residual input                                      res_models.py:79 */
+  SF_EPI_SAMPLE = 8     /* bias+LReLU, loc/raw split, loc + (softplus(raw)+1e-8)*eps           model_utils.py:81-85,107-108 */
+} sf_epilogue;
+
+/* One K-chunk of an implicit-GEMM stage: 64 input channels of one activation buffer, all RxR taps. */
+typedef struct {
+  int32_t buf;      /* activation buffer id (see sf_plan_bind_act); -1 = the event's x source            */
+  int32_t plane;    /* 0 = hi plane, 1 = lo (residual) plane                                             */
+  int32_t c0;       /* first channel of the chunk inside the buffer                                       */
+  int32_t R;        /* filter taps per side: 1, 3 or 7 (zero padding (R-1)/2)                             */
+  int32_t n;        /* output channels accumulated by this chunk (multiple of 64, <= 256)                 */
+  int32_t nrep;     /* weight tiles per tap applied to the same A tile and the same columns (1 or 2)      */
+  int32_t col;      /* first TMEM accumulator column                                                      */
+  int32_t wrow;     /* first row of this chunk in the packed weight matrix; tap (dx,dy) rep r starts at
+                       wrow + ((dx*R+dy)*nrep + r)*n                                                     */
+  int32_t init;     /* 1: the chunk's first MMA overwrites its columns instead of accumulating           */
+} sf_chunk;
+
+#define SF_MAX_CHUNKS 12
+#define SF_MAX_ACT_BUFS 32
+#define SF_MAX_STAGES 32
+
+typedef struct {
+  int32_t max_images;   /* capacity (samples) of the per-sample buffers                                  */
+  int32_t H, W;         /* ODE grid (latent) height / width                                               */
+  int32_t C;            /* hidden channels (64)                                                           */
+  int32_t precision;    /* SF_PREC_*                                                                      */
+  int32_t device;       /* CUDA device ordinal                                                            */
+} sf_geometry;
+
+/* fp32 side tensors, all NHWC [image][H][W][C] unless noted */
+typedef enum {
+  SF_F32_STATE0 = 0,    /* master ODE state, buffer 0                                                     */
+  SF_F32_STATE1 = 1,    /* second state buffer (midpoint stage k)                                         */
+  SF_F32_A = 2,         /* rnn_state1 (GRU-1 output)                                                      */
+  SF_F32_B = 3,         /* rnn_state2 (decoder of GRU-2)                                                  */
+  SF_F32_PATH = 4,      /* recorded states [slot][H][W][C]                                                */
+  SF_F32_SE_SUMS = 5,   /* [2][max_images][2C] channel sums for the two SE layers                         */
+  SF_F32_EPS = 6,       /* standard-normal noise, NCHW [slot][C][H][W] (torch's generation order)         */
+  SF_F32_X = 7,         /* optional fp32 copy of the sampled input x  (infer_state API)                   */
+  SF_F32_PARAMS = 8,    /* optional fp32 p_model output [image][H][W][2C] (infer_state API)               */
+  SF_F32_COUNT = 9
+} sf_f32_slot;
+
+/* One event = one pass of {cell stages} + optional {prior-network stages} over the listed samples. */
+typedef struct {
+  int32_t kind;          /* 0: ODE derivative step with the gru_c weights; 1: observation jump (gru_obs)  */
+  int32_t n_active;      /* samples taking part                                                           */
+  int32_t x_buf;         /* activation buffer holding the cell's x input (sampled input or encoded obs)    */
+  int32_t s_in;          /* state buffer (0/1) the cell reads                                              */
+  int32_t s_base;        /* state buffer the Euler update starts from (== s_in except midpoint stage 2)    */
+  int32_t s_out;         /* state buffer the new state is written to                                       */
+  int32_t run_cell;      /* 0 skips the cell stages (infer_state-only call)                                */
+  int32_t run_prior;     /* 1 runs p_model + sampling on s_out and refreshes the x buffer                  */
+  int32_t want_f32;      /* 1 also writes SF_F32_X / SF_F32_PARAMS                                         */
+  int32_t table_off;     /* offset (int32 elements) of this event's rows in the device event table:
+                            5 rows of n_active: sample id, x image index, record slot (-1 none),
+                            eps slot, dt (float bits)                                                      */
+} sf_event;
+
+typedef struct sf_plan sf_plan;
+
+int sf_abi_version(void);
+const char* sf_last_error(void);
+/* returns SF_OK when the current device can run the library (compute capability 10.x) */
+int sf_device_supported(int device);
+
+int sf_plan_create(const sf_geometry* g, sf_plan** out);
+int sf_plan_destroy(sf_plan* p);
+/* activation buffer: bf16 NHWC [n_images][H][W][channels]; lo may be NULL unless precision is BF16X3 */
+int sf_plan_bind_act(sf_plan* p, int buf, void* hi, void* lo, int channels, int n_images);
+int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
+/* packed weights: bf16 [w_rows][64] device pointer; vec: fp32 device pointer (bias / LN / gate weights) */
+int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
+                         const void* w_packed, int w_rows, const float* vec, int n_vec,
+                         const int32_t* io_bufs, int n_io);
+/* SE layer weights (fp32 device): fc1 [2C/8][2C], fc2 [2C][2C/8] for the two SE layers */
+int sf_plan_define_se(sf_plan* p, int which, const float* fc1, const float* fc2, int in_buf, int out_buf);
+/* stage slots used by an event: cell stages for kind 0 / kind 1, then the prior-network stages */
+int sf_plan_define_event_graph(sf_plan* p, const int32_t* cell0, const int32_t* cell1, int n_cell,
+                               const int32_t* prior, int n_prior);
+int sf_plan_finalize(sf_plan* p);
+int sf_plan_smem_bytes(sf_plan* p, int stage);
+
+/* runs ONE stage (unit tests / profiling); table points at the event's rows in device memory */
+int sf_plan_run_stage(sf_plan* p, int stage, const sf_event* ev, const int32_t* table, void* stream);
+int sf_plan_run_events(sf_plan* p, const sf_event* evs, int n_events, const int32_t* table, void* stream);
+/* number of kernels the last sf_plan_run_events call launched */
+int sf_plan_last_launches(sf_plan* p);
+
+/* layout kernels (HBM-bound, 128-bit vectorised) */
+int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);
+int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n_out, int C, int H, int W, void* stream);
+
+/* self-test kernels for bring-up: TMA tile dump and a single UMMA tile product */
+int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0,
+                     int rows, void* out_smem_copy, void* stream);
+int sf_diag_umma(const void* a_bf16, const void* b_bf16, float* d, int n, int k_chunks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SF_B200_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of libsf_b200.so (the C ABI in include/sf_b200.h).
+
+There is no fallback: if the shared library is missing or the device is not a B200, every entry point
+raises.  Build it with ``python -m streamingflow_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsf_b200.so")
+
+SF_ABI_VERSION = 1
+PREC_BF16, PREC_BF16X3 = 0, 1
+(EPI_GATES, EPI_PROPOSE, EPI_DECODE, EPI_LNGELU, EPI_MIX, EPI_BIAS_LRELU, EPI_RES_PROJ, EPI_RES_ID, EPI_SAMPLE) = range(9)
+(F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG) = range(10)
+SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
+SE_ITEM_BASE = 1000
+
+
+class Chunk(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("buf", "plane", "c0", "R", "n", "nrep", "col", "wrow", "init")]
+
+
+class Geometry(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("max_images", "H", "W", "C", "precision", "device")]
+
+
+class Event(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "n_active", "x_buf", "s_in", "s_base", "s_out", "run_cell", "run_prior",
+                                         "want_f32", "table_off")]
+
+
+EXPORTS = {
+    "sf_abi_version": (C.c_int, []),
+    "sf_last_error": (C.c_char_p, []),
+    "sf_device_supported": (C.c_int, [C.c_int]),
+    "sf_plan_create": (C.c_int, [C.POINTER(Geometry), C.POINTER(C.c_void_p)]),
+    "sf_plan_destroy": (C.c_int, [C.c_void_p]),
+    "sf_plan_bind_act": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sf_plan_bind_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "sf_plan_define_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Chunk), C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "sf_plan_define_se": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sf_plan_define_event_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                                             C.POINTER(C.c_int32), C.c_int]),
+    "sf_plan_finalize": (C.c_int, [C.c_void_p]),
+    "sf_plan_smem_bytes": (C.c_int, [C.c_void_p, C.c_int]),
+    "sf_plan_run_stage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_void_p]),
+    "sf_plan_run_events": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_plan_last_launches": (C.c_int, [C.c_void_p]),
+    "sf_pack_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
+    "sf_diag_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+class SfError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once and types every export; raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SfError(f"{LIB_PATH} not found: the CUDA library is not built (python -m streamingflow_b200.build). "
+                      "streamingflow_b200 has no CPU / PyTorch fallback for the ODE path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.sf_abi_version() != SF_ABI_VERSION:
+        raise SfError("libsf_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc < 0:
+        msg = load().sf_last_error()
+        raise SfError(f"{what}: {msg.decode() if msg else rc}")
+    return rc

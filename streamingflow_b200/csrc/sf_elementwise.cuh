@@ -1,0 +1,159 @@
+// sf_elementwise.cuh -- the HBM-bound kernels of the path: squeeze-excite reduce / apply
+// (res_models.py:150-165) and the NCHW fp32 <-> NHWC bf16 layout kernels. 128-bit accesses throughout.
+#pragma once
+#include "sf_ptx.cuh"
+
+namespace sf {
+
+// ---- SE step 1: per-(sample, channel) sums over the H*W pixels of a [img][H*W][CH] bf16 tensor --------
+// grid = (blocks_per_image, n_active); block = 256 threads = 16 channel groups (8 ch = 16 B) x 16 pixel lanes.
+template <int CH, bool X3>
+__global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
+                                                        float* __restrict__ sums, const int* __restrict__ sample_id, int hw) {
+  static_assert(CH == 128, "SE layers of the prior network have 2C = 128 channels");
+  constexpr int GROUPS = CH / 8;            // 16
+  constexpr int LANES = 256 / GROUPS;       // 16 pixels in flight per block iteration
+  const int bi = blockIdx.y;
+  const int sid = sample_id[bi];
+  const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS;
+  const size_t base = (size_t)sid * hw * CH;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int px = blockIdx.x * LANES + pl; px < hw; px += gridDim.x * LANES) {
+    const uint4 v = *reinterpret_cast<const uint4*>(zh + base + (size_t)px * CH + g * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(w[i]); acc[2 * i + 1] += bf16_hi_f(w[i]); }
+    if (X3) {
+      const uint4 u = *reinterpret_cast<const uint4*>(zl + base + (size_t)px * CH + g * 8);
+      const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(x[i]); acc[2 * i + 1] += bf16_hi_f(x[i]); }
+    }
+  }
+  __shared__ float red[LANES][CH + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[pl][g * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < LANES; ++l) s += red[l][threadIdx.x];
+    atomicAdd(sums + (size_t)bi * CH + threadIdx.x, s);
+  }
+}
+
+// ---- SE step 2: scale = sigmoid(fc2 * relu(fc1 * mean)); y = z * scale ---------------------------------
+// every block recomputes the 2 tiny FCs (128x16 each) for its sample, then streams its share of pixels.
+template <int CH, bool X3>
+__global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
+                                                       __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
+                                                       const float* __restrict__ sums, const float* __restrict__ fc1,
+                                                       const float* __restrict__ fc2, const int* __restrict__ sample_id, int hw) {
+  constexpr int HID = CH / 8;               // reduction 8
+  constexpr int GROUPS = CH / 8;
+  constexpr int LANES = 256 / GROUPS;
+  __shared__ float mean_s[CH], hid_s[HID], scale_s[CH];
+  const int bi = blockIdx.y;
+  const int sid = sample_id[bi];
+  if (threadIdx.x < CH) mean_s[threadIdx.x] = sums[(size_t)bi * CH + threadIdx.x] / (float)hw;
+  __syncthreads();
+  if (threadIdx.x < HID) {
+    float a = 0.0f;
+    for (int c = 0; c < CH; ++c) a = fmaf(fc1[threadIdx.x * CH + c], mean_s[c], a);
+    hid_s[threadIdx.x] = fmaxf(a, 0.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    float a = 0.0f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) a = fmaf(fc2[threadIdx.x * HID + j], hid_s[j], a);
+    scale_s[threadIdx.x] = 1.0f / (1.0f + __expf(-a));
+  }
+  __syncthreads();
+  const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS;
+  const size_t base = (size_t)sid * hw * CH;
+  float sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sc[i] = scale_s[g * 8 + i];
+  for (int px = blockIdx.x * LANES + pl; px < hw; px += gridDim.x * LANES) {
+    const size_t off = base + (size_t)px * CH + g * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(zh + off);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo_f(w[i]); f[2 * i + 1] = bf16_hi_f(w[i]); }
+    if (X3) {
+      const uint4 u = *reinterpret_cast<const uint4*>(zl + off);
+      const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { f[2 * i] += bf16_lo_f(x[i]); f[2 * i + 1] += bf16_hi_f(x[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= sc[i];
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(yh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
+      *reinterpret_cast<uint4*>(yl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---- NCHW fp32 -> NHWC bf16 (hi [+ lo]) : encoded observations entering the ODE loop ---------------------
+// block = 256 threads handles 32 consecutive pixels x 64 channels of one image through a padded smem tile.
+template <bool X3>
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dh,
+                                                        __nv_bfloat16* __restrict__ dl, int C, int hw) {
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, cb = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = w; c < 64; c += 8) {
+    const int px = p0 + lane;
+    tile[c][lane] = (px < hw) ? src[((size_t)img * C + cb + c) * hw + px] : 0.0f;
+  }
+  __syncthreads();
+  // 32 pixels x 8 groups of 8 channels = 256 work items
+  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
+  if (p0 + px < hw) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = tile[g * 8 + i][px];
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    const size_t off = ((size_t)img * hw + p0 + px) * C + cb + g * 8;
+    *reinterpret_cast<uint4*>(dh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
+      *reinterpret_cast<uint4*>(dl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---- NHWC fp32 (recorded path states) -> NCHW fp32 (decoder input), gathered by slot ----------------------
+__global__ void __launch_bounds__(256) unpack_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          const int* __restrict__ slots, int C, int hw) {
+  __shared__ float tile[32][65];
+  const int o = blockIdx.z, cb = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int slot = slots ? slots[o] : o;
+  // read: 32 pixels x 64 channels, 16 float4 per pixel
+  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
+  if (p0 + px < hw) {
+    const float4* q = reinterpret_cast<const float4*>(src + ((size_t)slot * hw + p0 + px) * C + cb + g * 8);
+    const float4 a = q[0], b = q[1];
+    float* t = &tile[px][g * 8];
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = w; c < 64; c += 8)
+    if (p0 + lane < hw) dst[((size_t)o * C + cb + c) * hw + p0 + lane] = tile[lane][c];
+}
+
+}  // namespace sf

@@ -1,0 +1,475 @@
+// sf_plan.cu -- host side of libsf_b200.so: the plan object (buffer bindings, stage definitions, TMA
+// descriptors), kernel launches and the extern "C" ABI declared in include/sf_b200.h.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "sf_conv.cuh"
+#include "sf_elementwise.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define SF_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(SF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct ActBuf {
+  void* hi = nullptr;
+  void* lo = nullptr;
+  int channels = 0;
+  int n_images = 0;
+};
+struct Stage {
+  bool defined = false;
+  int epi = 0;
+  std::vector<sf_chunk> chunks;
+  const void* w = nullptr;
+  int w_rows = 0;
+  const float* vec = nullptr;
+  int n_vec = 0;
+  std::vector<int> io;
+  CUtensorMap wmap;
+  int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
+};
+struct SeDef {
+  bool defined = false;
+  const float* fc1 = nullptr;
+  const float* fc2 = nullptr;
+  int in_buf = -1, out_buf = -1;
+};
+
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int BAR_AREA = 512;
+
+}  // namespace
+
+struct sf_plan {
+  sf_geometry g;
+  int num_sms = 148;
+  bool finalized = false;
+  ActBuf act[SF_MAX_ACT_BUFS];
+  void* f32[SF_F32_COUNT + 1] = {};
+  Stage stage[SF_MAX_STAGES];
+  SeDef se[2];
+  std::vector<int> cell[2], prior;
+  std::map<std::tuple<int, int, int>, CUtensorMap> amaps;   // (buf, plane, R) -> activation tensor map
+  int last_launches = 0;
+};
+
+namespace {
+
+using namespace sf;
+
+int encode_act_map(sf_plan* p, int buf, int plane, int R, CUtensorMap* out) {
+  auto key = std::make_tuple(buf, plane, R);
+  auto it = p->amaps.find(key);
+  if (it != p->amaps.end()) {
+    *out = it->second;
+    return SF_OK;
+  }
+  if (buf < 0 || buf >= SF_MAX_ACT_BUFS) return fail(SF_ERR_INVALID, "activation buffer id out of range");
+  const ActBuf& a = p->act[buf];
+  void* base = plane ? a.lo : a.hi;
+  if (!base) return fail(SF_ERR_STATE, "activation buffer " + std::to_string(buf) + " plane " + std::to_string(plane) + " not bound");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(SF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t C = a.channels, W = p->g.W, H = p->g.H, N = a.n_images;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TILE_W, (cuuint32_t)(TILE_H + R - 1), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SF_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+  p->amaps[key] = m;
+  *out = m;
+  return SF_OK;
+}
+
+int encode_weight_map(const void* w, int rows, CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(SF_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KC, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SF_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+  return SF_OK;
+}
+
+typedef void (*StageKernel)(const StageParams);
+template <bool X3>
+StageKernel kernel_for(int epi) {
+  switch (epi) {
+    case SF_EPI_GATES: return conv_stage_kernel<SF_EPI_GATES, X3>;
+    case SF_EPI_PROPOSE: return conv_stage_kernel<SF_EPI_PROPOSE, X3>;
+    case SF_EPI_DECODE: return conv_stage_kernel<SF_EPI_DECODE, X3>;
+    case SF_EPI_LNGELU: return conv_stage_kernel<SF_EPI_LNGELU, X3>;
+    case SF_EPI_MIX: return conv_stage_kernel<SF_EPI_MIX, X3>;
+    case SF_EPI_BIAS_LRELU: return conv_stage_kernel<SF_EPI_BIAS_LRELU, X3>;
+    case SF_EPI_RES_PROJ: return conv_stage_kernel<SF_EPI_RES_PROJ, X3>;
+    case SF_EPI_RES_ID: return conv_stage_kernel<SF_EPI_RES_ID, X3>;
+    case SF_EPI_SAMPLE: return conv_stage_kernel<SF_EPI_SAMPLE, X3>;
+  }
+  return nullptr;
+}
+StageKernel kernel_for(int epi, bool x3) { return x3 ? kernel_for<true>(epi) : kernel_for<false>(epi); }
+
+int state_act_buf(int which) { return which; }   // activation buffers 0 and 1 mirror fp32 state buffers 0 and 1
+
+int resolve_buf(const sf_event* ev, int buf) {
+  if (buf == -1) return ev->x_buf;
+  if (buf == -2) return state_act_buf(ev->s_in);
+  if (buf == -3) return state_act_buf(ev->s_out);
+  return buf;
+}
+
+int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  if (sidx < 0 || sidx >= SF_MAX_STAGES || !p->stage[sidx].defined) return fail(SF_ERR_STATE, "stage not defined");
+  if (ev->n_active <= 0) return SF_OK;
+  Stage& st = p->stage[sidx];
+  const bool x3 = p->g.precision == SF_PREC_BF16X3;
+  StageParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.nchunk = (int)st.chunks.size();
+  for (int c = 0; c < sp.nchunk; ++c) {
+    const sf_chunk& ck = st.chunks[c];
+    const int buf = resolve_buf(ev, ck.buf);
+    int rc = encode_act_map(p, buf, ck.plane, ck.R, &sp.amap[c]);
+    if (rc) return rc;
+    if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
+    sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0};
+  }
+  sp.wmap = st.wmap;
+  sp.H = p->g.H;
+  sp.W = p->g.W;
+  sp.tiles_x = (p->g.W + TILE_W - 1) / TILE_W;
+  sp.tiles_y = (p->g.H + TILE_H - 1) / TILE_H;
+  sp.n_active = ev->n_active;
+  const int n = ev->n_active;
+  const int32_t* rows = table + ev->table_off;
+  sp.sample_id = rows;
+  sp.x_img = rows + n;
+  sp.rec_slot = rows + 2 * n;
+  sp.eps_slot = rows + 3 * n;
+  sp.dt = reinterpret_cast<const float*>(rows + 4 * n);
+  sp.vec = st.vec;
+  sp.nvec = st.n_vec;
+  sp.a_slot_bytes = st.a_slot;
+  sp.b_slot_bytes = st.b_slot;
+  sp.nA = st.nA;
+  sp.nB = st.nB;
+  sp.acc_stages = 2;
+  sp.err = reinterpret_cast<int*>(p->f32[SF_F32_COUNT]);
+  EpiArgs& e = sp.e;
+  e.kind = ev->kind;
+  e.s_in = reinterpret_cast<const float*>(p->f32[SF_F32_STATE0 + ev->s_in]);
+  e.s_base = reinterpret_cast<const float*>(p->f32[SF_F32_STATE0 + ev->s_base]);
+  e.s_out = reinterpret_cast<float*>(p->f32[SF_F32_STATE0 + ev->s_out]);
+  e.a32 = reinterpret_cast<float*>(p->f32[SF_F32_A]);
+  e.b32 = reinterpret_cast<float*>(p->f32[SF_F32_B]);
+  e.path = reinterpret_cast<float*>(p->f32[SF_F32_PATH]);
+  e.eps = reinterpret_cast<const float*>(p->f32[SF_F32_EPS]);
+  e.x32 = ev->want_f32 ? reinterpret_cast<float*>(p->f32[SF_F32_X]) : nullptr;
+  e.params32 = ev->want_f32 ? reinterpret_cast<float*>(p->f32[SF_F32_PARAMS]) : nullptr;
+  auto out = [&](int slot, int buf) {
+    e.out_h[slot] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].hi);
+    e.out_l[slot] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].lo);
+  };
+  auto in = [&](int slot, int buf) {
+    e.in_h[slot] = reinterpret_cast<const __nv_bfloat16*>(p->act[buf].hi);
+    e.in_l[slot] = reinterpret_cast<const __nv_bfloat16*>(p->act[buf].lo);
+  };
+  auto need_io = [&](size_t k) { return st.io.size() >= k; };
+  for (int b : st.io)
+    if (b < 0 || b >= SF_MAX_ACT_BUFS || !p->act[b].hi || (x3 && !p->act[b].lo))
+      return fail(SF_ERR_STATE, "stage io buffer not bound");
+  switch (st.epi) {
+    case SF_EPI_GATES:
+      if (!need_io(4)) return fail(SF_ERR_INVALID, "gates stage needs 4 io buffers");
+      for (int i = 0; i < 4; ++i) out(i, st.io[i]);
+      break;
+    case SF_EPI_PROPOSE:
+      if (!need_io(4)) return fail(SF_ERR_INVALID, "propose stage needs 4 io buffers");
+      in(0, st.io[0]); in(1, st.io[1]); out(0, st.io[2]); out(1, st.io[3]);
+      break;
+    case SF_EPI_MIX:
+      out(0, state_act_buf(ev->s_out));
+      break;
+    case SF_EPI_RES_ID:
+      if (!need_io(2)) return fail(SF_ERR_INVALID, "residual stage needs 2 io buffers");
+      in(0, st.io[0]); out(0, st.io[1]);
+      e.n_out = p->act[st.io[1]].channels;
+      break;
+    default:
+      if (!need_io(1)) return fail(SF_ERR_INVALID, "stage needs an output buffer");
+      out(0, st.io[0]);
+      e.n_out = p->act[st.io[0]].channels;
+      break;
+  }
+  if (st.epi == SF_EPI_MIX || st.epi == SF_EPI_GATES || st.epi == SF_EPI_PROPOSE)
+    if (!e.s_in || !e.s_out || !e.s_base) return fail(SF_ERR_STATE, "state buffers not bound");
+  if (st.epi == SF_EPI_SAMPLE && !e.eps) return fail(SF_ERR_STATE, "eps buffer not bound");
+  const int ntiles = n * sp.tiles_x * sp.tiles_y;
+  const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
+  StageKernel k = kernel_for(st.epi, x3);
+  if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
+  void* args[] = {&sp};
+  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(256), args, (size_t)st.smem, stream));
+  p->last_launches += 1;
+  return SF_OK;
+}
+
+int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  const SeDef& se = p->se[which];
+  if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
+  if (ev->n_active <= 0) return SF_OK;
+  const bool x3 = p->g.precision == SF_PREC_BF16X3;
+  const int CH = 2 * p->g.C;
+  const int hw = p->g.H * p->g.W;
+  float* sums = reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]);
+  if (!sums) return fail(SF_ERR_STATE, "SE sums buffer not bound");
+  sums += (size_t)which * p->g.max_images * CH;
+  const ActBuf& zi = p->act[se.in_buf];
+  const ActBuf& yo = p->act[se.out_buf];
+  if (!zi.hi || !yo.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
+  const int* sid = table + ev->table_off;
+  SF_CUDA(cudaMemsetAsync(sums, 0, (size_t)ev->n_active * CH * sizeof(float), stream));
+  int bpi = (hw + 16 * 8 - 1) / (16 * 8);     // ~8 pixels per thread-lane
+  if (bpi > 64) bpi = 64;
+  if (bpi < 1) bpi = 1;
+  dim3 grid(bpi, ev->n_active);
+  auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
+  auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
+  auto yh = reinterpret_cast<__nv_bfloat16*>(yo.hi);
+  auto yl = reinterpret_cast<__nv_bfloat16*>(yo.lo);
+  int bpa = (hw + 16 * 4 - 1) / (16 * 4);
+  if (bpa > 296) bpa = 296;
+  if (bpa < 1) bpa = 1;
+  dim3 grid2(bpa, ev->n_active);
+  if (x3) {
+    se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
+    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, se.fc1, se.fc2, sid, hw);
+  } else {
+    se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
+    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, se.fc1, se.fc2, sid, hw);
+  }
+  SF_CUDA(cudaGetLastError());
+  p->last_launches += 2;
+  return SF_OK;
+}
+
+int run_item(sf_plan* p, int item, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  if (item >= 1000) return launch_se(p, item - 1000, ev, table, stream);
+  return launch_stage(p, item, ev, table, stream);
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C" ABI
+// ================================================================================================
+extern "C" {
+
+int sf_abi_version(void) { return SF_ABI_VERSION; }
+const char* sf_last_error(void) { return g_err.c_str(); }
+
+int sf_device_supported(int device) {
+  cudaDeviceProp prop;
+  SF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SF_ERR_UNSUPPORTED, "libsf_b200 needs an sm_100 (Blackwell B200) device, found sm_" +
+                                                            std::to_string(prop.major) + std::to_string(prop.minor));
+  return SF_OK;
+}
+
+int sf_plan_create(const sf_geometry* g, sf_plan** out) {
+  if (!g || !out) return fail(SF_ERR_INVALID, "null argument");
+  if (g->C != 64) return fail(SF_ERR_INVALID, "only C = 64 hidden channels is built (got " + std::to_string(g->C) + ")");
+  if (g->H <= 0 || g->W <= 0 || g->max_images <= 0) return fail(SF_ERR_INVALID, "bad geometry");
+  if (g->precision != SF_PREC_BF16 && g->precision != SF_PREC_BF16X3) return fail(SF_ERR_INVALID, "bad precision mode");
+  int rc = sf_device_supported(g->device);
+  if (rc) return rc;
+  SF_CUDA(cudaSetDevice(g->device));
+  sf_plan* p = new sf_plan();
+  p->g = *g;
+  cudaDeviceProp prop;
+  SF_CUDA(cudaGetDeviceProperties(&prop, g->device));
+  p->num_sms = prop.multiProcessorCount;
+  *out = p;
+  return SF_OK;
+}
+
+int sf_plan_destroy(sf_plan* p) {
+  delete p;
+  return SF_OK;
+}
+
+int sf_plan_bind_act(sf_plan* p, int buf, void* hi, void* lo, int channels, int n_images) {
+  if (!p || buf < 0 || buf >= SF_MAX_ACT_BUFS) return fail(SF_ERR_INVALID, "bad activation buffer id");
+  if (channels % KC != 0 || channels <= 0) return fail(SF_ERR_INVALID, "activation channels must be a multiple of 64");
+  if ((reinterpret_cast<uintptr_t>(hi) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15)) return fail(SF_ERR_INVALID, "activation buffers must be 16-byte aligned");
+  p->act[buf] = ActBuf{hi, lo, channels, n_images};
+  for (auto it = p->amaps.begin(); it != p->amaps.end();)
+    it = (std::get<0>(it->first) == buf) ? p->amaps.erase(it) : std::next(it);
+  return SF_OK;
+}
+
+int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr) {
+  if (!p || slot < 0 || slot > SF_F32_COUNT) return fail(SF_ERR_INVALID, "bad fp32 slot");   // slot SF_F32_COUNT = int32 error flag
+  p->f32[slot] = ptr;
+  return SF_OK;
+}
+
+int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks, const void* w_packed,
+                         int w_rows, const float* vec, int n_vec, const int32_t* io_bufs, int n_io) {
+  if (!p || stage < 0 || stage >= SF_MAX_STAGES) return fail(SF_ERR_INVALID, "bad stage id");
+  if (n_chunks <= 0 || n_chunks > SF_MAX_CHUNKS) return fail(SF_ERR_INVALID, "bad chunk count");
+  if (n_vec > sf::VEC_MAX) return fail(SF_ERR_INVALID, "stage vector too long");
+  Stage& st = p->stage[stage];
+  st = Stage();
+  st.epi = epilogue;
+  st.chunks.assign(chunks, chunks + n_chunks);
+  int a_slot = 0, b_slot = 0;
+  for (const sf_chunk& c : st.chunks) {
+    if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
+    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::ACC_STAGE_COLS) return fail(SF_ERR_INVALID, "bad chunk N / column range");
+    if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
+    if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
+    const int a = (TILE_H + c.R - 1) * TILE_W * ROW_BYTES, b = c.n * c.nrep * ROW_BYTES;
+    a_slot = a > a_slot ? a : a_slot;
+    b_slot = b > b_slot ? b : b_slot;
+  }
+  st.w = w_packed;
+  st.w_rows = w_rows;
+  st.vec = vec;
+  st.n_vec = n_vec;
+  st.io.assign(io_bufs, io_bufs + n_io);
+  const int fixed = 1024 + sf::VEC_MAX * 4 + BAR_AREA;
+  int nA = 3;
+  int nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
+  if (nB < 2) { nA = 2; nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot; }
+  if (nB > 8) nB = 8;
+  if (nB < 2) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
+  st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
+  st.smem = fixed + nA * a_slot + nB * b_slot;
+  int rc = encode_weight_map(w_packed, w_rows, &st.wmap);
+  if (rc) return rc;
+  st.defined = true;
+  p->finalized = false;
+  return SF_OK;
+}
+
+int sf_plan_define_se(sf_plan* p, int which, const float* fc1, const float* fc2, int in_buf, int out_buf) {
+  if (!p || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad SE index");
+  p->se[which] = SeDef{true, fc1, fc2, in_buf, out_buf};
+  return SF_OK;
+}
+
+int sf_plan_define_event_graph(sf_plan* p, const int32_t* cell0, const int32_t* cell1, int n_cell, const int32_t* prior, int n_prior) {
+  if (!p) return fail(SF_ERR_INVALID, "null plan");
+  p->cell[0].assign(cell0, cell0 + n_cell);
+  p->cell[1].assign(cell1, cell1 + n_cell);
+  p->prior.assign(prior, prior + n_prior);
+  return SF_OK;
+}
+
+int sf_plan_finalize(sf_plan* p) {
+  if (!p) return fail(SF_ERR_INVALID, "null plan");
+  int max_smem = 0;
+  for (const Stage& st : p->stage)
+    if (st.defined && st.smem > max_smem) max_smem = st.smem;
+  for (int epi = 0; epi <= SF_EPI_SAMPLE; ++epi)
+    for (int x3 = 0; x3 < 2; ++x3)
+      SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel_for(epi, x3 != 0)), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+  p->finalized = true;
+  return SF_OK;
+}
+
+int sf_plan_smem_bytes(sf_plan* p, int stage) {
+  if (!p || stage < 0 || stage >= SF_MAX_STAGES || !p->stage[stage].defined) return fail(SF_ERR_INVALID, "bad stage");
+  return p->stage[stage].smem;
+}
+
+int sf_plan_run_stage(sf_plan* p, int stage, const sf_event* ev, const int32_t* table, void* stream) {
+  if (!p || !ev || !table) return fail(SF_ERR_INVALID, "null argument");
+  if (!p->finalized) return fail(SF_ERR_STATE, "plan not finalised");
+  return run_item(p, stage, ev, table, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sf_plan_run_events(sf_plan* p, const sf_event* evs, int n_events, const int32_t* table, void* stream) {
+  if (!p || !evs || !table) return fail(SF_ERR_INVALID, "null argument");
+  if (!p->finalized) return fail(SF_ERR_STATE, "plan not finalised");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  p->last_launches = 0;
+  for (int i = 0; i < n_events; ++i) {
+    const sf_event* ev = evs + i;
+    if (ev->kind < 0 || ev->kind > 1) return fail(SF_ERR_INVALID, "bad event kind");
+    if (ev->run_cell)
+      for (int item : p->cell[ev->kind]) {
+        int rc = run_item(p, item, ev, table, s);
+        if (rc) return rc;
+      }
+    if (ev->run_prior)
+      for (int item : p->prior) {
+        int rc = run_item(p, item, ev, table, s);
+        if (rc) return rc;
+      }
+  }
+  return SF_OK;
+}
+
+int sf_plan_last_launches(sf_plan* p) { return p ? p->last_launches : 0; }
+
+int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream) {
+  if (!src || !dst_hi || C % 64 || n_images <= 0) return fail(SF_ERR_INVALID, "bad pack arguments");
+  const int hw = H * W;
+  dim3 grid((hw + 31) / 32, C / 64, n_images);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_lo)
+    pack_nchw_kernel<true><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), C, hw);
+  else
+    pack_nchw_kernel<false><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), nullptr, C, hw);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n_out, int C, int H, int W, void* stream) {
+  if (!src || !dst || C % 64 || n_out <= 0) return fail(SF_ERR_INVALID, "bad unpack arguments");
+  const int hw = H * W;
+  dim3 grid((hw + 31) / 32, C / 64, n_out);
+  unpack_nhwc_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, slots, C, hw);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+"""Host-side driver of the CUDA ODE engine: packs the reference's weights into the kernels' layouts,
+owns the NHWC workspace, and turns per-sample step schedules into batched event launches through the
+C ABI (include/sf_b200.h).  Python / PyTorch here is plumbing only: device memory, streams, RNG.
+
+Weight sources (reference parameter names) -> conv stages:
+  gates    conv_update_1/2, conv_reset_1/2            temporal_ode_bayes.py:135-140,150-155
+  propose  conv_state_tilde_1/2 + GRU blend           :143-146,158-161
+  decode   conv_decoder_2                             :121
+  trunk7   trusting_gate.0.layers.0 (7x7) + LN + GELU convolutions.py:356-358
+  trunk1   layers.3 (1x1) + LN + GELU                 :359-361
+  mix      layers.6 (3x3)+LN+GELU, projection, 1x1->2, softmax, mix, Euler/jump   :362-380, tob:124-131,446
+  q1..q5   p_model ConvNet with BatchNorm folded      res_models.py:168-180
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# activation buffer ids
+(BUF_S0, BUF_S1, BUF_X, BUF_OBS, BUF_ZERO, BUF_U1, BUF_U2, BUF_G1, BUF_G2, BUF_A, BUF_B, BUF_HH, BUF_T1, BUF_T2, BUF_Q1,
+ BUF_Z1, BUF_Y1, BUF_Q3, BUF_Z2, BUF_Y2) = range(20)
+_BUF_CHANNELS = {BUF_S0: 1, BUF_S1: 1, BUF_X: 1, BUF_U1: 1, BUF_U2: 1, BUF_G1: 1, BUF_G2: 1, BUF_A: 1, BUF_B: 1, BUF_HH: 1,
+                 BUF_T1: 1, BUF_T2: 1, BUF_Q1: 1, BUF_Z1: 2, BUF_Y1: 2, BUF_Q3: 2, BUF_Z2: 2, BUF_Y2: 2}
+# stage slots
+ST_G, ST_P, ST_D, ST_T7, ST_T1, ST_T3 = range(6)          # + 6 * weight_set (0: gru_c, 1: gru_obs.gru_d)
+ST_Q1, ST_Q2, ST_Q3, ST_Q4, ST_Q5 = 12, 13, 14, 15, 16
+CELL_STAGE_NAMES = ("gates", "propose", "decode", "trunk7", "trunk1", "mix")
+PRIOR_ITEMS = [ST_Q1, ST_Q2, L.SE_ITEM_BASE + 0, ST_Q3, ST_Q4, L.SE_ITEM_BASE + 1, ST_Q5]
+
+KIND_STEP, KIND_JUMP = 0, 1
+
+
+def _bn_fold(sd, p):
+    """eval-mode BatchNorm2d folded into the preceding bias-free conv: w' = w * g/sqrt(var+1e-5), b' = beta - mean*scale."""
+    w = sd[p + ".conv.weight"].float()
+    scale = sd[p + ".norm.weight"].float() / torch.sqrt(sd[p + ".norm.running_var"].float() + 1e-5)
+    bias = sd[p + ".norm.bias"].float() - sd[p + ".norm.running_mean"].float() * scale
+    return w * scale[:, None, None, None], bias
+
+
+class StageDef:
+    """Logical description of a stage before packing: chunks of (source buffer, first channel, weights [n,64,R,R], column, init)."""
+
+    def __init__(self, epilogue, vec, io):
+        self.epilogue, self.vec, self.io = epilogue, vec, list(io)
+        self.chunks: List[Tuple[int, int, torch.Tensor, int, int]] = []
+
+    def add(self, buf, c0, w, col, init):
+        assert w.shape[1] == 64 and w.shape[2] == w.shape[3]
+        self.chunks.append((buf, c0, w, col, init))
+        return self
+
+
+def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
+    """The six conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters."""
+    g = lambda k: sd[f"{p}.{k}"].float()
+    C_ = g("conv_update_1.weight").shape[0]
+    assert C_ == 64
+    wu1, wr1, wt1 = g("conv_update_1.weight"), g("conv_reset_1.weight"), g("conv_state_tilde_1.weight")
+    wu2, wr2, wt2 = g("conv_update_2.weight"), g("conv_reset_2.weight"), g("conv_state_tilde_2.weight")
+    fold = lambda w: w[:, :64] + w[:, 64:]        # gru_cell_2 sees cat[state, state] (tob:118): one 64-ch operand
+    gates = StageDef(L.EPI_GATES, torch.cat([g("conv_update_1.bias"), g("conv_reset_1.bias"), g("conv_update_2.bias"),
+                                              g("conv_reset_2.bias")]), [BUF_U1, BUF_U2, BUF_G1, BUF_G2])
+    gates.add(L.SRC_STATE_IN, 0, torch.cat([wu1[:, 64:], wr1[:, 64:], fold(wu2), fold(wr2)], 0), 0, 1)
+    gates.add(L.SRC_X, 0, torch.cat([wu1[:, :64], wr1[:, :64]], 0), 0, 0)
+    prop = StageDef(L.EPI_PROPOSE, torch.cat([g("conv_state_tilde_1.bias"), g("conv_state_tilde_2.bias")]),
+                    [BUF_U1, BUF_U2, BUF_A, BUF_HH])
+    prop.add(L.SRC_X, 0, wt1[:, :64], 0, 1).add(BUF_G1, 0, wt1[:, 64:], 0, 0)
+    prop.add(L.SRC_STATE_IN, 0, wt2[:, :64], 64, 1).add(BUF_G2, 0, wt2[:, 64:], 64, 0)
+    dec = StageDef(L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B]).add(BUF_HH, 0, g("conv_decoder_2.weight"), 0, 1)
+    t = "trusting_gate.0."
+    w7 = g(t + "layers.0.weight")
+    trunk7 = StageDef(L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1])
+    trunk7.add(BUF_A, 0, w7[:, :64], 0, 1).add(BUF_B, 0, w7[:, 64:], 0, 0)
+    trunk1 = StageDef(L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
+    trunk1.add(BUF_T1, 0, g(t + "layers.3.weight"), 0, 1)
+    wp = g(t + "projection.0.weight")
+    wg = g("trusting_gate.1.weight")[:, :, 0, 0]
+    mix = StageDef(L.EPI_MIX, torch.cat([g(t + "layers.7.weight"), g(t + "layers.7.bias"), wg[0], wg[1]]), [])
+    mix.add(BUF_T2, 0, g(t + "layers.6.weight"), 0, 1).add(BUF_A, 0, wp[:, :64], 64, 1).add(BUF_B, 0, wp[:, 64:], 64, 0)
+    return [gates, prop, dec, trunk7, trunk1, mix]
+
+
+def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
+    """The five conv stages of p_model = ConvNet(64, 128) with BatchNorm folded (res_models.py:168-180)."""
+    m = p + ".model."
+    w1, b1 = _bn_fold(sd, m + "0.layers.conv_1")
+    w2, b2 = _bn_fold(sd, m + "0.layers.conv_2")
+    q1 = StageDef(L.EPI_BIAS_LRELU, b1, [BUF_Q1]).add(L.SRC_STATE_OUT, 0, w1, 0, 1)
+    q2 = StageDef(L.EPI_RES_PROJ, torch.cat([b2, sd[m + "0.projection.bias"].float()]), [BUF_Z1])
+    q2.add(BUF_Q1, 0, w2, 0, 1).add(L.SRC_STATE_OUT, 0, sd[m + "0.projection.weight"].float(), 128, 1)
+    w3, b3 = _bn_fold(sd, m + "2.layers.conv_1")
+    w4, b4 = _bn_fold(sd, m + "2.layers.conv_2")
+    q3 = StageDef(L.EPI_BIAS_LRELU, b3, [BUF_Q3]).add(BUF_Y1, 0, w3[:, :64], 0, 1).add(BUF_Y1, 64, w3[:, 64:], 0, 0)
+    q4 = StageDef(L.EPI_RES_ID, b4, [BUF_Y1, BUF_Z2]).add(BUF_Q3, 0, w4[:, :64], 0, 1).add(BUF_Q3, 64, w4[:, 64:], 0, 0)
+    w5 = sd[m + "4.conv.weight"].float()
+    q5 = StageDef(L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(BUF_Y2, 0, w5[:, :64], 0, 1).add(BUF_Y2, 64, w5[:, 64:], 0, 0)
+    return [q1, q2, q3, q4, q5]
+
+
+def pack_stage(sdef: StageDef, x3: bool):
+    """Packs a stage's weights into the [rows, 64] bf16 matrix the TMA weight ring streams, in consumption order:
+    chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed)."""
+    chunks, blocks, row = [], [], 0
+    for buf, c0, w, col, init in sdef.chunks:
+        n, _, R, _ = w.shape
+        taps = w.permute(3, 2, 0, 1).contiguous()                  # [dx, dy, n, 64]
+        hi = taps.to(torch.bfloat16)
+        if not x3:
+            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=init))
+            blocks.append(hi.reshape(-1, 64))
+            row += R * R * n
+        else:
+            lo = (taps - hi.float()).to(torch.bfloat16)
+            both = torch.stack([hi, lo], dim=2)                     # [dx, dy, rep, n, 64]
+            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=2, col=col, wrow=row, init=init))
+            blocks.append(both.reshape(-1, 64))
+            row += R * R * 2 * n
+            chunks.append(dict(buf=buf, plane=1, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=0))
+            blocks.append(hi.reshape(-1, 64))
+            row += R * R * n
+    return chunks, torch.cat(blocks, 0).contiguous()
+
+
+def emulate_stage(sdef: StageDef, x3: bool, sources: Dict[int, torch.Tensor]) -> torch.Tensor:
+    """Numerically replays the packed plan on the host (pure indexing of the packed matrix, fp64 products): the
+    accumulator columns [pixels..., 256] the tensor core would produce.  Used by CPU tests to pin the packing and
+    the chunk / tap / column bookkeeping against F.conv2d without a GPU.  sources[buf] is NCHW [1, Cbuf, H, W]."""
+    import torch.nn.functional as F
+
+    chunks, wp = pack_stage(sdef, x3)
+    wp = wp.double()
+    any_src = next(iter(sources.values()))
+    H, W = any_src.shape[-2:]
+    acc = torch.zeros(256, H, W, dtype=torch.float64)
+    for ck in chunks:
+        x = sources[ck["buf"]][0, ck["c0"]:ck["c0"] + 64].double()
+        if x3:
+            xh = x.to(torch.bfloat16).double()
+            x = xh if ck["plane"] == 0 else (x - xh).to(torch.bfloat16).double()
+        else:
+            x = x.to(torch.bfloat16).double()
+        R, n, nrep = ck["R"], ck["n"], ck["nrep"]
+        pad = (R - 1) // 2
+        xp = F.pad(x, (pad, pad, pad, pad))
+        out = torch.zeros(n, H, W, dtype=torch.float64)
+        for dx in range(R):
+            for dy in range(R):
+                for rep in range(nrep):
+                    r0 = ck["wrow"] + ((dx * R + dy) * nrep + rep) * n
+                    wt = wp[r0:r0 + n]                                             # [n, 64]
+                    out += torch.einsum("nc,chw->nhw", wt, xp[:, dy:dy + H, dx:dx + W])
+        if ck["init"]:
+            acc[ck["col"]:ck["col"] + n] = out
+        else:
+            acc[ck["col"]:ck["col"] + n] += out
+    return acc
+
+
+class OdeEngine:
+    """One plan + workspace for a fixed (max_images, H, W, precision) on one CUDA device."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, H: int, W: int, max_images: int, precision: str = "bf16",
+                 device: Optional[torch.device] = None, path_slots: int = 0):
+        self.lib = L.load()
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.type != "cuda":
+            raise L.SfError("the ODE engine runs on a CUDA (B200) device only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device, self.H, self.W, self.C = dev, int(H), int(W), 64
+        self.max_images = int(max_images)
+        self.precision = precision
+        self.x3 = precision == "bf16x3"
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        L.check(self.lib.sf_device_supported(dev.index), "sf_device_supported")
+        geo = L.Geometry(self.max_images, self.H, self.W, self.C, L.PREC_BF16X3 if self.x3 else L.PREC_BF16, dev.index)
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(self.lib.sf_plan_create(C.byref(geo), C.byref(handle)), "sf_plan_create")
+        self.plan = handle
+        self._keep: List[torch.Tensor] = []          # packed weights / vectors referenced by the plan
+        self.act: Dict[int, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        self._alloc_workspace(path_slots)
+        self.load_weights(sd, prefix)
+        self.n_obs_images = 0
+        self.launches = 0
+
+    # ------------------------------------------------------------------ workspace
+    def _new_act(self, buf, n_images, channels):
+        shape = (n_images, self.H, self.W, channels)
+        hi = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+        lo = torch.zeros(shape, dtype=torch.bfloat16, device=self.device) if self.x3 else None
+        self.act[buf] = (hi, lo)
+        L.check(self.lib.sf_plan_bind_act(self.plan, buf, hi.data_ptr(), lo.data_ptr() if lo is not None else None, channels,
+                                          n_images), "sf_plan_bind_act")
+
+    def _bind_f32(self, slot, t):
+        L.check(self.lib.sf_plan_bind_f32(self.plan, slot, t.data_ptr() if t is not None else None), "sf_plan_bind_f32")
+
+    def _alloc_workspace(self, path_slots):
+        B, H, W, Cc = self.max_images, self.H, self.W, self.C
+        for buf, mult in _BUF_CHANNELS.items():
+            self._new_act(buf, B, Cc * mult)
+        self._new_act(BUF_ZERO, 1, Cc)
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
+        self.state32 = [f32(B, H, W, Cc), f32(B, H, W, Cc)]
+        self.a32, self.b32 = f32(B, H, W, Cc), f32(B, H, W, Cc)
+        self.se_sums = f32(2, B, 2 * Cc)
+        self.x32, self.params32 = f32(B, H, W, Cc), f32(B, H, W, 2 * Cc)
+        self.errflag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for slot, t in ((L.F32_STATE0, self.state32[0]), (L.F32_STATE1, self.state32[1]), (L.F32_A, self.a32), (L.F32_B, self.b32),
+                        (L.F32_SE_SUMS, self.se_sums), (L.F32_X, self.x32), (L.F32_PARAMS, self.params32),
+                        (L.F32_ERRFLAG, self.errflag)):
+            self._bind_f32(slot, t)
+        self.path = None
+        self.ensure_path_slots(max(1, path_slots))
+        self.eps = None
+
+    def ensure_path_slots(self, n):
+        if self.path is None or self.path.shape[0] < n:
+            self.path = torch.zeros((n, self.H, self.W, self.C), dtype=torch.float32, device=self.device)
+            self._bind_f32(L.F32_PATH, self.path)
+
+    def bind_eps(self, eps: torch.Tensor):
+        """eps: fp32 NCHW [slots, 64, H, W] standard-normal noise (torch's own generation order)."""
+        assert eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape[1:]) == (self.C, self.H, self.W)
+        self.eps = eps
+        self._bind_f32(L.F32_EPS, eps)
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, sd: Dict[str, torch.Tensor], prefix: str):
+        """(Re)packs every stage from reference-named parameters ``{prefix}gru_c.*``, ``{prefix}gru_obs.gru_d.*``,
+        ``{prefix}p_model.*``."""
+        sd = {k: v.detach().to(self.device) for k, v in sd.items() if k.startswith(prefix)}
+        pre = prefix
+        self._keep = []
+        self.stage_defs: Dict[int, StageDef] = {}
+        for ws, cell in enumerate((pre + "gru_c", pre + "gru_obs.gru_d")):
+            for i, sdef in enumerate(cell_stage_defs(sd, cell)):
+                self.stage_defs[i + 6 * ws] = sdef
+        for slot, sdef in zip((ST_Q1, ST_Q2, ST_Q3, ST_Q4, ST_Q5), prior_stage_defs(sd, pre + "p_model")):
+            self.stage_defs[slot] = sdef
+        for slot, sdef in self.stage_defs.items():
+            chunks, wp = pack_stage(sdef, self.x3)
+            vec = sdef.vec.to(torch.float32).contiguous()
+            arr = (L.Chunk * len(chunks))(*[L.Chunk(**c) for c in chunks])
+            io = (C.c_int32 * max(1, len(sdef.io)))(*sdef.io)
+            self._keep += [wp, vec]
+            L.check(self.lib.sf_plan_define_stage(self.plan, slot, sdef.epilogue, len(chunks), arr, wp.data_ptr(), wp.shape[0],
+                                                  vec.data_ptr(), vec.numel(), io, len(sdef.io)), f"sf_plan_define_stage({slot})")
+        for which, (idx, zin, yout) in enumerate(((1, BUF_Z1, BUF_Y1), (3, BUF_Z2, BUF_Y2))):
+            fc1 = sd[f"{pre}p_model.model.{idx}.fc.0.weight"].float().contiguous()
+            fc2 = sd[f"{pre}p_model.model.{idx}.fc.2.weight"].float().contiguous()
+            self._keep += [fc1, fc2]
+            L.check(self.lib.sf_plan_define_se(self.plan, which, fc1.data_ptr(), fc2.data_ptr(), zin, yout), "sf_plan_define_se")
+        i32 = lambda v: (C.c_int32 * len(v))(*v)
+        L.check(self.lib.sf_plan_define_event_graph(self.plan, i32(list(range(0, 6))), i32(list(range(6, 12))), 6,
+                                                    i32(PRIOR_ITEMS), len(PRIOR_ITEMS)), "sf_plan_define_event_graph")
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sf_plan_finalize(self.plan), "sf_plan_finalize")
+
+    # ------------------------------------------------------------------ data movement
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def pack_into(self, buf: int, src_nchw: torch.Tensor, n_images: Optional[int] = None):
+        """NCHW fp32 -> the NHWC bf16 activation buffer ``buf`` (first n images)."""
+        src = src_nchw.contiguous().float()
+        n, c, h, w = src.shape
+        assert (h, w) == (self.H, self.W)
+        hi, lo = self.act[buf]
+        assert n <= hi.shape[0] and c == hi.shape[3]
+        L.check(self.lib.sf_pack_nchw_f32(src.data_ptr(), hi.data_ptr(), lo.data_ptr() if lo is not None else None, n, c, h, w,
+                                          self._stream()), "sf_pack_nchw_f32")
+
+    def bind_observations(self, hx_nchw: torch.Tensor):
+        """Encoded observations [n_img, 64, H, W] fp32 -> OBS activation buffer (the jump cell's x input)."""
+        n = hx_nchw.shape[0]
+        if BUF_OBS not in self.act or self.act[BUF_OBS][0].shape[0] < n:
+            self._new_act(BUF_OBS, n, self.C)
+        self.pack_into(BUF_OBS, hx_nchw)
+        self.n_obs_images = n
+
+    def set_state(self, which: int, state_nchw: torch.Tensor):
+        n = state_nchw.shape[0]
+        nhwc = state_nchw.float().permute(0, 2, 3, 1).contiguous()
+        self.state32[which][:n].copy_(nhwc)
+        self.pack_into(BUF_S0 + which, state_nchw)
+
+    def zero_state(self, which: int = 0):
+        self.state32[which].zero_()
+        hi, lo = self.act[BUF_S0 + which]
+        hi.zero_()
+        if lo is not None:
+            lo.zero_()
+
+    def unpack_path(self, slots: Sequence[int]) -> torch.Tensor:
+        """Recorded states (NHWC fp32 path buffer) -> NCHW fp32 [len(slots), 64, H, W]."""
+        idx = torch.tensor(list(slots), dtype=torch.int32, device=self.device)
+        out = torch.empty((len(slots), self.C, self.H, self.W), dtype=torch.float32, device=self.device)
+        L.check(self.lib.sf_unpack_nhwc_f32(self.path.data_ptr(), out.data_ptr(), idx.data_ptr(), len(slots), self.C, self.H, self.W,
+                                            self._stream()), "sf_unpack_nhwc_f32")
+        return out
+
+    def unpack_f32(self, t_nhwc: torch.Tensor, n: int) -> torch.Tensor:
+        c = t_nhwc.shape[3]
+        out = torch.empty((n, c, self.H, self.W), dtype=torch.float32, device=self.device)
+        L.check(self.lib.sf_unpack_nhwc_f32(t_nhwc.data_ptr(), out.data_ptr(), None, n, c, self.H, self.W, self._stream()),
+                "sf_unpack_nhwc_f32")
+        return out
+
+    # ------------------------------------------------------------------ events
+    @staticmethod
+    def build_table(events: List[dict]) -> Tuple[np.ndarray, List[L.Event]]:
+        """events: dicts with kind, samples, x_img, rec, eps, dt (lists of equal length) + x_buf, s_in, s_base, s_out,
+        run_cell, run_prior, want_f32.  Returns the packed int32 table and the sf_event structs."""
+        rows, evs, off = [], [], 0
+        for e in events:
+            n = len(e["samples"])
+            blk = np.empty((5, n), dtype=np.int32)
+            blk[0] = e["samples"]
+            blk[1] = e["x_img"]
+            blk[2] = e.get("rec", [-1] * n)
+            blk[3] = e.get("eps", [0] * n)
+            blk[4] = np.asarray(e.get("dt", [0.0] * n), dtype=np.float64).astype(np.float32).view(np.int32)
+            rows.append(blk.reshape(-1))
+            evs.append(L.Event(e["kind"], n, e["x_buf"], e.get("s_in", 0), e.get("s_base", 0), e.get("s_out", 0),
+                               int(e.get("run_cell", 1)), int(e.get("run_prior", 1)), int(e.get("want_f32", 0)), off))
+            off += 5 * n
+        return (np.concatenate(rows) if rows else np.zeros(0, np.int32)), evs
+
+    def upload_table(self, table: np.ndarray) -> torch.Tensor:
+        t = torch.from_numpy(table)
+        return t.to(self.device, non_blocking=False)
+
+    def run_events(self, evs: List[L.Event], table_dev: torch.Tensor):
+        arr = (L.Event * len(evs))(*evs)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sf_plan_run_events(self.plan, arr, len(evs), table_dev.data_ptr(), self._stream()), "sf_plan_run_events")
+        n = self.lib.sf_plan_last_launches(self.plan)
+        self.launches += n
+        return n
+
+    def run_rollout(self, events: List[dict]) -> int:
+        """events (dicts, see build_table) -> one table upload + one C call that enqueues every stage launch."""
+        table, evs = self.build_table(events)
+        return self.run_events(evs, self.upload_table(table))
+
+    def run_stage(self, stage: int, ev: L.Event, table_dev: torch.Tensor):
+        with torch.cuda.device(self.device):
+            L.check(self.lib.sf_plan_run_stage(self.plan, stage, C.byref(ev), table_dev.data_ptr(), self._stream()), "sf_plan_run_stage")
+
+    def check_errflag(self):
+        v = int(self.errflag.item())
+        if v:
+            raise L.SfError(f"device-side pipeline timeout, code 0x{v:x}")
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.sf_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass

@@ -1,0 +1,307 @@
+"""GRU-ODE-Bayes integration of the BEV latent state on B200 -- drop-in for the reference classes of
+``streamingflow/layers/temporal_ode_bayes.py`` (same constructor arguments, ``forward`` signatures, attribute and
+``state_dict`` names), with all arithmetic of the integration loop executed by the CUDA engine (engine.py ->
+libsf_b200.so).  There is no PyTorch / CPU fallback for the loop: on a non-CUDA tensor these modules raise.
+
+What differs from the reference, on purpose:
+  * the step schedule is computed on the host up front (schedule.py) instead of with ``.item()`` syncs per step;
+  * samples are integrated together, event by event (rollout.py), instead of one Python loop iteration per sample;
+  * the wasted ``srvp_encode(input)`` (reference :503) is skipped -- only its shape was used;
+  * noise is pre-drawn with the same torch calls in the same order, so a same-device reference run sees the same
+    stream (``noise='reference'``); ``noise='bulk'`` draws it in one launch.
+Inner API (``ode_step``, ``infer_state``, cell ``forward``) accepts N > 1 samples as an independent batch; the
+reference's own N > 1 behaviour on 4-D inputs is the degenerate ``n_present`` path and is not reproduced.
+"""
+from __future__ import annotations
+
+import math
+import os
+import weakref
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from ..rollout import compile_rollout
+from ..schedule import JUMP, STEP, plan_sample
+from .convolutions import Bottleblock
+from .res_models import ConvNet, SmallDecoder, SmallEncoder
+
+__all__ = ["DualGRUODECell", "DualGRUCell", "GRUObservationCell", "NNFOwithBayesianJumps", "init_weights"]
+
+
+class _DualGRUBase(nn.Module):
+    """Parameters of the dual ConvGRU + trusting-gate cell (reference :64-90 / :211-237)."""
+
+    def __init__(self, input_size, hidden_size, gru_bias_init=0.0, norm='bn', activation='relu', bias=True):
+        super().__init__()
+        self.input_size, self.hidden_size, self.gru_bias_init = input_size, hidden_size, gru_bias_init
+        mk = lambda cin: nn.Conv2d(cin, hidden_size, kernel_size=3, bias=True, padding=1)
+        self.conv_update_1 = mk(input_size + hidden_size)
+        self.conv_reset_1 = mk(input_size + hidden_size)
+        self.conv_state_tilde_1 = mk(input_size + hidden_size)
+        self.conv_update_2 = mk(hidden_size + hidden_size)
+        self.conv_reset_2 = mk(hidden_size + hidden_size)
+        self.conv_state_tilde_2 = mk(hidden_size + hidden_size)
+        self.conv_decoder_2 = mk(hidden_size)
+        self.trusting_gate = nn.Sequential(Bottleblock(hidden_size + hidden_size, hidden_size),
+                                           nn.Conv2d(hidden_size, 2, kernel_size=1, bias=False))
+        self.__dict__["_owner"] = None          # weakref to the NNFOwithBayesianJumps that owns the engine
+
+    def _run(self, x, state, derivative: bool):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None:
+            raise RuntimeError(f"{type(self).__name__} evaluates on the CUDA ODE engine of its owning NNFOwithBayesianJumps; "
+                               "a free-standing cell has no engine (and there is no PyTorch fallback).")
+        squeeze5 = x.dim() == 5
+        if squeeze5:
+            if state.shape[1] != 1 or x.shape[1] != 1:
+                raise NotImplementedError("n_present > 1 (5-D state) is never produced by the reference's call sites")
+            x, state = x[:, 0], state[:, 0]
+        if x.shape[1] != self.input_size:
+            raise AssertionError(f'feature sizes must match, got input {x.shape[1]} for layer with size {self.input_size}')
+        if x.shape[0] != state.shape[0]:
+            raise NotImplementedError("x and state must have the same batch size (independent samples)")
+        return owner._cell_call(self, x, state, derivative)
+
+
+class DualGRUODECell(_DualGRUBase):
+    """ODE derivative: trust-mixed dual-GRU proposal minus the state (reference :92-131)."""
+
+    def forward(self, x, state):
+        return self._run(x, state, derivative=True)
+
+
+class DualGRUCell(_DualGRUBase):
+    """Discrete update: the trust-mixed dual-GRU proposal itself (reference :239-275)."""
+
+    def forward(self, x, state):
+        return self._run(x, state, derivative=False)
+
+
+class GRUObservationCell(nn.Module):
+    """Observation jump (reference :308-344): ``state <- gru_d(X_obs, state)``; the Bayes loss is disabled upstream."""
+
+    def __init__(self, input_size, hidden_size, min_log_sigma=-5.0, max_log_sigma=5.0, bias=True):
+        super().__init__()
+        self.gru_d = DualGRUCell(input_size, hidden_size, bias=bias)
+        self.input_size, self.prep_hidden, self.var_eps = input_size, hidden_size, 1e-6
+        self.min_log_sigma, self.max_log_sigma = min_log_sigma, max_log_sigma
+
+    def forward(self, state, p, X_obs):
+        if state.shape[0] != X_obs.shape[0] and X_obs.shape[0] == 1:
+            # the reference's first call passes the all-zero [B, C, h, w] initial state; n_present collapses it to one sample
+            state = state[-1:]
+        return self.gru_d(X_obs, state), None
+
+
+def init_weights(m):
+    """Reference :349-353: Xavier-uniform Linear weights (the squeeze-excite FCs), bias 0.05."""
+    if type(m) == nn.Linear:
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            m.bias.data.fill_(0.05)
+
+
+class NNFOwithBayesianJumps(nn.Module):
+    """Neural negative-feedback ODE with observation jumps over the /4 BEV latent (reference :355-627)."""
+
+    def __init__(self, input_size, hidden_size, cfg, bias=True, logvar=True, mixing=1, solver="euler", min_log_sigma=-5.0,
+                 max_log_sigma=5.0, impute=False):
+        super().__init__()
+        self.impute = cfg.MODEL.IMPUTE                # the reference reads cfg, not the kwargs (:365,384)
+        self.cfg = cfg
+        self.min_log_sigma, self.max_log_sigma = min_log_sigma, max_log_sigma
+        self.p_model = ConvNet(hidden_size, hidden_size * 2)
+        self.gru_c = DualGRUODECell(input_size, hidden_size, bias=bias)
+        self.gru_obs = GRUObservationCell(input_size, hidden_size, min_log_sigma=min_log_sigma, max_log_sigma=max_log_sigma, bias=bias)
+        self.skipco = cfg.MODEL.SMALL_ENCODER.SKIPCO
+        ch, nf = cfg.MODEL.ENCODER.OUT_CHANNELS, cfg.MODEL.SMALL_ENCODER.FILTER_SIZE
+        self.srvp_encoder = SmallEncoder(ch, ch, nf)
+        self.srvp_decoder = SmallDecoder(ch, ch, nf, self.skipco)
+        self.solver = cfg.MODEL.SOLVER
+        self.use_variable_ode_step = cfg.MODEL.FUTURE_PRED.USE_VARIABLE_ODE_STEP
+        assert self.solver in ["euler", "midpoint"], "Solver must be either 'euler' or 'midpoint'."
+        self.input_size, self.hidden_size, self.logvar, self.mixing = input_size, hidden_size, logvar, mixing
+        self.apply(init_weights)
+        me = weakref.ref(self)
+        self.gru_c.__dict__["_owner"] = me
+        self.gru_obs.gru_d.__dict__["_owner"] = me
+        # engine options (not part of the reference API)
+        self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
+        self.noise = "reference"
+        self.__dict__["_engines"] = {}
+        self.__dict__["_engine_factory"] = None        # tests inject a checker backend here; the product path never does
+        self.last_rollout = None
+
+    # ------------------------------------------------------------------ engine management
+    def _weights_fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for mod in (self.gru_c, self.gru_obs, self.p_model)
+                     for p in list(mod.parameters()) + list(mod.buffers()))
+
+    def _engine_for(self, h, w, n_images, device):
+        if self.training:
+            raise L.SfError("the CUDA ODE engine implements inference (eval mode, BatchNorm folded); call .eval()")
+        key = (str(device), h, w, self.precision)
+        fp = self._weights_fingerprint()
+        ent = self._engines.get(key)
+        if ent is not None and ent["engine"].max_images >= n_images:
+            if ent["fp"] != fp:
+                ent["engine"].load_weights(self._hot_state_dict(), "")
+                ent["fp"] = fp
+            return ent["engine"]
+        if self._engine_factory is not None:
+            eng = self._engine_factory(self._hot_state_dict(), h, w, n_images, self.precision, device)
+        else:
+            if device.type != "cuda":
+                raise L.SfError("streamingflow_b200 integrates the ODE on a B200 GPU only; got a tensor on " + str(device))
+            if self.hidden_size != 64 or self.input_size != 64:
+                raise L.SfError("the CUDA ODE engine is built for 64 hidden channels")
+            from ..engine import OdeEngine
+
+            eng = OdeEngine(self._hot_state_dict(), "", h, w, n_images, self.precision, device)
+        self._engines[key] = dict(engine=eng, fp=fp)
+        return eng
+
+    def _hot_state_dict(self):
+        sd = {}
+        for name in ("gru_c", "gru_obs", "p_model"):
+            for k, v in getattr(self, name).state_dict().items():
+                sd[f"{name}.{k}"] = v
+        return sd
+
+    def _draw_noise(self, n, h, w, device):
+        """Standard-normal tensors in the reference's order: one ``torch.empty([1,C,h,w]).normal_()`` per infer_state call
+        (torch.distributions.Normal.rsample -> _standard_normal), here drawn in place into one [n, C, h, w] buffer."""
+        eps = torch.empty((max(n, 1), self.hidden_size, h, w), dtype=torch.float32, device=device)
+        if self.noise == "bulk":
+            eps.normal_()
+        else:
+            for i in range(n):
+                eps[i].normal_()
+        return eps
+
+    # ------------------------------------------------------------------ encoder / decoder wrappers (reference :396-434)
+    def srvp_decode(self, x, skip=None):
+        b, t, c, h, w = x.shape
+        flat = x.reshape(b * t, c, h, w)
+        if skip:
+            skip = [s.unsqueeze(1).expand(b, t, *s.shape[1:]).reshape(t * b, *s.shape[1:]) for s in skip]
+        out = self.srvp_decoder(flat, skip=skip)
+        return out.view(b, t, *out.shape[1:])
+
+    def srvp_encode(self, x):
+        b, t, c, h, w = x.shape
+        hx, skips = self.srvp_encoder(x.view(b * t, c, h, w), return_skip=True)
+        hx = hx.view(b, t, *hx.shape[1:])
+        if self.skipco:
+            if self.training:
+                tx = torch.randint(t, size=(b,)).to(hx.device)
+                skips = [s.view(b, t, *s.shape[1:])[torch.arange(b).to(hx.device), tx] for s in skips]
+            else:
+                skips = [s.view(b, t, *s.shape[1:])[:, -1] for s in skips]
+        else:
+            skips = None
+        return hx, skips
+
+    # ------------------------------------------------------------------ inner API on the engine
+    def _single_event(self, eng, n, **kw):
+        ev = dict(samples=list(range(n)), x_img=list(range(n)), rec=[-1] * n, eps=list(range(n)), dt=[0.0] * n, x_buf=2,
+                  s_in=0, s_base=0, s_out=0, run_cell=1, run_prior=0, want_f32=0, kind=STEP)
+        ev.update(kw)
+        return ev
+
+    def _cell_call(self, cell, x, state, derivative):
+        n, _, h, w = x.shape
+        eng = self._engine_for(h, w, n, x.device)
+        eng.set_state(0, state)
+        eng.pack_into(2, x)
+        if derivative:
+            # dh = 0 + 1.0 * (mix - state): Euler epilogue with a zero base buffer and dt = 1
+            eng.zero_state(1)
+            ev = self._single_event(eng, n, kind=STEP, dt=[1.0] * n, s_in=0, s_base=1, s_out=1)
+            if cell is not self.gru_c:
+                raise RuntimeError("derivative cell is not this module's gru_c")
+        else:
+            ev = self._single_event(eng, n, kind=JUMP)
+            if cell is not self.gru_obs.gru_d:
+                raise RuntimeError("jump cell is not this module's gru_obs.gru_d")
+        eng.run_rollout([ev])
+        return eng.unpack_f32(eng.state32[1 if derivative else 0], n)
+
+    def infer_state(self, x, deterministic=False):
+        """(sample, params) of the latent prior at state x (reference :463-477)."""
+        n, _, h, w = x.shape
+        eng = self._engine_for(h, w, n, x.device)
+        eng.set_state(0, x)
+        eng.bind_eps(self._draw_noise(n, h, w, x.device))
+        eng.run_rollout([self._single_event(eng, n, run_cell=0, run_prior=1, want_f32=1)])
+        return eng.unpack_f32(eng.x32, n), eng.unpack_f32(eng.params32, n)
+
+    def ode_step(self, state, input, delta_t, current_time):
+        """One solver step (reference :436-459). Returns (state, input, current_time + delta_t, eval_times, eval_ps)."""
+        n, _, h, w = state.shape
+        dev = state.device
+        eng = self._engine_for(h, w, n, dev)
+        dt = float(delta_t)
+        eng.set_state(0, state)
+        x_buf = 2
+        if self.impute is False:
+            x_buf = 4
+        else:
+            eng.pack_into(2, input)
+        ximg = list(range(n)) if x_buf == 2 else [0] * n
+        if self.solver == "euler":
+            eng.bind_eps(self._draw_noise(n, h, w, dev))
+            evs = [self._single_event(eng, n, x_buf=x_buf, x_img=ximg, dt=[dt] * n, run_prior=1, want_f32=1)]
+        else:
+            eps = self._draw_noise(2 * n, h, w, dev)       # per sample: noise for infer(k), then for infer(state)
+            eng.bind_eps(eps)
+            evs = [self._single_event(eng, n, x_buf=x_buf, x_img=ximg, dt=[dt / 2] * n, s_out=1, run_prior=1,
+                                      eps=[2 * i for i in range(n)]),
+                   self._single_event(eng, n, x_buf=2, dt=[dt] * n, s_in=1, s_base=0, s_out=0, run_prior=1, want_f32=1,
+                                      eps=[2 * i + 1 for i in range(n)])]
+        eng.run_rollout(evs)
+        eval_times = torch.tensor([0], device=dev, dtype=torch.float64)
+        eval_ps = torch.tensor([0], device=dev, dtype=torch.float32)
+        current_time = current_time + delta_t
+        return eng.unpack_f32(eng.state32[0], n), eng.unpack_f32(eng.x32, n), current_time, eval_times, eval_ps
+
+    # ------------------------------------------------------------------ the rollout
+    def integrate_latents(self, hx_obs, obs_counts: Sequence[int], times: Sequence[Sequence[float]],
+                          targets: Sequence[Sequence[float]], delta_t: float):
+        """Batched jump / integrate loop on already-encoded observations.
+
+        hx_obs: [sum(obs_counts), C, h, w] fp32 latents, sample-major, each sample's frames in processing order.
+        times[b] / targets[b]: python floats.  Returns (final states [B,C,h,w], selected latents [B,T,C,h,w])."""
+        B = len(obs_counts)
+        _, c, h, w = hx_obs.shape
+        dev = hx_obs.device
+        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
+        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute))
+        eng = self._engine_for(h, w, B, dev)
+        eng.bind_observations(hx_obs)
+        eng.zero_state(0)
+        eng.ensure_path_slots(ro.n_path)
+        eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
+        ro.launches = eng.run_rollout(ro.events)
+        self.last_rollout = ro
+        T = len(targets[0])
+        flat = [s for slots in ro.out_slots for s in slots]
+        sel = eng.unpack_path(flat).view(B, T, c, h, w)
+        return eng.unpack_f32(eng.state32[0], B), sel
+
+    def forward(self, times, input, obs, delta_t, T, return_path=True):
+        """Reference :479-627.  times: observation times in processing order; input: only its shape is used;
+        obs: [1, n_obs, C, H, W]; T: target times.  Returns (final latent state, 0, decoded frames [1, T, C, H, W])."""
+        if obs.shape[0] != 1:
+            raise NotImplementedError("the reference calls gru_ode with one sample (obs batch 1); use FuturePredictionODE for batches")
+        t_list = times.tolist() if isinstance(times, torch.Tensor) else [float(t) for t in times]
+        T_list = T.tolist() if isinstance(T, torch.Tensor) else [float(t) for t in T]
+        hx_obs, _ = self.srvp_encode(obs)
+        state, sel = self.integrate_latents(hx_obs[0], [hx_obs.shape[1]], [t_list], [T_list], delta_t)
+        x = self.srvp_decode(sel)
+        return state, 0, x

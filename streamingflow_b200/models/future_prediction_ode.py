@@ -1,0 +1,60 @@
+"""Drop-in for ``streamingflow/models/future_prediction_ode.py::FuturePredictionODE`` (reference :9-64).
+
+Same constructor, ``forward`` signature, return value ``(x [B, T, C, H, W], 0)`` and ``state_dict`` names, so a
+reference checkpoint loads with ``strict=True`` and ``streamingflow.forward`` (models/streamingflow.py:258-267) can
+call it unchanged.  The per-sample Python loop of the reference (:36-51) becomes ONE batched rollout on the CUDA
+engine: all observation frames of all samples are encoded together, every sample's schedule is computed on the host,
+and the samples advance event by event (rollout.py).  The result is the same as the reference's loop because
+samples are independent and the noise is drawn in the reference's sample-major order.
+"""
+import torch
+import torch.nn as nn
+
+from ..layers.convolutions import Block, DeepLabHead
+from ..layers.temporal import SpatialGRU
+from ..layers.temporal_ode_bayes import NNFOwithBayesianJumps
+from ..schedule import merge_observations
+
+
+class FuturePredictionODE(nn.Module):
+    def __init__(self, in_channels, latent_dim, n_future, cfg, mixture=True, n_gru_blocks=2, n_res_layers=1, delta_t=0.05):
+        super().__init__()
+        self.n_spatial_gru = n_gru_blocks
+        self.delta_t = delta_t
+        self.gru_ode = NNFOwithBayesianJumps(input_size=in_channels, hidden_size=latent_dim, cfg=cfg, mixing=int(mixture))
+        grus, blocks = [], []
+        for i in range(n_gru_blocks):
+            grus.append(SpatialGRU(in_channels, in_channels))
+            last = i == n_gru_blocks - 1
+            blocks.append(DeepLabHead(in_channels, in_channels, 128) if last
+                          else nn.Sequential(*[Block(in_channels) for _ in range(n_res_layers)]))
+        self.spatial_grus = nn.ModuleList(grus)
+        self.res_blocks = nn.ModuleList(blocks)
+
+    @staticmethod
+    def _host_times(t):
+        """Timestamps as python doubles with ONE device->host copy (the reference syncs once per dict key)."""
+        return None if t is None else t.detach().to("cpu", torch.float64).tolist()
+
+    def forward(self, future_prediction_input, camera_states, lidar_states, camera_timestamp, lidar_timestamp, target_timestamp):
+        # camera_states [B, n_cam, C, H, W]; lidar_states [B, n_lidar, C, H, W] or None; timestamps [B, n] (seconds)
+        B = camera_states.shape[0]
+        cam_t = self._host_times(camera_timestamp)
+        lid_t = self._host_times(lidar_timestamp) if lidar_states is not None else None
+        tgt_t = self._host_times(target_timestamp)
+        frames, counts, times = [], [], []
+        for b in range(B):
+            order = merge_observations(cam_t[b], None if lid_t is None else lid_t[b])
+            frames += [camera_states[b, i] if sensor == 0 else lidar_states[b, i] for _, sensor, i in order]
+            counts.append(len(order))
+            times.append([t for t, _, _ in order])
+        ode = self.gru_ode
+        hx = ode.srvp_encoder(torch.stack(frames, dim=0))
+        _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t)
+        x = ode.srvp_decode(sel)                                       # [B, T, C, H, W]
+        hidden_state = x[:, 0]
+        for gru, block in zip(self.spatial_grus, self.res_blocks):
+            x = gru(x, hidden_state)
+            b, s, c, h, w = x.shape
+            x = block(x.view(b * s, c, h, w)).view(b, s, c, h, w)
+        return x, 0

@@ -1,0 +1,95 @@
+"""Compiles per-sample step plans into batched engine events.
+
+The reference integrates one sample at a time (future_prediction_ode.py:36-51).  Samples are
+independent, so round r of the batched rollout executes the r-th engine event of every sample that still
+has one, grouped by (event kind, state buffers, x source): one set of stage launches per group with the
+sample list as a device-side index table.  Schedules may differ between samples (jitter, micro-steps),
+which only changes group membership -- a sample is never padded with a fake step, because even a dt = 0
+step would redraw the sampled input (SURVEY 7.3 'Schedule parity').
+
+Noise slots follow the reference's consumption order exactly: sample-major, then event order, one
+standard-normal tensor per infer_state call (two per midpoint step).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+from .schedule import JUMP, STEP, SamplePlan
+
+# keep in sync with engine.py buffer ids
+BUF_X, BUF_OBS, BUF_ZERO = 2, 3, 4
+
+
+@dataclass
+class Rollout:
+    events: List[dict] = field(default_factory=list)      # engine event dicts (see OdeEngine.build_table)
+    n_eps: int = 0                                         # noise tensors to draw, in slot order
+    n_path: int = 0                                        # recorded states
+    out_slots: List[List[int]] = field(default_factory=list)   # per sample, per target: path slot
+    n_state_steps: int = 0                                 # ode_step calls over all samples (the metric's unit)
+    n_jumps: int = 0
+    n_cell_evals: int = 0
+    n_prior_evals: int = 0
+
+
+def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool) -> Rollout:
+    ro = Rollout()
+    per_sample: List[List[dict]] = []
+    eps = 0
+    for b, plan in enumerate(plans):
+        picked: Dict[int, int] = {}
+        slots = []
+        for op_idx in plan.picks:
+            if op_idx not in picked:
+                picked[op_idx] = ro.n_path
+                ro.n_path += 1
+            slots.append(picked[op_idx])
+        ro.out_slots.append(slots)
+        evs: List[dict] = []
+        for i, op in enumerate(plan.ops):
+            rec = picked.get(i, -1)
+            if op.kind == JUMP:
+                evs.append(dict(kind=JUMP, x_buf=BUF_OBS, x_img=obs_base[b] + op.obs, s_in=0, s_base=0, s_out=0, dt=0.0, eps=eps,
+                                rec=rec, run_prior=impute))
+                eps += 1
+                ro.n_jumps += 1
+            else:
+                xb, xi = (BUF_X, b) if impute else (BUF_ZERO, 0)
+                if solver == "euler":
+                    evs.append(dict(kind=STEP, x_buf=xb, x_img=xi, s_in=0, s_base=0, s_out=0, dt=op.dt, eps=eps, rec=rec,
+                                    run_prior=impute))
+                    eps += 1
+                elif solver == "midpoint":
+                    # k = s + dt/2 f(x, s); pk = infer(k)   |   s = s + dt f(pk, k); x = infer(s)      (tob:449-454)
+                    evs.append(dict(kind=STEP, x_buf=xb, x_img=xi, s_in=0, s_base=0, s_out=1, dt=op.dt / 2, eps=eps, rec=-1,
+                                    run_prior=True))
+                    evs.append(dict(kind=STEP, x_buf=BUF_X, x_img=b, s_in=1, s_base=0, s_out=0, dt=op.dt, eps=eps + 1, rec=rec,
+                                    run_prior=impute))
+                    eps += 2
+                else:
+                    raise ValueError(f"Unknown solver '{solver}'.")
+                ro.n_state_steps += 1
+        per_sample.append(evs)
+    ro.n_eps = eps
+    depth = max((len(e) for e in per_sample), default=0)
+    for r in range(depth):
+        groups: Dict[Tuple, dict] = {}
+        for b, evs in enumerate(per_sample):
+            if r >= len(evs):
+                continue
+            e = evs[r]
+            key = (e["kind"], e["x_buf"], e["s_in"], e["s_base"], e["s_out"], e["run_prior"])
+            g = groups.setdefault(key, dict(kind=e["kind"], x_buf=e["x_buf"], s_in=e["s_in"], s_base=e["s_base"], s_out=e["s_out"],
+                                            run_cell=1, run_prior=int(e["run_prior"]), want_f32=0, samples=[], x_img=[], rec=[],
+                                            eps=[], dt=[]))
+            g["samples"].append(b)
+            g["x_img"].append(e["x_img"])
+            g["rec"].append(e["rec"])
+            g["eps"].append(e["eps"])
+            g["dt"].append(e["dt"])
+        for g in groups.values():
+            ro.events.append(g)
+            ro.n_cell_evals += len(g["samples"])
+            ro.n_prior_evals += len(g["samples"]) * g["run_prior"]
+    return ro

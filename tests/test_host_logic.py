@@ -1,0 +1,182 @@
+"""CPU tests of the product's host logic: schedule, rollout compilation, weight packing plan, module glue, C-ABI symbols.
+No GPU and no CUDA compute: the engine is replaced by a checker backend built on the oracle (tests/_oracle_backend.py)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sf_oracle as so
+from oracle.shapes import nnfo_shapes
+from oracle._refimport import make_cfg
+from streamingflow_b200 import schedule as sc
+from streamingflow_b200.rollout import compile_rollout
+from tests._oracle_backend import OracleBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_schedule_matches_reference_traces(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "sched.json")))["cases"]
+    for c in cases:
+        plan = sc.plan_sample(c["times"], c["targets"], c["delta_t"], c["variable"], c["solver"])
+        assert [("step" if o.kind == sc.STEP else "jump") for o in plan.ops] == c["kinds"], c["tag"]
+        for o, dt, ta in zip(plan.ops, c["dts"], c["t_after"]):
+            if o.kind == sc.STEP:
+                assert o.dt == dt and o.t == ta, c["tag"]
+        assert plan.picks == c["selected"], c["tag"]
+
+
+def test_schedule_matches_oracle_on_random_stamps():
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        n = rng.randint(1, 9)
+        times = sorted((rng.uniform(-1.2, 0.05, n)).tolist())
+        tg = sorted(rng.uniform(-1.2, 2.5, rng.randint(1, 9)).tolist())
+        var = bool(trial & 1)
+        a = sc.plan_sample(times, tg, 0.05, var)
+        b = so.build_schedule(times, tg, 0.05, var)
+        assert [(o.kind == sc.STEP, o.dt) for o in a.ops] == [(e.kind == "step", e.dt) for e in b.events]
+        assert a.picks == [b.path_ev[i] for i in b.select]
+
+
+def test_merge_observations_stable_and_keeps_duplicates():
+    order = sc.merge_observations([-1.0, -0.5, 0.0], [-0.8, -0.5, 0.0, 0.0])
+    assert [(s, i) for _, s, i in order] == [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2), (1, 3)]
+    with pytest.raises(ValueError):
+        sc.plan_sample([], [0.0], 0.05, True)
+
+
+def test_rollout_grouping_and_noise_order():
+    times = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
+    tg = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+    p0 = sc.plan_sample(times, tg, 0.05, True)
+    p1 = sc.plan_sample([t - 0.013 if i % 3 else t for i, t in enumerate(times)], tg, 0.05, True)
+    ro = compile_rollout([p0, p1], [0, 8], "euler", True)
+    assert ro.n_eps == p0.n_noise + p1.n_noise and ro.n_state_steps == p0.n_steps + p1.n_steps
+    seen = {}
+    for e in ro.events:
+        for b, s in zip(e["samples"], e["eps"]):
+            seen.setdefault(b, []).append(s)
+    assert seen[0] == list(range(p0.n_noise))                                   # sample-major noise slots
+    assert seen[1] == list(range(p0.n_noise, p0.n_noise + p1.n_noise))
+    assert all(len(set(e["samples"])) == len(e["samples"]) for e in ro.events)
+    rm = compile_rollout([p0], [0], "midpoint", False)
+    steps = [e for e in rm.events if e["kind"] == sc.STEP]
+    assert len(steps) == 2 * p0.n_steps and rm.n_eps == sc.plan_sample(times, tg, 0.05, True, "midpoint").n_noise
+    assert steps[0]["x_buf"] == 4 and steps[0]["run_prior"] == 1 and steps[1]["x_buf"] == 2 and steps[1]["run_prior"] == 0
+
+
+@pytest.mark.parametrize("x3", [False, True])
+def test_packed_stage_plans_reproduce_the_convolutions(x3):
+    """The chunk / tap / column plan + packed weight matrix the TMA ring streams, replayed on the host, equals F.conv2d."""
+    from streamingflow_b200 import engine as en
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    sd = {k: v for k, v in so.recipe_state_dict(nnfo_shapes(64), 5, 1.0, torch.float32).items()}
+    H, W = 5, 6
+    rnd = lambda c: torch.randn(1, c, H, W)
+    q = (lambda t: t) if x3 else (lambda t: t.to(torch.bfloat16).float())
+    tol = 2e-4 if x3 else 1e-12
+    x, s, g1, g2, a, b = (rnd(64) for _ in range(6))
+    src = {-1: x, -2: s, -3: s, en.BUF_G1: g1, en.BUF_G2: g2, en.BUF_A: a, en.BUF_B: b, en.BUF_HH: a, en.BUF_T1: g1,
+           en.BUF_T2: g2, en.BUF_Q1: x, en.BUF_Y1: rnd(128), en.BUF_Q3: rnd(128), en.BUF_Y2: rnd(128)}
+    cell = en.cell_stage_defs(sd, "gru_c")
+    conv = lambda inp, key, pad: F.conv2d(q(inp).double(), q(sd[key]).double(), None, padding=pad)[0]
+    if x3:   # compare against exact fp64 convs; the split carries ~2^-16 relative error
+        conv = lambda inp, key, pad: F.conv2d(inp.double(), sd[key].double(), None, padding=pad)[0]
+    xs, ss = torch.cat([x, s], 1), torch.cat([s, s], 1)
+    acc = en.emulate_stage(cell[0], x3, src)
+    ref = torch.cat([conv(xs, "gru_c.conv_update_1.weight", 1), conv(xs, "gru_c.conv_reset_1.weight", 1),
+                     conv(ss, "gru_c.conv_update_2.weight", 1), conv(ss, "gru_c.conv_reset_2.weight", 1)])
+    # the cat[s,s] fold rounds (Wa+Wb) once instead of Wa and Wb separately: compare u2/r2 loosely in bf16 mode
+    assert (acc[:128] - ref[:128]).abs().max() < max(tol, 1e-9) * 10 + (0 if x3 else 0)
+    assert (acc[128:] - ref[128:]).abs().max() < (2e-4 if x3 else 5e-2)
+    acc = en.emulate_stage(cell[1], x3, src)
+    ref = torch.cat([conv(torch.cat([x, g1], 1), "gru_c.conv_state_tilde_1.weight", 1),
+                     conv(torch.cat([s, g2], 1), "gru_c.conv_state_tilde_2.weight", 1)])
+    assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 10
+    acc = en.emulate_stage(cell[3], x3, src)
+    ref = conv(torch.cat([a, b], 1), "gru_c.trusting_gate.0.layers.0.weight", 3)
+    assert (acc[:64] - ref).abs().max() < max(tol, 1e-9) * 30
+    acc = en.emulate_stage(cell[5], x3, src)
+    ref = torch.cat([conv(g2, "gru_c.trusting_gate.0.layers.6.weight", 1),
+                     conv(torch.cat([a, b], 1), "gru_c.trusting_gate.0.projection.0.weight", 0)])
+    assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 10
+    prior = en.prior_stage_defs(sd, "p_model")
+    acc = en.emulate_stage(prior[3], x3, src)           # q4: 128 -> 128 with BN folded
+    w4, b4 = en._bn_fold(sd, "p_model.model.2.layers.conv_2")
+    ref = F.conv2d((src[en.BUF_Q3] if x3 else q(src[en.BUF_Q3])).double(), (w4 if x3 else q(w4)).double(), None, padding=1)[0]
+    assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 30
+    bn = so._bn_eval(sd, "p_model.model.2.layers.conv_2.norm", F.conv2d(src[en.BUF_Q3], sd["p_model.model.2.layers.conv_2.conv.weight"], None, padding=1))
+    assert (F.conv2d(src[en.BUF_Q3], w4, b4, padding=1) - bn).abs().max() < 1e-4
+
+
+def _tiny_module(z, dtype):
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+
+    C = int(z["C"])
+    m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval().to(dtype)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(so.recipe_state_dict(shapes, int(z["seed"]), float(z["gain"]), dtype), strict=True)
+    m.gru_ode.__dict__["_engine_factory"] = lambda sd, H, W, n, prec, dev: OracleBackend(sd, H, W, n, prec, dev, dtype)
+    return m
+
+
+def test_module_glue_reproduces_reference_output(golden_dir, monkeypatch):
+    """FuturePredictionODE.forward of the product (batched rollout, host schedule, pre-drawn noise, window selection,
+    torch encoder / decoder / refinement) with the oracle standing in for the CUDA engine == the reference's output."""
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C, H, B, seed = int(z["C"]), int(z["H"]), int(z["B"]), int(z["seed"])
+    dtype = torch.float64
+    m = _tiny_module(z, dtype)
+    tape = [so.recipe_array(f"eps{i}", (C, H // 4, H // 4), seed, torch.float32) for i in range(64)]
+    drawn = {}
+
+    def fake_noise(n, h, w, device):       # the fixture's noise tape stands in for torch's RNG, in slot order
+        drawn["n"] = n
+        return torch.stack(tape[:n]).to(torch.float32)
+
+    monkeypatch.setattr(m.gru_ode, "_draw_noise", fake_noise)
+    # fp32 eps tape (as the engine consumes) vs the fp64 reference tape differ by rounding: regenerate the tape in fp64
+    m.gru_ode._draw_noise = lambda n, h, w, device: (drawn.__setitem__("n", n) or torch.stack(
+        [so.recipe_array(f"eps{i}", (C, H // 4, H // 4), seed, torch.float64) for i in range(n)]))
+    cam = so.recipe_array("cam", (B, 3, C, H, H), seed, dtype)
+    lid = so.recipe_array("lidar", (B, 5, C, H, H), seed, dtype)
+    with torch.no_grad():
+        x, aux = m(torch.zeros(B, 1, C, H, H, dtype=dtype), cam, lid, torch.from_numpy(z["camera_timestamp"]),
+                   torch.from_numpy(z["lidar_timestamp"]), torch.from_numpy(z["target_timestamp"]))
+    assert aux == 0 and drawn["n"] == int(z["n_eps"])
+    ref = torch.from_numpy(z["x_f64"])
+    assert ((x - ref).abs().max() / ref.abs().max()).item() < 1e-11
+
+
+def test_module_requires_cuda_and_has_no_fallback():
+    from streamingflow_b200._lib import SfError
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+
+    m = FuturePredictionODE(64, 64, 4, make_cfg(64)).eval()
+    B, H = 1, 8
+    with pytest.raises(SfError):
+        m(torch.zeros(B, 1, 64, H, H), torch.zeros(B, 1, 64, H, H), None, torch.zeros(B, 1, dtype=torch.float64), None,
+          torch.zeros(B, 1, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        m.gru_ode.p_model(torch.zeros(1, 64, 2, 2))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from streamingflow_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "sf_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(sf_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert os.path.exists(_lib.LIB_PATH), "libsf_b200.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.sf_abi_version.restype = ctypes.c_int
+    assert lib.sf_abi_version() == _lib.SF_ABI_VERSION
