@@ -132,6 +132,8 @@ class NNFOwithBayesianJumps(nn.Module):
         # engine options (not part of the reference API)
         self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
         self.noise = "reference"
+        self.record_all = False                         # debug: keep the state after every event (last_trace)
+        self.last_trace = None
         self.__dict__["_engines"] = {}
         self.__dict__["_engine_factory"] = None        # tests inject a checker backend here; the product path never does
         self.last_rollout = None
@@ -281,7 +283,7 @@ class NNFOwithBayesianJumps(nn.Module):
         dev = hx_obs.device
         plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-        ro = compile_rollout(plans, base, self.solver, bool(self.impute))
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all)
         eng = self._engine_for(h, w, B, dev)
         eng.bind_observations(hx_obs)
         eng.zero_state(0)
@@ -292,6 +294,8 @@ class NNFOwithBayesianJumps(nn.Module):
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
         sel = eng.unpack_path(flat).view(B, T, c, h, w)
+        if self.record_all:
+            self.last_trace = [eng.unpack_path(slots) for slots in ro.trace_slots]
         return eng.unpack_f32(eng.state32[0], B), sel
 
     def forward(self, times, input, obs, delta_t, T, return_path=True):

@@ -31,9 +31,12 @@ class Rollout:
     n_jumps: int = 0
     n_cell_evals: int = 0
     n_prior_evals: int = 0
+    trace_slots: List[List[int]] = field(default_factory=list)  # record_all: per sample, per op: path slot
 
 
-def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool) -> Rollout:
+def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool,
+                    record_all: bool = False) -> Rollout:
+    """record_all additionally records the state after EVERY op (debug / parity traces)."""
     ro = Rollout()
     per_sample: List[List[dict]] = []
     eps = 0
@@ -46,6 +49,12 @@ def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver
                 ro.n_path += 1
             slots.append(picked[op_idx])
         ro.out_slots.append(slots)
+        if record_all:
+            for i in range(len(plan.ops)):
+                if i not in picked:
+                    picked[i] = ro.n_path
+                    ro.n_path += 1
+            ro.trace_slots.append([picked[i] for i in range(len(plan.ops))])
         evs: List[dict] = []
         for i, op in enumerate(plan.ops):
             rec = picked.get(i, -1)

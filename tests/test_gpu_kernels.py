@@ -1,0 +1,213 @@
+"""GPU bring-up and per-stage parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libsf_b200.so via ctypes); expected values come from the oracle (oracle/sf_oracle.py) evaluated in fp64 on the same
+seeded inputs, with the tensor-core operands' bf16 rounding emulated where a tight bound is wanted."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sf_oracle as so
+from oracle.shapes import nnfo_shapes
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from streamingflow_b200 import _lib as L
+
+    return L, L.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+# ------------------------------------------------------------------------------------------------ bring-up
+def test_device_is_blackwell_and_library_loads():
+    L, lib = _lib()
+    assert lib.sf_abi_version() == L.SF_ABI_VERSION
+    L.check(lib.sf_device_supported(torch.cuda.current_device()), "sf_device_supported")
+
+
+@pytest.mark.parametrize("y0,x0", [(0, 0), (-1, -1), (-3, 5), (10, 14)])
+def test_tma_box_lands_swizzled_with_zero_fill(y0, x0):
+    """A (rows x 8 px x 64 ch) box of an NHWC bf16 image: pixel row r of the box sits at byte r*128, its 16-byte chunk j
+    at ((j ^ (r & 7)) * 16) (SWIZZLE_128B), and out-of-image pixels read as zero (the convolution's padding)."""
+    L, lib = _lib()
+    n, H, W, Cc, rows = 2, 21, 19, 128, 18
+    img, c0 = 1, 64
+    act = torch.randn(n, H, W, Cc, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(rows * 8 * 128, dtype=torch.uint8, device="cuda")
+    L.check(lib.sf_diag_tma_dump(act.data_ptr(), n, H, W, Cc, img, y0, x0, c0, rows, out.data_ptr(), _stream()), "tma_dump")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint16).reshape(rows * 8, 8, 8)          # [pixel row][16B chunk][8 bf16]
+    ref = np.zeros((rows * 8, 8, 8), dtype=np.uint16)
+    a = act.cpu().view(torch.int16).numpy().view(np.uint16)
+    for r in range(rows * 8):
+        y, x = y0 + r // 8, x0 + r % 8
+        if 0 <= y < H and 0 <= x < W:
+            px = a[img, y, x, c0:c0 + 64].reshape(8, 8)
+            for j in range(8):
+                ref[r, j ^ (r & 7)] = px[j]
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n,kc", [(64, 1), (128, 2), (256, 3)])
+def test_single_umma_tile_product(n, kc):
+    """D[128, n] = A[128, 64*kc] . B[n, 64*kc]^T through TMA -> swizzled smem -> tcgen05.mma -> TMEM -> tcgen05.ld."""
+    L, lib = _lib()
+    a = torch.randn(128, 64 * kc, device="cuda").to(torch.bfloat16)
+    b = torch.randn(n, 64 * kc, device="cuda").to(torch.bfloat16)
+    d = torch.zeros(128, n, device="cuda")
+    L.check(lib.sf_diag_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, kc, _stream()), "diag_umma")
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    assert (d.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_layout_kernels_roundtrip():
+    L, lib = _lib()
+    n, Cc, H, W = 3, 64, 50, 50
+    src = torch.randn(n, Cc, H, W, device="cuda")
+    hi = torch.zeros(n, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    lo = torch.zeros_like(hi)
+    L.check(lib.sf_pack_nchw_f32(src.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, Cc, H, W, _stream()), "pack")
+    want_hi = src.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(hi, want_hi)
+    assert torch.equal(lo, (src.permute(0, 2, 3, 1) - want_hi.float()).to(torch.bfloat16))
+    nhwc = torch.randn(5, H, W, Cc, device="cuda")
+    slots = torch.tensor([4, 0, 2], dtype=torch.int32, device="cuda")
+    dst = torch.zeros(3, Cc, H, W, device="cuda")
+    L.check(lib.sf_unpack_nhwc_f32(nhwc.data_ptr(), dst.data_ptr(), slots.data_ptr(), 3, Cc, H, W, _stream()), "unpack")
+    assert torch.equal(dst, nhwc[[4, 0, 2]].permute(0, 3, 1, 2))
+
+
+# ------------------------------------------------------------------------------------------------ one event, every buffer
+def _engine(H, W, B, precision, seed=5):
+    from streamingflow_b200.engine import OdeEngine
+
+    sd = so.recipe_state_dict(nnfo_shapes(64), seed, 1.0, torch.float32)
+    hot = {k: v.cuda() for k, v in sd.items() if k.startswith(("gru_c", "gru_obs", "p_model"))}
+    return OdeEngine(hot, "", H, W, B, precision, torch.device("cuda")), {"g." + k: v.double() for k, v in sd.items()}
+
+
+def _nhwc_to_nchw(t):
+    return t.permute(0, 3, 1, 2).double().cpu()
+
+
+def _act(eng, buf, n):
+    hi, lo = eng.act[buf]
+    v = hi[:n].float()
+    if lo is not None:
+        v = v + lo[:n].float()
+    return _nhwc_to_nchw(v)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("kind", ["step", "jump"])
+@pytest.mark.parametrize("H,W", [(20, 13), (50, 50)])
+def test_one_event_every_intermediate_matches_oracle(precision, kind, H, W):
+    """Runs ONE event (6 cell stages + 5 prior stages + 2 SE layers) and checks every buffer a stage writes against the
+    oracle's corresponding tensor.  Sizes with ragged tiles (20x13: partial 16x8 tiles in both directions)."""
+    from streamingflow_b200 import engine as en
+
+    B = 3
+    eng, sd = _engine(H, W, B, precision)
+    g = torch.Generator().manual_seed(11)
+    state = 0.5 * torch.randn(B, 64, H, W, generator=g)
+    x = torch.tanh(torch.randn(B, 64, H, W, generator=g))
+    eps = torch.randn(B, 64, H, W, generator=g)
+    dts = [0.05, 0.2, 0.45]
+    eng.set_state(0, state.cuda())
+    eng.pack_into(en.BUF_X, x.cuda())
+    eng.bind_eps(eps.cuda().contiguous())
+    eng.ensure_path_slots(B)
+    ev = dict(kind=0 if kind == "step" else 1, samples=[0, 1, 2], x_img=[0, 1, 2], rec=[2, -1, 0], eps=[0, 1, 2], dt=dts,
+              x_buf=en.BUF_X, s_in=0, s_base=0, s_out=0, run_cell=1, run_prior=1, want_f32=1)
+    eng.run_rollout([ev])
+    torch.cuda.synchronize()
+    eng.check_errflag()
+
+    # oracle, with bf16-rounded conv operands in bf16 mode so the comparison is tight
+    ctx = so.operand_rounding(so.round_bf16) if precision == "bf16" else so.operand_rounding(so.round_bf16, split3=True)
+    cell = "g.gru_c" if kind == "step" else "g.gru_obs.gru_d"
+    taps = {}
+    xs, ss = x.double(), state.double()
+    if precision == "bf16":     # the engine's cell reads the bf16 copies of x and s as conv operands; fp32 s elementwise
+        pass
+    with torch.no_grad(), ctx:
+        mixed = so.dual_gru_mix(sd, cell, xs, ss, taps)
+        if kind == "step":
+            dtv = torch.tensor(dts, dtype=torch.float32).double()[:, None, None, None]
+            new = ss + dtv * (mixed - ss)
+        else:
+            new = mixed
+        y, params = so.infer_state(sd, "g.p_model", new, eps.double())
+    tol = 2e-2 if precision == "bf16" else 2e-4
+
+    def close(name, got, want, scale=None):
+        err = (got - want).abs().max().item() / (scale or max(want.abs().max().item(), 1e-6))
+        assert err < tol, f"{name}: rel err {err:.3e} (tol {tol})"
+        return err
+
+    close("a (rnn_state1)", _nhwc_to_nchw(eng.a32[:B]), taps["a"])
+    close("b (rnn_state2)", _nhwc_to_nchw(eng.b32[:B]), taps["b"])
+    close("h (gru2 hidden)", _act(eng, en.BUF_HH, B), taps["h"])
+    close("new state", _nhwc_to_nchw(eng.state32[0][:B]), new)
+    close("state bf16 copy", _act(eng, en.BUF_S0, B), new)
+    close("sampled input", _nhwc_to_nchw(eng.x32[:B]), y)
+    close("prior params", _nhwc_to_nchw(eng.params32[:B]), params)
+    close("x buffer", _act(eng, en.BUF_X, B), y)
+    rec = eng.unpack_path([2, 0]).double().cpu()
+    assert torch.equal(rec[0].float(), eng.state32[0][0].permute(2, 0, 1).cpu()) and torch.equal(rec[1].float(), eng.state32[0][2].permute(2, 0, 1).cpu())
+
+
+def test_batch_composition_does_not_change_a_sample():
+    """Size-independent property: a sample's trajectory is bit-identical whether it is integrated alone or inside a
+    batch, in any position (tiles never mix samples; no batch-dependent reduction order)."""
+    from streamingflow_b200 import engine as en
+
+    H = W = 50
+    eng, _ = _engine(H, W, 4, "bf16")
+    g = torch.Generator().manual_seed(3)
+    state = 0.5 * torch.randn(4, 64, H, W, generator=g).cuda()
+    x = torch.tanh(torch.randn(4, 64, H, W, generator=g)).cuda()
+    eps = torch.randn(4, 64, H, W, generator=g).cuda()
+
+    def run(order):
+        eng.set_state(0, state[order])
+        eng.pack_into(en.BUF_X, x[order])
+        eng.bind_eps(eps[order].contiguous())
+        n = len(order)
+        ev = dict(kind=0, samples=list(range(n)), x_img=list(range(n)), rec=[-1] * n, eps=list(range(n)), dt=[0.3] * n,
+                  x_buf=en.BUF_X, s_in=0, s_base=0, s_out=0, run_cell=1, run_prior=1, want_f32=1)
+        eng.run_rollout([ev, ev])
+        torch.cuda.synchronize()
+        return eng.state32[0][:n].clone(), eng.x32[:n].clone()
+
+    s_all, x_all = run([0, 1, 2, 3])
+    s_perm, x_perm = run([2, 0, 3, 1])
+    assert torch.equal(s_perm, s_all[[2, 0, 3, 1]]) and torch.equal(x_perm, x_all[[2, 0, 3, 1]])
+    s_one, x_one = run([1])
+    assert torch.equal(s_one[0], s_all[1]) and torch.equal(x_one[0], x_all[1])
+
+
+def test_zero_dt_step_keeps_the_state():
+    from streamingflow_b200 import engine as en
+
+    H, W = 24, 16
+    eng, _ = _engine(H, W, 1, "bf16")
+    s = torch.randn(1, 64, H, W).cuda()
+    eng.set_state(0, s)
+    eng.pack_into(en.BUF_X, torch.randn(1, 64, H, W).cuda())
+    ev = dict(kind=0, samples=[0], x_img=[0], rec=[-1], eps=[0], dt=[0.0], x_buf=en.BUF_X, s_in=0, s_base=0, s_out=0,
+              run_cell=1, run_prior=0, want_f32=0)
+    eng.run_rollout([ev])
+    torch.cuda.synchronize()
+    assert torch.equal(eng.state32[0][0].permute(2, 0, 1), s[0])
