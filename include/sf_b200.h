@@ -87,7 +87,7 @@ typedef enum {
   SF_F32_A = 2,         /* rnn_state1 (GRU-1 output)                                                      */
   SF_F32_B = 3,         /* rnn_state2 (decoder of GRU-2)                                                  */
   SF_F32_PATH = 4,      /* recorded states [slot][H][W][C]                                                */
-  SF_F32_SE_SUMS = 5,   /* [2][max_images][2C] channel sums for the two SE layers                         */
+  SF_F32_SE_SUMS = 5,   /* [2][max_images][64][2C] per-block partial channel sums of the two SE layers    */
   SF_F32_EPS = 6,       /* standard-normal noise, NCHW [slot][C][H][W] (torch's generation order)         */
   SF_F32_X = 7,         /* optional fp32 copy of the sampled input x  (infer_state API)                   */
   SF_F32_PARAMS = 8,    /* optional fp32 p_model output [image][H][W][2C] (infer_state API)               */

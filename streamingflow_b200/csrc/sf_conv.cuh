@@ -2,16 +2,18 @@
 //
 // One launch = one conv stage of an event over all active samples:
 //   M = 128 output pixels per tile (16 rows x 8 columns of the NHWC grid; TMEM lane m <-> pixel (m/8, m%8)),
-//   N = up to 256 fp32 accumulator columns in TMEM, double buffered (2 x 256 of the SM's 512 columns),
+//   N = up to 256 fp32 accumulator columns in TMEM; the SM's 512 columns hold S = 2 (N <= 256) or 4 (N <= 128)
+//       accumulator stages, each owned by its own epilogue warpgroup,
 //   K = sum over "chunks": 64 input channels of one activation buffer x RxR taps.
 // A operand: for every horizontal tap dx the producer TMA-loads ONE box of (16+R-1) rows x 8 pixels x 64 ch
 //   (128 B per pixel, SWIZZLE_128B; out-of-image pixels are zero-filled by TMA = the conv's zero padding).
 //   A vertical tap dy is then just a 1024-byte (8 pixel-rows) offset of the UMMA descriptor into that box, so
 //   every descriptor start stays 1024-byte aligned.  R loads serve R*R taps.
 // B operand: packed weights [rows][64] bf16, one TMA tile of n*nrep rows per tap, streamed through its own ring.
-// Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
-//   warps 4..7 = epilogue (one thread per pixel: its TMEM lane holds all output channels of that pixel, so
-//   LayerNorm / softmax-mix / GRU blends are thread-local).  Persistent over tiles, static round-robin.
+//   Tap order is rotated per tile position so that the CTAs do not all pull the same weight tile from L2 at once.
+// Warp roles: warps [0,4S) = S epilogue warpgroups, then TMA producer (one lane), MMA issuer (one lane), TMEM allocator;
+//   epilogue: (one thread per pixel: its TMEM lane holds all output channels of that pixel,
+//   so LayerNorm / softmax-mix / GRU blends are thread-local).  Persistent over tiles, static round-robin.
 #pragma once
 #include "sf_ptx.cuh"
 #include "../../include/sf_b200.h"
@@ -23,10 +25,12 @@ constexpr int TILE_W = 8;
 constexpr int KC = 64;            // channels per K-chunk (128 bytes of bf16)
 constexpr int ROW_BYTES = 128;    // one pixel of one chunk
 constexpr int VEC_MAX = 512;      // per-stage constant vector (bias / LN / gate weights), floats
-constexpr int ACC_STAGE_COLS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_RING = 16;
 
 struct ChunkK {
   int R, n, nrep, col, wrow, init, c0, img_sel;   // img_sel: 0 = sample id, 1 = the event's x image index
+  int tb;                                         // taps (along dy) per B tile: 1 or R
 };
 
 struct EpiArgs {
@@ -61,83 +65,88 @@ struct alignas(64) StageParams {
   const float* vec;
   int nvec;
   int a_slot_bytes, b_slot_bytes, nA, nB;
-  int acc_stages;
   int* err;
   EpiArgs e;
 };
 
+// number of accumulator stages (= epilogue warpgroups) per epilogue kind: 256-column stages get 2, the rest 4
+__host__ __device__ constexpr int acc_stages_for(int epi) { return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ) ? 2 : 4; }
+
 // ------------------------------------------------------------------------------------------------
-// epilogue helpers (one thread = one pixel)
+// epilogue helpers (one thread = one pixel; 16 channels at a time)
 // ------------------------------------------------------------------------------------------------
 template <bool X3>
 __device__ __forceinline__ void store_act16(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float (&v)[16]) {
   uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-  uint4* ph = reinterpret_cast<uint4*>(hi + off);
-  ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
-  ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  stg256(hi + off, h);
   if (X3) {
     uint32_t l[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) l[i] = pack_bf16x2(v[2 * i] - bf16_lo_f(h[i]), v[2 * i + 1] - bf16_hi_f(h[i]));
-    uint4* pl = reinterpret_cast<uint4*>(lo + off);
-    pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
-    pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    stg256(lo + off, l);
   }
 }
 template <bool X3>
 __device__ __forceinline__ void load_act16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&v)[16]) {
-  const uint4* ph = reinterpret_cast<const uint4*>(hi + off);
-  uint4 a = ph[0], b = ph[1];
-  uint32_t h[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[8];
+  ldg256(hi + off, h);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[2 * i] = bf16_lo_f(h[i]); v[2 * i + 1] = bf16_hi_f(h[i]); }
   if (X3) {
-    const uint4* pl = reinterpret_cast<const uint4*>(lo + off);
-    uint4 c = pl[0], d = pl[1];
-    uint32_t l[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    uint32_t l[8];
+    ldg256(lo + off, l);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo_f(l[i]); v[2 * i + 1] += bf16_hi_f(l[i]); }
   }
 }
 __device__ __forceinline__ void load_f32x16(const float* p, float (&v)[16]) {
-  const float4* q = reinterpret_cast<const float4*>(p);
+  uint32_t a[8], b[8];
+  ldg256(p, a);
+  ldg256(p + 8, b);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { float4 t = q[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+  for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(a[i]); v[8 + i] = __uint_as_float(b[i]); }
 }
 __device__ __forceinline__ void store_f32x16(float* p, const float (&v)[16]) {
-  float4* q = reinterpret_cast<float4*>(p);
+  uint32_t a[8], b[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 8; ++i) { a[i] = __float_as_uint(v[i]); b[i] = __float_as_uint(v[8 + i]); }
+  stg256(p, a);
+  stg256(p + 8, b);
 }
 __device__ __forceinline__ void zero16(float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.0f;
 }
-
-// LayerNorm over the 64 channels of one pixel (convolutions.py:299-304: biased variance, eps 1e-6) + exact GELU.
-__device__ __forceinline__ void ln_gelu64(float (&v)[64], const float* w, const float* b) {
-  float mean = 0.0f;
+// 16 floats of the per-stage constant vector from shared memory (128-bit broadcast loads)
+__device__ __forceinline__ void vec16(const float* vec, int off, float (&v)[16]) {
+  const float4* q = reinterpret_cast<const float4*>(vec + off);
 #pragma unroll
-  for (int i = 0; i < 64; ++i) mean += v[i];
-  mean *= (1.0f / 64.0f);
-  float var = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) { float d = v[i] - mean; var += d * d; }
-  var *= (1.0f / 64.0f);
-  const float rstd = 1.0f / sqrtf(var + 1e-6f);
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = gelu_erf(w[i] * ((v[i] - mean) * rstd) + b[i]);
+  for (int i = 0; i < 4; ++i) { const float4 t = q[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
 }
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+
+// LayerNorm statistics over the 64 accumulator columns [col, col+64) of this thread's pixel, two passes over TMEM
+// (convolutions.py:299-304: biased variance, eps 1e-6).  Returns mean and 1/sqrt(var + eps).
+__device__ __forceinline__ void ln_stats64(uint32_t taddr, float& mean, float& rstd) {
+  float s = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {
+    float a[16], b[16];
+    tmem_ld16x2(taddr + j * 32, taddr + j * 32 + 16, a, b);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float t[16];
-    tmem_ld16(taddr + j * 16, t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[j * 16 + i] = t[i];
+    for (int i = 0; i < 16; ++i) s += a[i] + b[i];
   }
+  mean = s * (1.0f / 64.0f);
+  float q = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {
+    float a[16], b[16];
+    tmem_ld16x2(taddr + j * 32, taddr + j * 32 + 16, a, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float da = a[i] - mean, db = b[i] - mean; q = fmaf(da, da, q); q = fmaf(db, db, q); }
+  }
+  rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
 }
 
 struct PixelCtx {
@@ -162,14 +171,15 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       const int ucol = g * 128, rcol = g * 128 + 64;
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-        float u[16], r[16], s[16];
-        tmem_ld16(taddr + ucol + j * 16, u);
-        tmem_ld16(taddr + rcol + j * 16, r);
+        float u[16], r[16], s[16], bu[16], br[16];
         if (c.valid) load_f32x16(e.s_in + c.pix * 64 + j * 16, s); else zero16(s);
+        tmem_ld16x2(taddr + ucol + j * 16, taddr + rcol + j * 16, u, r);
+        vec16(vec, ucol + j * 16, bu);
+        vec16(vec, rcol + j * 16, br);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          u[i] = sigmoidf_(u[i] + vec[ucol + j * 16 + i]);
-          r[i] = (1.0f - sigmoidf_(r[i] + vec[rcol + j * 16 + i])) * s[i];
+          u[i] = sigmoidf_(u[i] + bu[i]);
+          r[i] = (1.0f - sigmoidf_(r[i] + br[i])) * s[i];
         }
         if (c.valid) {
           store_act16<X3>(e.out_h[g], e.out_l[g], c.pix * 64 + j * 16, u);           // u1 / u2
@@ -181,18 +191,23 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     // columns: [0,64) s~1 | [64,128) s~2 ; vec = [bias~1, bias~2]; in[0]=u1, in[1]=u2; out[0]=a, out[1]=h
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      float t1[16], t2[16], s[16], u1[16], u2[16];
-      tmem_ld16(taddr + j * 16, t1);
-      tmem_ld16(taddr + 64 + j * 16, t2);
+      float t1[16], t2[16], s[16], u1[16], u2[16], b1[16], b2[16];
       if (c.valid) {
         load_f32x16(e.s_in + c.pix * 64 + j * 16, s);
         load_act16<X3>(e.in_h[0], e.in_l[0], c.pix * 64 + j * 16, u1);
         load_act16<X3>(e.in_h[1], e.in_l[1], c.pix * 64 + j * 16, u2);
+      } else {
+        zero16(s); zero16(u1); zero16(u2);
+      }
+      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, t1, t2);
+      vec16(vec, j * 16, b1);
+      vec16(vec, 64 + j * 16, b2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          t1[i] = (1.0f - u1[i]) * s[i] + u1[i] * (t1[i] + vec[j * 16 + i]);
-          t2[i] = (1.0f - u2[i]) * s[i] + u2[i] * (t2[i] + vec[64 + j * 16 + i]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        t1[i] = (1.0f - u1[i]) * s[i] + u1[i] * (t1[i] + b1[i]);
+        t2[i] = (1.0f - u2[i]) * s[i] + u2[i] * (t2[i] + b2[i]);
+      }
+      if (c.valid) {
         store_f32x16(e.a32 + c.pix * 64 + j * 16, t1);
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, t1);
         store_act16<X3>(e.out_h[1], e.out_l[1], c.pix * 64 + j * 16, t2);
@@ -201,50 +216,51 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
   } else if constexpr (EPI == SF_EPI_DECODE) {
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      float b[16];
+      float b[16], bb[16];
       tmem_ld16(taddr + j * 16, b);
+      vec16(vec, j * 16, bb);
       if (c.valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) b[i] += vec[j * 16 + i];
+        for (int i = 0; i < 16; ++i) b[i] += bb[i];
         store_f32x16(e.b32 + c.pix * 64 + j * 16, b);
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, b);
       }
     }
   } else if constexpr (EPI == SF_EPI_LNGELU) {
-    float v[64];
-    tmem_ld64(taddr, v);
-    ln_gelu64(v, vec, vec + 64);
-    if (c.valid) {
+    float mean, rstd;
+    ln_stats64(taddr, mean, rstd);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      float v[16], w[16], b[16];
+      tmem_ld16(taddr + j * 16, v);
+      vec16(vec, j * 16, w);
+      vec16(vec, 64 + j * 16, b);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) t[i] = v[j * 16 + i];
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, t);
-      }
+      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
+      if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, v);
     }
   } else if constexpr (EPI == SF_EPI_MIX) {
     // columns: [0,64) 3x3 trunk conv | [64,128) 1x1 projection of cat[a,b];
     // vec = [LN w (64), LN b (64), gate row 0 (64), gate row 1 (64)]
-    float l0 = 0.0f, l1 = 0.0f;
-    {
-      float v[64];
-      tmem_ld64(taddr, v);
-      ln_gelu64(v, vec, vec + 64);
+    float mean, rstd, l0 = 0.0f, l1 = 0.0f;
+    ln_stats64(taddr, mean, rstd);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      float v[16], pr[16], w[16], b[16], g0w[16], g1w[16];
+      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, v, pr);
+      vec16(vec, j * 16, w);
+      vec16(vec, 64 + j * 16, b);
+      vec16(vec, 128 + j * 16, g0w);
+      vec16(vec, 192 + j * 16, g1w);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float pr[16];
-        tmem_ld16(taddr + 64 + j * 16, pr);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float yv = v[j * 16 + i] + gelu_erf(pr[i]);
-          l0 = fmaf(vec[128 + j * 16 + i], yv, l0);
-          l1 = fmaf(vec[192 + j * 16 + i], yv, l1);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float yv = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i])) + gelu_erf(pr[i]);
+        l0 = fmaf(g0w[i], yv, l0);
+        l1 = fmaf(g1w[i], yv, l1);
       }
     }
     if (c.valid) {
-      const float g0 = 1.0f / (1.0f + expf(l1 - l0));     // softmax over the two logits, channel 0
+      const float g0 = __fdividef(1.0f, 1.0f + __expf(l1 - l0));     // softmax over the two logits, channel 0
       const float g1 = 1.0f - g0;
       const float dt = p.dt[c.bi];
       const int slot = p.rec_slot ? p.rec_slot[c.bi] : -1;
@@ -273,11 +289,12 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     const int n = e.n_out;
 #pragma unroll 1
     for (int j = 0; j < n / 16; ++j) {
-      float v[16];
+      float v[16], b[16];
       tmem_ld16(taddr + j * 16, v);
+      vec16(vec, j * 16, b);
       if (c.valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + vec[j * 16 + i]);
+        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]);
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * n + j * 16, v);
       }
     }
@@ -285,24 +302,26 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     // columns: [0,128) conv_2 (BN folded) | [128,256) 1x1 projection ; vec = [bn bias (128), proj bias (128)]
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
-      float v[16], q[16];
-      tmem_ld16(taddr + j * 16, v);
-      tmem_ld16(taddr + 128 + j * 16, q);
+      float v[16], q[16], b[16], pb[16];
+      tmem_ld16x2(taddr + j * 16, taddr + 128 + j * 16, v, q);
+      vec16(vec, j * 16, b);
+      vec16(vec, 128 + j * 16, pb);
       if (c.valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + vec[j * 16 + i]) + (q[i] + vec[128 + j * 16 + i]);
+        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + (q[i] + pb[i]);
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 128 + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_RES_ID) {
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
-      float v[16], r[16];
+      float v[16], r[16], b[16];
+      if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], c.pix * 128 + j * 16, r); else zero16(r);
       tmem_ld16(taddr + j * 16, v);
+      vec16(vec, j * 16, b);
       if (c.valid) {
-        load_act16<X3>(e.in_h[0], e.in_l[0], c.pix * 128 + j * 16, r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + vec[j * 16 + i]) + r[i];
+        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + r[i];
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 128 + j * 16, v);
       }
     }
@@ -313,21 +332,28 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     if (c.valid) eps = e.eps + (size_t)p.eps_slot[c.bi] * 64 * hw + (size_t)c.y * p.W + c.x;
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      float loc[16], raw[16];
-      tmem_ld16(taddr + j * 16, loc);
-      tmem_ld16(taddr + 64 + j * 16, raw);
+      float loc[16], raw[16], bl[16], br[16], ep[16];
+      if (c.valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ep[i] = __ldg(eps + (size_t)(j * 16 + i) * hw);
+      } else {
+        zero16(ep);
+      }
+      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, loc, raw);
+      vec16(vec, j * 16, bl);
+      vec16(vec, 64 + j * 16, br);
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          loc[i] = lrelu01(loc[i] + vec[j * 16 + i]);
-          raw[i] = lrelu01(raw[i] + vec[64 + j * 16 + i]);
+          loc[i] = lrelu01(loc[i] + bl[i]);
+          raw[i] = lrelu01(raw[i] + br[i]);
         }
         if (e.params32) {
           store_f32x16(e.params32 + c.pix * 128 + j * 16, loc);
           store_f32x16(e.params32 + c.pix * 128 + 64 + j * 16, raw);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) loc[i] = loc[i] + (softplus_(raw[i]) + 1e-8f) * __ldg(eps + (size_t)(j * 16 + i) * hw);
+        for (int i = 0; i < 16; ++i) loc[i] = loc[i] + (softplus_(raw[i]) + 1e-8f) * ep[i];
         store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, loc);
         if (e.x32) store_f32x16(e.x32 + c.pix * 64 + j * 16, loc);
       }
@@ -339,7 +365,9 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
 // the stage kernel
 // ------------------------------------------------------------------------------------------------
 template <int EPI, bool X3>
-__global__ void __launch_bounds__(256, 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
+__global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
+  constexpr int S = acc_stages_for(EPI);
+  constexpr uint32_t STAGE_COLS = TMEM_COLS / S;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nA = p.nA, nB = p.nB;
@@ -352,18 +380,20 @@ __global__ void __launch_bounds__(256, 1) conv_stage_kernel(const __grid_constan
   uint64_t* b_full = a_empty + nA;
   uint64_t* b_empty = b_full + nB;
   uint64_t* acc_full = b_empty + nB;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp roles: [0, 4S) epilogue warpgroups (warp % 4 = TMEM lane quadrant), then producer, MMA issuer, TMEM allocator
+  constexpr int W_PROD = 4 * S, W_MMA = 4 * S + 1, W_ALLOC = 4 * S + 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128); }
+    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == W_ALLOC) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   for (int i = threadIdx.x; i < p.nvec; i += blockDim.x) vec_s[i] = p.vec[i];
   tc_fence_before();
   __syncthreads();
@@ -372,14 +402,15 @@ __global__ void __launch_bounds__(256, 1) conv_stage_kernel(const __grid_constan
 
   const int tpi = p.tiles_x * p.tiles_y;
   const int ntiles = p.n_active * tpi;
-  const int acc2 = (p.acc_stages == 2);
+  const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
+  const uint32_t a_smem0 = smem_u32(a_base), b_smem0 = smem_u32(b_base);
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer (lean loop: ring indices are counters, no div/mod per tap) =====================
       for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
       tma_prefetch_desc(&p.wmap);
-      uint32_t ia = 0, ib = 0;
+      uint32_t sa = 0, pa = 1, sb = 0, pb = 1;      // slot index and the parity to wait for on the EMPTY barrier
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int bi = tile / tpi, rem = tile - bi * tpi;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -387,84 +418,96 @@ __global__ void __launch_bounds__(256, 1) conv_stage_kernel(const __grid_constan
         const int sid = p.sample_id[bi], ximg = p.x_img[bi];
         for (int c = 0; c < p.nchunk; ++c) {
           const ChunkK ck = p.chunk[c];
-          const int pad = (ck.R - 1) >> 1;
+          const int R = ck.R, pad = (R - 1) >> 1;
           const int img = ck.img_sel ? ximg : sid;
-          const uint32_t a_bytes = (uint32_t)(TILE_H + ck.R - 1) * TILE_W * ROW_BYTES;
-          const uint32_t b_rows = (uint32_t)ck.n * ck.nrep;
-          for (int dx = 0; dx < ck.R; ++dx) {
-            const uint32_t sa = ia % nA, pha = (ia / nA) & 1;
-            mbar_wait(smem_u32(a_empty + sa), pha ^ 1, p.err, 1);
-            mbar_expect_tx(smem_u32(a_full + sa), a_bytes);
-            tma_load_4d(smem_u32(a_base + (size_t)sa * p.a_slot_bytes), &p.amap[c], smem_u32(a_full + sa), ck.c0,
-                        x0 + dx - pad, y0 - pad, img);
-            ++ia;
-            for (int dy = 0; dy < ck.R; ++dy) {
-              const uint32_t sb = ib % nB, phb = (ib / nB) & 1;
-              mbar_wait(smem_u32(b_empty + sb), phb ^ 1, p.err, 2);
-              mbar_expect_tx(smem_u32(b_full + sb), b_rows * ROW_BYTES);
-              const int row0 = ck.wrow + (dx * ck.R + dy) * (int)b_rows;
-              const uint32_t dst = smem_u32(b_base + (size_t)sb * p.b_slot_bytes);
-              for (uint32_t j = 0; j < b_rows / 64; ++j)
-                tma_load_2d(dst + j * 64 * ROW_BYTES, &p.wmap, smem_u32(b_full + sb), 0, row0 + (int)j * 64);
-              ++ib;
+          const uint32_t a_bytes = (uint32_t)(TILE_H + R - 1) * TILE_W * ROW_BYTES;
+          const int tap_rows = ck.n * ck.nrep;                  // weight rows of one tap
+          const int grp_rows = tap_rows * ck.tb;                // rows of one B tile (tb taps)
+          const int ngrp = R / ck.tb;                           // B tiles per dx column (R or 1)
+          int dx = rem % R, g0 = (ck.tb == 1) ? (rem / R) % R : 0;     // tap rotation (same formula in the MMA warp)
+          for (int i = 0; i < R; ++i) {
+            mbar_wait(a_empty0 + sa * 8, pa, p.err, 1);
+            mbar_expect_tx(a_full0 + sa * 8, a_bytes);
+            tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 + dx - pad, y0 - pad, img);
+            if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
+            int gi = g0;
+            for (int j = 0; j < ngrp; ++j) {
+              mbar_wait(b_empty0 + sb * 8, pb, p.err, 2);
+              mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
+              int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows;
+              uint32_t dst = b_smem0 + sb * p.b_slot_bytes;
+              for (int q = 0; q < grp_rows; q += 64, row += 64, dst += 64 * ROW_BYTES)
+                tma_load_2d(dst, &p.wmap, b_full0 + sb * 8, 0, row);
+              if (++sb == (uint32_t)nB) { sb = 0; pb ^= 1; }
+              if (++gi == ngrp) gi = 0;
             }
+            if (++dx == R) dx = 0;
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      uint32_t ia = 0, ib = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t as = acc2 ? (it & 1) : 0;
-        const uint32_t aph = acc2 ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait(smem_u32(acc_empty + as), aph ^ 1, p.err, 3);
+      // descriptor high word is constant: SBO = 1024 B (>>4 = 64), version 1 (bit 46), SWIZZLE_128B (2 << 61)
+      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 1;   // parities to wait for on the FULL barriers / acc EMPTY
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int rem = tile % tpi;
+        mbar_wait(smem_u32(acc_empty + as), pacc, p.err, 3);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + as * ACC_STAGE_COLS;
+        const uint32_t d_base = tmem_base + as * STAGE_COLS;
         for (int c = 0; c < p.nchunk; ++c) {
           const ChunkK ck = p.chunk[c];
+          const int R = ck.R;
           const uint32_t idesc = make_idesc_bf16(128, (uint32_t)ck.n);
+          const uint32_t d_addr = d_base + ck.col;
+          const uint32_t tap_lo = (uint32_t)(ck.n * ck.nrep * ROW_BYTES) >> 4;    // descriptor-lo step per tap inside a B tile
+          const uint32_t rep_lo = (uint32_t)(ck.n * ROW_BYTES) >> 4;
+          const int ngrp = R / ck.tb;
+          const int g0 = (ck.tb == 1) ? (rem / R) % R : 0;
           uint32_t accumulate = ck.init ? 0u : 1u;
-          for (int dx = 0; dx < ck.R; ++dx) {
-            const uint32_t sa = ia % nA, pha = (ia / nA) & 1;
-            mbar_wait(smem_u32(a_full + sa), pha, p.err, 4);
-            tc_fence_after();
-            const uint32_t a_slot = smem_u32(a_base + (size_t)sa * p.a_slot_bytes);
-            for (int dy = 0; dy < ck.R; ++dy) {
-              const uint32_t sb = ib % nB, phb = (ib / nB) & 1;
-              mbar_wait(smem_u32(b_full + sb), phb, p.err, 5);
+          for (int i = 0; i < R; ++i) {
+            mbar_wait(a_full0 + sa * 8, pa, p.err, 4);
+            const uint32_t a_lo0 = ((a_smem0 + sa * p.a_slot_bytes) & 0x3FFFFu) >> 4;
+            int gi = g0;
+            for (int j = 0; j < ngrp; ++j) {
+              mbar_wait(b_full0 + sb * 8, pb, p.err, 5);
               tc_fence_after();
-              const uint32_t a_addr = a_slot + (uint32_t)dy * TILE_W * ROW_BYTES;
-              const uint32_t b_slot = smem_u32(b_base + (size_t)sb * p.b_slot_bytes);
-              for (int rep = 0; rep < ck.nrep; ++rep) {
-                const uint32_t b_addr = b_slot + (uint32_t)rep * ck.n * ROW_BYTES;
+              uint32_t b_lo = ((b_smem0 + sb * p.b_slot_bytes) & 0x3FFFFu) >> 4;
+              uint32_t a_lo = a_lo0 + (uint32_t)(gi * ck.tb) * ((TILE_W * ROW_BYTES) >> 4);
+              for (int t = 0; t < ck.tb; ++t, a_lo += (TILE_W * ROW_BYTES) >> 4) {
+                for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes) per 64-channel chunk
-                  umma_bf16(d_base + ck.col, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
-                            accumulate);
-                  accumulate = 1u;
+                  for (uint32_t k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes = 2 descriptor units) per 64-channel chunk
+                    umma_bf16(d_addr, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (b_lo + 2 * k), idesc,
+                              accumulate);
+                    accumulate = 1u;
+                  }
                 }
               }
-              umma_commit(smem_u32(b_empty + sb));   // frees the weight tile once these MMAs retire
-              ++ib;
+              (void)tap_lo;
+              umma_commit(b_empty0 + sb * 8);        // frees the weight tile once these MMAs retire
+              if (++sb == (uint32_t)nB) { sb = 0; pb ^= 1; }
+              if (++gi == ngrp) gi = 0;
             }
-            umma_commit(smem_u32(a_empty + sa));
-            ++ia;
+            umma_commit(a_empty0 + sa * 8);
+            if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
           }
         }
         umma_commit(smem_u32(acc_full + as));
+        if (++as == (uint32_t)S) { as = 0; pacc ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> fused math -> global =====================
-    const int q = warp - 4;
+  } else if (warp < 4 * S) {
+    // ===================== epilogue warpgroup g owns accumulator stage g =====================
+    const int g = warp >> 2;
+    const int q = warp & 3;
     const int m = q * 32 + lane;
     const int r = m >> 3, cx = m & 7;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const uint32_t as = acc2 ? (it & 1) : 0;
-      const uint32_t aph = acc2 ? ((it >> 1) & 1) : (it & 1);
+    const uint32_t taddr = tmem_base + (uint32_t)g * STAGE_COLS + ((uint32_t)(q * 32) << 16);
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
       const int bi = tile / tpi, rem = tile - bi * tpi;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       PixelCtx c;
@@ -474,19 +517,18 @@ __global__ void __launch_bounds__(256, 1) conv_stage_kernel(const __grid_constan
       c.x = tx * TILE_W + cx;
       c.valid = (c.y < p.H) && (c.x < p.W);
       c.pix = ((size_t)c.sid * p.H + c.y) * p.W + c.x;
-      mbar_wait(smem_u32(acc_full + as), aph, p.err, 6);
+      mbar_wait(smem_u32(acc_full + g), aph, p.err, 6);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * ACC_STAGE_COLS + ((uint32_t)(q * 32) << 16);
       run_epilogue<EPI, X3>(p, vec_s, taddr, c);
       tc_fence_before();
-      mbar_arrive(smem_u32(acc_empty + as));
+      mbar_arrive(smem_u32(acc_empty + g));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
     float s = 0.0f;
 #pragma unroll
     for (int l = 0; l < LANES; ++l) s += red[l][threadIdx.x];
-    atomicAdd(sums + (size_t)bi * CH + threadIdx.x, s);
+    // per-block partial sums, combined in a fixed order by se_apply: deterministic (no float atomics)
+    sums[((size_t)bi * gridDim.x + blockIdx.x) * CH + threadIdx.x] = s;
   }
 }
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
 template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
                                                        __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
-                                                       const float* __restrict__ sums, const float* __restrict__ fc1,
+                                                       const float* __restrict__ sums, int n_partials, const float* __restrict__ fc1,
                                                        const float* __restrict__ fc2, const int* __restrict__ sample_id, int hw) {
   constexpr int HID = CH / 8;               // reduction 8
   constexpr int GROUPS = CH / 8;
@@ -55,7 +56,11 @@ __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __re
   __shared__ float mean_s[CH], hid_s[HID], scale_s[CH];
   const int bi = blockIdx.y;
   const int sid = sample_id[bi];
-  if (threadIdx.x < CH) mean_s[threadIdx.x] = sums[(size_t)bi * CH + threadIdx.x] / (float)hw;
+  if (threadIdx.x < CH) {
+    float t = 0.0f;
+    for (int k = 0; k < n_partials; ++k) t += sums[((size_t)bi * n_partials + k) * CH + threadIdx.x];
+    mean_s[threadIdx.x] = t / (float)hw;
+  }
   __syncthreads();
   if (threadIdx.x < HID) {
     float a = 0.0f;

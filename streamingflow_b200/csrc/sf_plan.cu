@@ -56,6 +56,7 @@ struct Stage {
   std::vector<int> io;
   CUtensorMap wmap;
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
+  std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
 };
 struct SeDef {
   bool defined = false;
@@ -66,6 +67,7 @@ struct SeDef {
 
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_AREA = 512;
+constexpr int B_TILE_MAX = 56 * 1024;
 
 }  // namespace
 
@@ -168,7 +170,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
     int rc = encode_act_map(p, buf, ck.plane, ck.R, &sp.amap[c]);
     if (rc) return rc;
     if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
-    sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0};
+    sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c]};
   }
   sp.wmap = st.wmap;
   sp.H = p->g.H;
@@ -189,7 +191,6 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.b_slot_bytes = st.b_slot;
   sp.nA = st.nA;
   sp.nB = st.nB;
-  sp.acc_stages = 2;
   sp.err = reinterpret_cast<int*>(p->f32[SF_F32_COUNT]);
   EpiArgs& e = sp.e;
   e.kind = ev->kind;
@@ -245,7 +246,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   StageKernel k = kernel_for(st.epi, x3);
   if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
   void* args[] = {&sp};
-  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(256), args, (size_t)st.smem, stream));
+  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::acc_stages_for(st.epi)), args, (size_t)st.smem, stream));
   p->last_launches += 1;
   return SF_OK;
 }
@@ -259,14 +260,14 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   const int hw = p->g.H * p->g.W;
   float* sums = reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]);
   if (!sums) return fail(SF_ERR_STATE, "SE sums buffer not bound");
-  sums += (size_t)which * p->g.max_images * CH;
+  constexpr int SE_MAX_PARTIALS = 64;
+  sums += (size_t)which * p->g.max_images * SE_MAX_PARTIALS * CH;
   const ActBuf& zi = p->act[se.in_buf];
   const ActBuf& yo = p->act[se.out_buf];
   if (!zi.hi || !yo.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
   const int* sid = table + ev->table_off;
-  SF_CUDA(cudaMemsetAsync(sums, 0, (size_t)ev->n_active * CH * sizeof(float), stream));
   int bpi = (hw + 16 * 8 - 1) / (16 * 8);     // ~8 pixels per thread-lane
-  if (bpi > 64) bpi = 64;
+  if (bpi > SE_MAX_PARTIALS) bpi = SE_MAX_PARTIALS;
   if (bpi < 1) bpi = 1;
   dim3 grid(bpi, ev->n_active);
   auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
@@ -279,10 +280,10 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   dim3 grid2(bpa, ev->n_active);
   if (x3) {
     se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
-    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, se.fc1, se.fc2, sid, hw);
+    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw);
   } else {
     se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
-    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, se.fc1, se.fc2, sid, hw);
+    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw);
   }
   SF_CUDA(cudaGetLastError());
   p->last_launches += 2;
@@ -362,10 +363,13 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   int a_slot = 0, b_slot = 0;
   for (const sf_chunk& c : st.chunks) {
     if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
-    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::ACC_STAGE_COLS) return fail(SF_ERR_INVALID, "bad chunk N / column range");
+    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::acc_stages_for(epilogue)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
-    const int a = (TILE_H + c.R - 1) * TILE_W * ROW_BYTES, b = c.n * c.nrep * ROW_BYTES;
+    // a whole dx column of taps travels as ONE weight tile when it is small enough: fewer barrier round trips per MMA
+    const int tb = (c.R * c.n * c.nrep * ROW_BYTES <= B_TILE_MAX) ? c.R : 1;
+    st.tb.push_back(tb);
+    const int a = (TILE_H + c.R - 1) * TILE_W * ROW_BYTES, b = tb * c.n * c.nrep * ROW_BYTES;
     a_slot = a > a_slot ? a : a_slot;
     b_slot = b > b_slot ? b : b_slot;
   }
@@ -375,11 +379,13 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.n_vec = n_vec;
   st.io.assign(io_bufs, io_bufs + n_io);
   const int fixed = 1024 + sf::VEC_MAX * 4 + BAR_AREA;
+  if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
   int nA = 3;
   int nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
   if (nB < 2) { nA = 2; nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot; }
-  if (nB > 8) nB = 8;
+  if (nB > sf::MAX_RING) nB = sf::MAX_RING;
   if (nB < 2) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
+  while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
   st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
   st.smem = fixed + nA * a_slot + nB * b_slot;
   int rc = encode_weight_map(w_packed, w_rows, &st.wmap);

@@ -212,7 +212,7 @@ class OdeEngine:
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
         self.state32 = [f32(B, H, W, Cc), f32(B, H, W, Cc)]
         self.a32, self.b32 = f32(B, H, W, Cc), f32(B, H, W, Cc)
-        self.se_sums = f32(2, B, 2 * Cc)
+        self.se_sums = f32(2, B, 64, 2 * Cc)          # per-block partial channel sums of the two SE layers
         self.x32, self.params32 = f32(B, H, W, Cc), f32(B, H, W, 2 * Cc)
         self.errflag = torch.zeros(1, dtype=torch.int32, device=self.device)
         for slot, t in ((L.F32_STATE0, self.state32[0]), (L.F32_STATE1, self.state32[1]), (L.F32_A, self.a32), (L.F32_B, self.b32),
