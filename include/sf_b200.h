@@ -148,6 +148,9 @@ int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n
 int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0,
                      int rows, void* out_smem_copy, void* stream);
 int sf_diag_umma(const void* a_bf16, const void* b_bf16, float* d, int n, int k_chunks, void* stream);
+/* experiment: 128 operand rows starting `shift` rows into a swizzled box, 8-row groups `sbo_rows` rows apart */
+int sf_diag_umma_shift(const void* a_bf16, const void* b_bf16, float* d, int n, int rows_a, int shift, int sbo_rows, int base_mode,
+                       void* stream);
 
 #ifdef __cplusplus
 }

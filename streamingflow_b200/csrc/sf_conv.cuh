@@ -1,19 +1,23 @@
 // sf_conv.cuh -- the implicit-GEMM convolution stage kernel (tcgen05 + TMEM + TMA) and its fused epilogues.
 //
 // One launch = one conv stage of an event over all active samples:
-//   M = 128 output pixels per tile (16 rows x 8 columns of the NHWC grid; TMEM lane m <-> pixel (m/8, m%8)),
-//   N = up to 256 fp32 accumulator columns in TMEM; the SM's 512 columns hold S = 2 (N <= 256) or 4 (N <= 128)
-//       accumulator stages, each owned by its own epilogue warpgroup,
+//   CTA tile = 16 rows x (8*MT) columns of the NHWC grid = MT "M-tiles" of 128 pixels (TMEM lane m <-> pixel (m/8, m%8));
+//       MT = 2 for stages with <= 128 accumulator columns, 1 for the 256-column stages (gates, q2),
+//   N = up to 256/MT fp32 accumulator columns per M-tile; the SM's 512 TMEM columns hold 2 pipeline stages x MT M-tiles,
+//       each (stage, M-tile) slot owned by its own epilogue warpgroup,
 //   K = sum over "chunks": 64 input channels of one activation buffer x RxR taps.
-// A operand: for every horizontal tap dx the producer TMA-loads ONE box of (16+R-1) rows x 8 pixels x 64 ch
-//   (128 B per pixel, SWIZZLE_128B; out-of-image pixels are zero-filled by TMA = the conv's zero padding).
-//   A vertical tap dy is then just a 1024-byte (8 pixel-rows) offset of the UMMA descriptor into that box, so
-//   every descriptor start stays 1024-byte aligned.  R loads serve R*R taps.
-// B operand: packed weights [rows][64] bf16, one TMA tile of n*nrep rows per tap, streamed through its own ring.
-//   Tap order is rotated per tile position so that the CTAs do not all pull the same weight tile from L2 at once.
-// Warp roles: warps [0,4S) = S epilogue warpgroups, then TMA producer (one lane), MMA issuer (one lane), TMEM allocator;
-//   epilogue: (one thread per pixel: its TMEM lane holds all output channels of that pixel,
-//   so LayerNorm / softmax-mix / GRU blends are thread-local).  Persistent over tiles, static round-robin.
+// A operand: ONE TMA box per chunk: the tile plus its halo, (16+R-1) rows x (8*MT+R-1) pixels x 64 ch (128 B per pixel,
+//   SWIZZLE_128B; out-of-image pixels are zero-filled by TMA = the conv's zero padding).  Every tap (dy,dx) and M-tile is
+//   the SAME box read through a UMMA descriptor whose start is shifted by (dy*WP + dx + 8*mt) pixel rows and whose 8-row
+//   group stride is WP*128 B.  The 128-byte swizzle is a function of the absolute shared-memory address (verified on
+//   B200: scripts/exp_shift.py, profiles/r01_exp_shifted_descriptors.txt), so such 128-byte-aligned starts read correctly
+//   with base_offset = 0.  One load of (tile + halo) serves R*R taps: activation re-reads from L2 drop from 3.4x to ~1.3x.
+// B operand: packed weights [rows][64] bf16 streamed through their own ring, one TMA tile per tap or per column of taps;
+//   each weight tile feeds the MMAs of all MT M-tiles.  Tap order is rotated per tile position so that the CTAs do not all
+//   pull the same weight tile from L2 at once.
+// Warp roles: warps [0, 8*MT) = epilogue warpgroups (one thread per pixel: its TMEM lane holds all output channels of that
+//   pixel, so LayerNorm / softmax-mix / GRU blends are thread-local), then TMA producer (one lane), MMA issuer (one lane),
+//   TMEM allocator.  Persistent over tiles, static round-robin.
 #pragma once
 #include "sf_ptx.cuh"
 #include "../../include/sf_b200.h"
@@ -69,8 +73,10 @@ struct alignas(64) StageParams {
   EpiArgs e;
 };
 
-// number of accumulator stages (= epilogue warpgroups) per epilogue kind: 256-column stages get 2, the rest 4
-__host__ __device__ constexpr int acc_stages_for(int epi) { return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ) ? 2 : 4; }
+// M-tiles per CTA tile: 256-column stages get 1, the rest 2 (accumulator slot = 256 / MT columns)
+__host__ __device__ constexpr int mtiles_for(int epi) { return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ) ? 1 : 2; }
+constexpr int ACC_STAGES = 2;
+__host__ __device__ constexpr int a_box_bytes(int R, int MT) { return (TILE_H + R - 1) * (TILE_W * MT + R - 1) * ROW_BYTES; }
 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers (one thread = one pixel; 16 channels at a time)
@@ -365,9 +371,12 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
 // the stage kernel
 // ------------------------------------------------------------------------------------------------
 template <int EPI, bool X3>
-__global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
-  constexpr int S = acc_stages_for(EPI);
-  constexpr uint32_t STAGE_COLS = TMEM_COLS / S;
+__global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
+  constexpr int S = ACC_STAGES;
+  constexpr int MT = mtiles_for(EPI);
+  constexpr int NGROUPS = S * MT;                       // epilogue warpgroups = accumulator slots
+  constexpr uint32_t STAGE_COLS = TMEM_COLS / S;        // 256
+  constexpr uint32_t SLOT_COLS = STAGE_COLS / MT;       // 256 or 128
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nA = p.nA, nB = p.nB;
@@ -383,14 +392,14 @@ __global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage
   uint64_t* acc_empty = acc_full + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // warp roles: [0, 4S) epilogue warpgroups (warp % 4 = TMEM lane quadrant), then producer, MMA issuer, TMEM allocator
-  constexpr int W_PROD = 4 * S, W_MMA = 4 * S + 1, W_ALLOC = 4 * S + 2;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably warp-uniform
+  // warp roles: [0, 4*NGROUPS) epilogue warpgroups (warp % 4 = TMEM lane quadrant), then producer, MMA issuer, TMEM allocator
+  constexpr int W_PROD = 4 * NGROUPS, W_MMA = 4 * NGROUPS + 1, W_ALLOC = 4 * NGROUPS + 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
-    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128); }
+    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128 * MT); }
     mbar_fence_init();
   }
   if (warp == W_ALLOC) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int tpi = p.tiles_x * p.tiles_y;
   const int ntiles = p.n_active * tpi;
@@ -406,38 +415,48 @@ __global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage
   const uint32_t a_smem0 = smem_u32(a_base), b_smem0 = smem_u32(b_base);
 
   if (warp == W_PROD) {
-    if (lane == 0) {
-      // ===================== TMA producer (lean loop: ring indices are counters, no div/mod per tap) =====================
-      for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
-      tma_prefetch_desc(&p.wmap);
+    {
+      // ===================== TMA producer =====================
+      // The whole warp runs this loop converged and ONE elected lane issues: all operands stay warp-uniform (uniform
+      // registers), so no per-instruction R2UR waterfall.  Ring indices are counters: no div/mod per tap.
+      if (elect_one()) {
+        for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
+        tma_prefetch_desc(&p.wmap);
+      }
       uint32_t sa = 0, pa = 1, sb = 0, pb = 1;      // slot index and the parity to wait for on the EMPTY barrier
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int bi = tile / tpi, rem = tile - bi * tpi;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int y0 = ty * TILE_H, x0 = tx * TILE_W;
-        const int sid = p.sample_id[bi], ximg = p.x_img[bi];
+        const int y0 = ty * TILE_H, x0 = tx * TILE_W * MT;
+        const int sid = __shfl_sync(0xffffffffu, p.sample_id[bi], 0), ximg = __shfl_sync(0xffffffffu, p.x_img[bi], 0);
         for (int c = 0; c < p.nchunk; ++c) {
           const ChunkK ck = p.chunk[c];
           const int R = ck.R, pad = (R - 1) >> 1;
           const int img = ck.img_sel ? ximg : sid;
-          const uint32_t a_bytes = (uint32_t)(TILE_H + R - 1) * TILE_W * ROW_BYTES;
+          // the tile + halo of this chunk: one box, all taps read it through shifted descriptors
+          mbar_wait(a_empty0 + sa * 8, pa, p.err, 1);
+          if (elect_one()) {
+            mbar_expect_tx(a_full0 + sa * 8, (uint32_t)a_box_bytes(R, MT));
+            tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 - pad, y0 - pad, img);
+          }
+          __syncwarp();
+          if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
           const int tap_rows = ck.n * ck.nrep;                  // weight rows of one tap
           const int grp_rows = tap_rows * ck.tb;                // rows of one B tile (tb taps)
           const int ngrp = R / ck.tb;                           // B tiles per dx column (R or 1)
           int dx = rem % R, g0 = (ck.tb == 1) ? (rem / R) % R : 0;     // tap rotation (same formula in the MMA warp)
           for (int i = 0; i < R; ++i) {
-            mbar_wait(a_empty0 + sa * 8, pa, p.err, 1);
-            mbar_expect_tx(a_full0 + sa * 8, a_bytes);
-            tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 + dx - pad, y0 - pad, img);
-            if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
               mbar_wait(b_empty0 + sb * 8, pb, p.err, 2);
-              mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
-              int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows;
-              uint32_t dst = b_smem0 + sb * p.b_slot_bytes;
-              for (int q = 0; q < grp_rows; q += 64, row += 64, dst += 64 * ROW_BYTES)
-                tma_load_2d(dst, &p.wmap, b_full0 + sb * 8, 0, row);
+              if (elect_one()) {
+                mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
+                int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows;
+                uint32_t dst = b_smem0 + sb * p.b_slot_bytes;
+                for (int q = 0; q < grp_rows; q += 64, row += 64, dst += 64 * ROW_BYTES)
+                  tma_load_2d(dst, &p.wmap, b_full0 + sb * 8, 0, row);
+              }
+              __syncwarp();
               if (++sb == (uint32_t)nB) { sb = 0; pb ^= 1; }
               if (++gi == ngrp) gi = 0;
             }
@@ -447,10 +466,8 @@ __global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      // descriptor high word is constant: SBO = 1024 B (>>4 = 64), version 1 (bit 46), SWIZZLE_128B (2 << 61)
-      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+    {
+      // ===================== MMA issuer (converged warp, one elected lane issues) =====================
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 1;   // parities to wait for on the FULL barriers / acc EMPTY
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int rem = tile % tpi;
@@ -460,68 +477,84 @@ __global__ void __launch_bounds__(128 + 128 * acc_stages_for(EPI), 1) conv_stage
         for (int c = 0; c < p.nchunk; ++c) {
           const ChunkK ck = p.chunk[c];
           const int R = ck.R;
+          const uint32_t WP = TILE_W * MT + R - 1;                   // pixels per row of the halo box
+          // descriptor high word: SBO = WP*128 B between 8-row groups, version 1 (bit 46), SWIZZLE_128B (2 << 61)
+          const uint32_t a_hi = ((WP * ROW_BYTES) >> 4) | (1u << 14) | (2u << 29);
+          constexpr uint32_t B_HI = 64u | (1u << 14) | (2u << 29);
           const uint32_t idesc = make_idesc_bf16(128, (uint32_t)ck.n);
           const uint32_t d_addr = d_base + ck.col;
-          const uint32_t tap_lo = (uint32_t)(ck.n * ck.nrep * ROW_BYTES) >> 4;    // descriptor-lo step per tap inside a B tile
           const uint32_t rep_lo = (uint32_t)(ck.n * ROW_BYTES) >> 4;
           const int ngrp = R / ck.tb;
           const int g0 = (ck.tb == 1) ? (rem / R) % R : 0;
           uint32_t accumulate = ck.init ? 0u : 1u;
+          mbar_wait(a_full0 + sa * 8, pa, p.err, 4);
+          const uint32_t a_lo0 = ((a_smem0 + sa * p.a_slot_bytes) & 0x3FFFFu) >> 4;
+          int dx = rem % R;
           for (int i = 0; i < R; ++i) {
-            mbar_wait(a_full0 + sa * 8, pa, p.err, 4);
-            const uint32_t a_lo0 = ((a_smem0 + sa * p.a_slot_bytes) & 0x3FFFFu) >> 4;
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
               mbar_wait(b_full0 + sb * 8, pb, p.err, 5);
               tc_fence_after();
               uint32_t b_lo = ((b_smem0 + sb * p.b_slot_bytes) & 0x3FFFFu) >> 4;
-              uint32_t a_lo = a_lo0 + (uint32_t)(gi * ck.tb) * ((TILE_W * ROW_BYTES) >> 4);
-              for (int t = 0; t < ck.tb; ++t, a_lo += (TILE_W * ROW_BYTES) >> 4) {
-                for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo) {
+              // first tap of this group: dy = gi*tb; one pixel row = 128 B = 8 descriptor units
+              uint32_t a_lo = a_lo0 + ((uint32_t)(gi * ck.tb) * WP + (uint32_t)dx) * (ROW_BYTES >> 4);
+              if (elect_one()) {
+                uint32_t acc = accumulate;
+                for (int t = 0; t < ck.tb; ++t, a_lo += WP * (ROW_BYTES >> 4)) {
+                  for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo) {
 #pragma unroll
-                  for (uint32_t k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes = 2 descriptor units) per 64-channel chunk
-                    umma_bf16(d_addr, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (b_lo + 2 * k), idesc,
-                              accumulate);
-                    accumulate = 1u;
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                      for (uint32_t k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes = 2 descriptor units) per 64-channel chunk
+                        umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_lo + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
+                                  ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc, acc | (k > 0 ? 1u : 0u));
+                      }
+                    }
+                    acc = 1u;
                   }
                 }
+                umma_commit(b_empty0 + sb * 8);        // frees the weight tile once these MMAs retire
               }
-              (void)tap_lo;
-              umma_commit(b_empty0 + sb * 8);        // frees the weight tile once these MMAs retire
+              __syncwarp();
+              accumulate = 1u;
               if (++sb == (uint32_t)nB) { sb = 0; pb ^= 1; }
               if (++gi == ngrp) gi = 0;
             }
-            umma_commit(a_empty0 + sa * 8);
-            if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
+            if (++dx == R) dx = 0;
           }
+          if (elect_one()) umma_commit(a_empty0 + sa * 8);
+          __syncwarp();
+          if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(smem_u32(acc_full + as));
+        if (elect_one()) umma_commit(smem_u32(acc_full + as));
+        __syncwarp();
         if (++as == (uint32_t)S) { as = 0; pacc ^= 1; }
       }
     }
-  } else if (warp < 4 * S) {
-    // ===================== epilogue warpgroup g owns accumulator stage g =====================
+  } else if (warp < 4 * NGROUPS) {
+    // ===================== epilogue warpgroup g owns accumulator slot (stage g / MT, M-tile g % MT) =====================
     const int g = warp >> 2;
+    const int st = g / MT, mt = g % MT;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int r = m >> 3, cx = m & 7;
-    const uint32_t taddr = tmem_base + (uint32_t)g * STAGE_COLS + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = tmem_base + (uint32_t)st * STAGE_COLS + (uint32_t)mt * SLOT_COLS + ((uint32_t)(q * 32) << 16);
     uint32_t aph = 0;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
+    for (int tile = blockIdx.x + st * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
       const int bi = tile / tpi, rem = tile - bi * tpi;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       PixelCtx c;
       c.bi = bi;
       c.sid = p.sample_id[bi];
       c.y = ty * TILE_H + r;
-      c.x = tx * TILE_W + cx;
+      c.x = (tx * MT + mt) * TILE_W + cx;
       c.valid = (c.y < p.H) && (c.x < p.W);
       c.pix = ((size_t)c.sid * p.H + c.y) * p.W + c.x;
-      mbar_wait(smem_u32(acc_full + g), aph, p.err, 6);
+      mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
       run_epilogue<EPI, X3>(p, vec_s, taddr, c);
       tc_fence_before();
-      mbar_arrive(smem_u32(acc_empty + g));
+      mbar_arrive(smem_u32(acc_empty + st));
     }
   }
   tc_fence_before();

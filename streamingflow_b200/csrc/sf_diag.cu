@@ -87,9 +87,86 @@ __global__ void __launch_bounds__(128) diag_umma_kernel(const __grid_constant__ 
     tmem_dealloc(tmem, 256);
   }
 }
+
+// Experiment: A is a [rows_a x 64] bf16 matrix (rows_a >= 128 + shift) loaded as ONE swizzled TMA box; the MMA reads
+// 128 rows starting at row `shift` with 8-row-group stride `sbo_rows` rows.  D[m][n] should equal
+// sum_k A[shift + (m/8)*sbo_rows + m%8][k] * B[n][k].  base_mode: 0 -> base_offset field 0; 1 -> (start>>7)&7.
+__global__ void __launch_bounds__(128) diag_umma_shift_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                                                              float* d, int n, int rows_a, int shift, int sbo_rows, int base_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                       // rows_a x 128 B (<= 64 KB)
+  uint8_t* sb = smem + 65536;               // n rows x 128 B
+  __shared__ uint64_t full, done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&full), 1);
+    mbar_init(smem_u32(&done), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(smem_u32(&full), (uint32_t)(rows_a + n) * 128);
+    for (int r = 0; r < rows_a; r += 64) tma_load_2d(smem_u32(sa) + r * 128, &amap, smem_u32(&full), 0, r);
+    for (int j = 0; j < n / 64; ++j) tma_load_2d(smem_u32(sb) + j * 64 * 128, &bmap, smem_u32(&full), 0, j * 64);
+    mbar_wait(smem_u32(&full), 0, nullptr, 8);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n);
+    const uint32_t a_start = smem_u32(sa) + shift * 128;
+    const uint64_t base_off = base_mode ? (uint64_t)((a_start >> 7) & 7) : 0ull;
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint64_t adesc = (uint64_t)(((a_start + kk * 32) & 0x3FFFFu) >> 4) | ((uint64_t)((sbo_rows * 128) >> 4) << 32) | (1ull << 46) |
+                             (base_off << 49) | (2ull << 61);
+      umma_bf16(tmem, adesc, make_sw128_desc(smem_u32(sb) + kk * 32), idesc, kk ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&done));
+    mbar_wait(smem_u32(&done), 0, nullptr, 9);
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int m = warp * 32 + lane;
+  for (int j = 0; j < n / 16; ++j) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + j * 16, v);
+    for (int i = 0; i < 16; ++i) d[(size_t)m * n + j * 16 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
 }  // namespace
 
 extern "C" {
+
+int sf_diag_umma_shift(const void* a_bf16, const void* b_bf16, float* d, int n, int rows_a, int shift, int sbo_rows, int base_mode,
+                       void* stream) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || n % 64 || n > 256 || n <= 0 || rows_a % 64 || rows_a > 512) return SF_ERR_INVALID;
+  CUtensorMap am, bm;
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t stride[1] = {128};
+  cuuint64_t adims[2] = {64, (cuuint64_t)rows_a};
+  cuuint64_t bdims[2] = {64, (cuuint64_t)n};
+  if (enc(&am, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a_bf16), adims, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return SF_ERR_CUDA;
+  if (enc(&bm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b_bf16), bdims, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return SF_ERR_CUDA;
+  const int smem = 65536 + 32768 + 1024;
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(diag_umma_shift_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  diag_umma_shift_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(am, bm, d, n, rows_a, shift, sbo_rows, base_mode);
+  return cudaGetLastError() == cudaSuccess ? SF_OK : SF_ERR_CUDA;
+}
 
 int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0, int rows,
                      void* out_smem_copy, void* stream) {

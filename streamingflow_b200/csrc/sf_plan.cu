@@ -67,7 +67,7 @@ struct SeDef {
 
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_AREA = 512;
-constexpr int B_TILE_MAX = 56 * 1024;
+constexpr int B_TILE_MAX = 24 * 1024;
 
 }  // namespace
 
@@ -80,7 +80,7 @@ struct sf_plan {
   Stage stage[SF_MAX_STAGES];
   SeDef se[2];
   std::vector<int> cell[2], prior;
-  std::map<std::tuple<int, int, int>, CUtensorMap> amaps;   // (buf, plane, R) -> activation tensor map
+  std::map<std::tuple<int, int, int, int>, CUtensorMap> amaps;   // (buf, plane, R, MT) -> activation tensor map
   int last_launches = 0;
 };
 
@@ -88,8 +88,8 @@ namespace {
 
 using namespace sf;
 
-int encode_act_map(sf_plan* p, int buf, int plane, int R, CUtensorMap* out) {
-  auto key = std::make_tuple(buf, plane, R);
+int encode_act_map(sf_plan* p, int buf, int plane, int R, int MT, CUtensorMap* out) {
+  auto key = std::make_tuple(buf, plane, R, MT);
   auto it = p->amaps.find(key);
   if (it != p->amaps.end()) {
     *out = it->second;
@@ -104,7 +104,7 @@ int encode_act_map(sf_plan* p, int buf, int plane, int R, CUtensorMap* out) {
   const cuuint64_t C = a.channels, W = p->g.W, H = p->g.H, N = a.n_images;
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TILE_W, (cuuint32_t)(TILE_H + R - 1), 1};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(TILE_W * MT + R - 1), (cuuint32_t)(TILE_H + R - 1), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -167,7 +167,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   for (int c = 0; c < sp.nchunk; ++c) {
     const sf_chunk& ck = st.chunks[c];
     const int buf = resolve_buf(ev, ck.buf);
-    int rc = encode_act_map(p, buf, ck.plane, ck.R, &sp.amap[c]);
+    int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.epi), &sp.amap[c]);
     if (rc) return rc;
     if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
     sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c]};
@@ -175,7 +175,8 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.wmap = st.wmap;
   sp.H = p->g.H;
   sp.W = p->g.W;
-  sp.tiles_x = (p->g.W + TILE_W - 1) / TILE_W;
+  const int MT = sf::mtiles_for(st.epi);
+  sp.tiles_x = (p->g.W + TILE_W * MT - 1) / (TILE_W * MT);
   sp.tiles_y = (p->g.H + TILE_H - 1) / TILE_H;
   sp.n_active = ev->n_active;
   const int n = ev->n_active;
@@ -246,7 +247,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   StageKernel k = kernel_for(st.epi, x3);
   if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
   void* args[] = {&sp};
-  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::acc_stages_for(st.epi)), args, (size_t)st.smem, stream));
+  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::ACC_STAGES * sf::mtiles_for(st.epi)), args, (size_t)st.smem, stream));
   p->last_launches += 1;
   return SF_OK;
 }
@@ -363,13 +364,13 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   int a_slot = 0, b_slot = 0;
   for (const sf_chunk& c : st.chunks) {
     if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
-    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::acc_stages_for(epilogue)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
+    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(epilogue)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
     // a whole dx column of taps travels as ONE weight tile when it is small enough: fewer barrier round trips per MMA
     const int tb = (c.R * c.n * c.nrep * ROW_BYTES <= B_TILE_MAX) ? c.R : 1;
     st.tb.push_back(tb);
-    const int a = (TILE_H + c.R - 1) * TILE_W * ROW_BYTES, b = tb * c.n * c.nrep * ROW_BYTES;
+    const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
     a_slot = a > a_slot ? a : a_slot;
     b_slot = b > b_slot ? b : b_slot;
   }
@@ -380,9 +381,10 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.io.assign(io_bufs, io_bufs + n_io);
   const int fixed = 1024 + sf::VEC_MAX * 4 + BAR_AREA;
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
-  int nA = 3;
+  // activation ring: one slot = one chunk's tile + halo (3 slots when they leave room for >= 2 weight slots);
+  // weight ring: everything that is left, up to MAX_RING slots
+  int nA = (fixed + 3 * a_slot + 2 * b_slot <= SMEM_BUDGET) ? 3 : 2;
   int nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
-  if (nB < 2) { nA = 2; nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot; }
   if (nB > sf::MAX_RING) nB = sf::MAX_RING;
   if (nB < 2) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
   while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
