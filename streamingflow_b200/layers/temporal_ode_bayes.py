@@ -132,6 +132,7 @@ class NNFOwithBayesianJumps(nn.Module):
         # engine options (not part of the reference API)
         self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
         self.noise = "reference"
+        self.noise_skip = 0                             # draws to discard first (batch sharding: samples of earlier ranks)
         self.record_all = False                         # debug: keep the state after every event (last_trace)
         self.last_trace = None
         self.__dict__["_engines"] = {}
@@ -178,6 +179,9 @@ class NNFOwithBayesianJumps(nn.Module):
         """Standard-normal tensors in the reference's order: one ``torch.empty([1,C,h,w]).normal_()`` per infer_state call
         (torch.distributions.Normal.rsample -> _standard_normal), here drawn in place into one [n, C, h, w] buffer."""
         eps = torch.empty((max(n, 1), self.hidden_size, h, w), dtype=torch.float32, device=device)
+        for _ in range(self.noise_skip):                # keep the global sample-major stream when the batch is sharded
+            eps[0].normal_()
+        self.noise_skip = 0
         if self.noise == "bulk":
             eps.normal_()
         else:
