@@ -6,33 +6,53 @@
 namespace sf {
 
 // ---- SE step 1: per-(sample, channel) sums over the H*W pixels of a [img][H*W][CH] bf16 tensor --------
-// grid = (blocks_per_image, n_active); block = 256 threads = 16 channel groups (8 ch = 16 B) x 16 pixel lanes.
+// grid = (blocks_per_image, n_active); block = 256 threads = 8 channel groups (16 ch = 32 B, one 256-bit load) x 32 pixel
+// lanes, 4 independent loads in flight per thread.  Optional row window [row0, row1) (row sharding: own rows only).
 template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
-                                                        float* __restrict__ sums, const int* __restrict__ sample_id, int hw) {
+                                                        float* __restrict__ sums, const int* __restrict__ sample_id, int hw, int px0, int px1) {
   static_assert(CH == 128, "SE layers of the prior network have 2C = 128 channels");
-  constexpr int GROUPS = CH / 8;            // 16
-  constexpr int LANES = 256 / GROUPS;       // 16 pixels in flight per block iteration
+  constexpr int GROUPS = CH / 16;           // 8
+  constexpr int LANES = 256 / GROUPS;       // 32 pixels per block iteration
+  constexpr int UNROLL = 4;
   const int bi = blockIdx.y;
   const int sid = sample_id[bi];
   const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS;
   const size_t base = (size_t)sid * hw * CH;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int px = blockIdx.x * LANES + pl; px < hw; px += gridDim.x * LANES) {
-    const uint4 v = *reinterpret_cast<const uint4*>(zh + base + (size_t)px * CH + g * 8);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float acc[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(w[i]); acc[2 * i + 1] += bf16_hi_f(w[i]); }
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+  for (int px = px0 + blockIdx.x * LANES * UNROLL + pl; px < px1; px += gridDim.x * LANES * UNROLL) {
+    uint32_t v[UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int q = px + u * LANES;
+      if (q < px1) ldg256(zh + base + (size_t)q * CH + g * 16, v[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[u][i] = 0u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[2 * i] += bf16_lo_f(v[u][i]); acc[2 * i + 1] += bf16_hi_f(v[u][i]); }
     if (X3) {
-      const uint4 u = *reinterpret_cast<const uint4*>(zl + base + (size_t)px * CH + g * 8);
-      const uint32_t x[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(x[i]); acc[2 * i + 1] += bf16_hi_f(x[i]); }
+      for (int u = 0; u < UNROLL; ++u) {
+        const int q = px + u * LANES;
+        if (q < px1) {
+          uint32_t w[8];
+          ldg256(zl + base + (size_t)q * CH + g * 16, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[2 * i] += bf16_lo_f(w[i]); acc[2 * i + 1] += bf16_hi_f(w[i]); }
+        }
+      }
     }
   }
   __shared__ float red[LANES][CH + 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[pl][g * 8 + i] = acc[i];
+  for (int i = 0; i < 16; ++i) red[pl][g * 16 + i] = acc[i];
   __syncthreads();
   if (threadIdx.x < CH) {
     float s = 0.0f;
@@ -44,22 +64,25 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
 }
 
 // ---- SE step 2: scale = sigmoid(fc2 * relu(fc1 * mean)); y = z * scale ---------------------------------
-// every block recomputes the 2 tiny FCs (128x16 each) for its sample, then streams its share of pixels.
+// every block recomputes the 2 tiny FCs (128x16 each) for its sample, then streams its share of pixels with 256-bit
+// loads / stores, 4 in flight per thread.  n_mean = number of pixels behind the sums (H*W of the WHOLE image).
 template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
                                                        __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
                                                        const float* __restrict__ sums, int n_partials, const float* __restrict__ fc1,
-                                                       const float* __restrict__ fc2, const int* __restrict__ sample_id, int hw) {
+                                                       const float* __restrict__ fc2, const int* __restrict__ sample_id, int hw,
+                                                       float inv_n_mean) {
   constexpr int HID = CH / 8;               // reduction 8
-  constexpr int GROUPS = CH / 8;
+  constexpr int GROUPS = CH / 16;
   constexpr int LANES = 256 / GROUPS;
+  constexpr int UNROLL = 4;
   __shared__ float mean_s[CH], hid_s[HID], scale_s[CH];
   const int bi = blockIdx.y;
   const int sid = sample_id[bi];
   if (threadIdx.x < CH) {
     float t = 0.0f;
     for (int k = 0; k < n_partials; ++k) t += sums[((size_t)bi * n_partials + k) * CH + threadIdx.x];
-    mean_s[threadIdx.x] = t / (float)hw;
+    mean_s[threadIdx.x] = t * inv_n_mean;
   }
   __syncthreads();
   if (threadIdx.x < HID) {
@@ -72,38 +95,47 @@ __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __re
     float a = 0.0f;
 #pragma unroll
     for (int j = 0; j < HID; ++j) a = fmaf(fc2[threadIdx.x * HID + j], hid_s[j], a);
-    scale_s[threadIdx.x] = 1.0f / (1.0f + __expf(-a));
+    scale_s[threadIdx.x] = __fdividef(1.0f, 1.0f + __expf(-a));
   }
   __syncthreads();
   const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS;
   const size_t base = (size_t)sid * hw * CH;
-  float sc[8];
+  float sc[16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sc[i] = scale_s[g * 8 + i];
-  for (int px = blockIdx.x * LANES + pl; px < hw; px += gridDim.x * LANES) {
-    const size_t off = base + (size_t)px * CH + g * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(zh + off);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    float f[8];
+  for (int i = 0; i < 16; ++i) sc[i] = scale_s[g * 16 + i];
+  for (int px = blockIdx.x * LANES * UNROLL + pl; px < hw; px += gridDim.x * LANES * UNROLL) {
+    uint32_t v[UNROLL][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo_f(w[i]); f[2 * i + 1] = bf16_hi_f(w[i]); }
-    if (X3) {
-      const uint4 u = *reinterpret_cast<const uint4*>(zl + off);
-      const uint32_t x[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { f[2 * i] += bf16_lo_f(x[i]); f[2 * i + 1] += bf16_hi_f(x[i]); }
+    for (int u = 0; u < UNROLL; ++u) {
+      const int q = px + u * LANES;
+      if (q < hw) ldg256(zh + base + (size_t)q * CH + g * 16, v[u]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] *= sc[i];
-    uint32_t h[4];
+    for (int u = 0; u < UNROLL; ++u) {
+      const int q = px + u * LANES;
+      if (q >= hw) continue;
+      const size_t off = base + (size_t)q * CH + g * 16;
+      float f[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-    *reinterpret_cast<uint4*>(yh + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (X3) {
-      uint32_t l[4];
+      for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_lo_f(v[u][i]); f[2 * i + 1] = bf16_hi_f(v[u][i]); }
+      if (X3) {
+        uint32_t w[8];
+        ldg256(zl + off, w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
-      *reinterpret_cast<uint4*>(yl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int i = 0; i < 8; ++i) { f[2 * i] += bf16_lo_f(w[i]); f[2 * i + 1] += bf16_hi_f(w[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] *= sc[i];
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      stg256(yh + off, h);
+      if (X3) {
+        uint32_t l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
+        stg256(yl + off, l);
+      }
     }
   }
 }

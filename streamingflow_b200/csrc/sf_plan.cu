@@ -267,7 +267,7 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   const ActBuf& yo = p->act[se.out_buf];
   if (!zi.hi || !yo.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
   const int* sid = table + ev->table_off;
-  int bpi = (hw + 16 * 8 - 1) / (16 * 8);     // ~8 pixels per thread-lane
+  int bpi = (hw + 32 * 4 * 2 - 1) / (32 * 4 * 2);     // ~2 iterations of 4 x 32 pixels per block
   if (bpi > SE_MAX_PARTIALS) bpi = SE_MAX_PARTIALS;
   if (bpi < 1) bpi = 1;
   dim3 grid(bpi, ev->n_active);
@@ -275,16 +275,18 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
   auto yh = reinterpret_cast<__nv_bfloat16*>(yo.hi);
   auto yl = reinterpret_cast<__nv_bfloat16*>(yo.lo);
-  int bpa = (hw + 16 * 4 - 1) / (16 * 4);
-  if (bpa > 296) bpa = 296;
+  int bpa = (hw + 32 * 4 - 1) / (32 * 4);
+  const int cap = (4 * p->num_sms + ev->n_active - 1) / ev->n_active;      // ~4 resident blocks per SM over all samples
+  if (bpa > cap) bpa = cap;
   if (bpa < 1) bpa = 1;
   dim3 grid2(bpa, ev->n_active);
+  const float inv_n = 1.0f / (float)hw;
   if (x3) {
-    se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
-    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw);
+    se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, 0, hw);
+    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw, inv_n);
   } else {
-    se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw);
-    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw);
+    se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, 0, hw);
+    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw, inv_n);
   }
   SF_CUDA(cudaGetLastError());
   p->last_launches += 2;

@@ -270,15 +270,20 @@ class OdeEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def pack_into(self, buf: int, src_nchw: torch.Tensor, n_images: Optional[int] = None):
-        """NCHW fp32 -> the NHWC bf16 activation buffer ``buf`` (first n images)."""
+    def pack_into(self, buf: int, src_nchw: torch.Tensor, img_offset: int = 0):
+        """NCHW fp32 -> the NHWC bf16 activation buffer ``buf`` (images [img_offset, img_offset + n))."""
         src = src_nchw.contiguous().float()
         n, c, h, w = src.shape
         assert (h, w) == (self.H, self.W)
         hi, lo = self.act[buf]
-        assert n <= hi.shape[0] and c == hi.shape[3]
-        L.check(self.lib.sf_pack_nchw_f32(src.data_ptr(), hi.data_ptr(), lo.data_ptr() if lo is not None else None, n, c, h, w,
-                                          self._stream()), "sf_pack_nchw_f32")
+        assert img_offset + n <= hi.shape[0] and c == hi.shape[3]
+        L.check(self.lib.sf_pack_nchw_f32(src.data_ptr(), hi[img_offset:].data_ptr(), lo[img_offset:].data_ptr() if lo is not None else None,
+                                          n, c, h, w, self._stream()), "sf_pack_nchw_f32")
+
+    def reserve_observations(self, n_images: int):
+        if BUF_OBS not in self.act or self.act[BUF_OBS][0].shape[0] < n_images:
+            self._new_act(BUF_OBS, n_images, self.C)
+        self.n_obs_images = n_images
 
     def bind_observations(self, hx_nchw: torch.Tensor):
         """Encoded observations [n_img, 64, H, W] fp32 -> OBS activation buffer (the jump cell's x input)."""

@@ -302,6 +302,79 @@ class NNFOwithBayesianJumps(nn.Module):
             self.last_trace = [eng.unpack_path(slots) for slots in ro.trace_slots]
         return eng.unpack_f32(eng.state32[0], B), sel
 
+    def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None):
+        """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final
+        states on device, selected latents in the pinned CPU tensor ``out_host`` [B, T, C, h, w]).  Host<->device copies are
+        pipelined against the rollout: observation k of every sample is uploaded on a copy stream while earlier events run
+        (a jump only needs its own frame), and each target's selected state is gathered and downloaded as soon as the
+        event that produces it has been enqueued."""
+        B = len(obs_counts)
+        _, c, h, w = hx_host.shape
+        dev = next(self.parameters()).device
+        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
+        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+        kmax = max(obs_counts)
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b)
+        eng = self._engine_for(h, w, B, dev)
+        eng.reserve_observations(kmax * B)
+        eng.zero_state(0)
+        eng.ensure_path_slots(ro.n_path)
+        eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
+        T = len(targets[0])
+        if out_host is None:
+            out_host = torch.empty((B, T, c, h, w), dtype=torch.float32).pin_memory()
+        main = torch.cuda.current_stream(dev)
+        if "_copy_streams" not in self.__dict__:
+            self.__dict__["_copy_streams"] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._copy_streams
+        stage = self.__dict__.setdefault("_stage_bufs", {})
+        key = (str(dev), kmax * B, B, T, c, h, w)
+        if stage.get("key") != key:
+            stage.update(key=key, hx=torch.empty((kmax * B, c, h, w), dtype=torch.float32, device=dev),
+                         out=torch.empty((T, B, c, h, w), dtype=torch.float32, device=dev))
+        hx_dev, out_dev = stage["hx"], stage["out"]
+        # uploads, in order of need (observation index k across all samples)
+        s_in.wait_stream(main)
+        up_done = []
+        with torch.cuda.stream(s_in):
+            for k in range(kmax):
+                for b in range(B):
+                    if k < obs_counts[b]:
+                        hx_dev[k * B + b].copy_(hx_host[base[b] + k], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                up_done.append(e)
+        table, evs = eng.build_table(ro.events)
+        tdev = eng.upload_table(table)
+        last_writer = {}
+        for i, e in enumerate(ro.events):
+            for slot in e["rec"]:
+                if slot >= 0:
+                    last_writer[slot] = i
+        ready_at = [max(last_writer[ro.out_slots[b][t]] for b in range(B)) for t in range(T)]
+        packed, flushed, launches = set(), set(), 0
+        for i, e in enumerate(ro.events):
+            if e["kind"] == JUMP:
+                for k in sorted({xi // B for xi in e["x_img"]}):
+                    if k not in packed:
+                        main.wait_event(up_done[k])
+                        eng.pack_into(3, hx_dev[k * B:(k + 1) * B], img_offset=k * B)
+                        packed.add(k)
+            launches += eng.run_events(evs[i:i + 1], tdev)
+            for t in range(T):
+                if t not in flushed and ready_at[t] <= i:
+                    out_dev[t].copy_(eng.unpack_path([ro.out_slots[b][t] for b in range(B)]))
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    s_out.wait_event(done)
+                    with torch.cuda.stream(s_out):
+                        out_host[:, t].copy_(out_dev[t], non_blocking=True)
+                    flushed.add(t)
+        main.wait_stream(s_out)
+        ro.launches = launches
+        self.last_rollout = ro
+        return eng.unpack_f32(eng.state32[0], B), out_host
+
     def forward(self, times, input, obs, delta_t, T, return_path=True):
         """Reference :479-627.  times: observation times in processing order; input: only its shape is used;
         obs: [1, n_obs, C, H, W]; T: target times.  Returns (final latent state, 0, decoded frames [1, T, C, H, W])."""

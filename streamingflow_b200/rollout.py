@@ -35,9 +35,12 @@ class Rollout:
 
 
 def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool,
-                    record_all: bool = False) -> Rollout:
-    """record_all additionally records the state after EVERY op (debug / parity traces)."""
+                    record_all: bool = False, obs_index=None) -> Rollout:
+    """record_all additionally records the state after EVERY op (debug / parity traces).  obs_index(b, k) overrides the
+    image index of sample b's k-th observation in the OBS buffer (default: sample-major obs_base[b] + k)."""
     ro = Rollout()
+    if obs_index is None:
+        obs_index = lambda b, k: obs_base[b] + k
     per_sample: List[List[dict]] = []
     eps = 0
     for b, plan in enumerate(plans):
@@ -59,7 +62,7 @@ def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver
         for i, op in enumerate(plan.ops):
             rec = picked.get(i, -1)
             if op.kind == JUMP:
-                evs.append(dict(kind=JUMP, x_buf=BUF_OBS, x_img=obs_base[b] + op.obs, s_in=0, s_base=0, s_out=0, dt=0.0, eps=eps,
+                evs.append(dict(kind=JUMP, x_buf=BUF_OBS, x_img=obs_index(b, op.obs), s_in=0, s_base=0, s_out=0, dt=0.0, eps=eps,
                                 rec=rec, run_prior=impute))
                 eps += 1
                 ro.n_jumps += 1

@@ -144,3 +144,22 @@ def test_forward_is_deterministic_and_batch_equals_sequential():
     # the torch encoder/decoder may pick batch-size dependent cuDNN algorithms; compare with a tight tolerance there,
     # the ODE latents themselves are checked bit-exactly in test_gpu_kernels.test_batch_composition_does_not_change_a_sample
     assert _rel(xb[0:1], x0) < 1e-4 and _rel(xb[1:2], x1) < 1e-4
+
+
+def test_streamed_host_buffer_rollout_equals_device_rollout():
+    """integrate_latents_streamed (pinned host buffers, uploads / downloads pipelined on copy streams) returns exactly what
+    integrate_latents returns on device-resident inputs, for samples with different schedules."""
+    m = _nnfo("euler", True, True, 5, 1.0, "bf16")
+    h = w = 24
+    times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0]), sorted([-1.013, -0.492, -0.004, -0.81, -0.6, -0.418, -0.2, 0.011]),
+             [-1.0, -0.5, 0.0]]
+    targets = [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0], [-1.0, -0.5, 0.0, 0.49, 1.0, 1.52, 2.0], [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]]
+    counts = [len(t) for t in times]
+    hx = torch.tanh(so.recipe_array("hx", (sum(counts), 64, h, w), 5))
+    tape = torch.stack([so.recipe_array(f"eps{i}", (64, h, w), 5) for i in range(64)]).cuda()
+    m._draw_noise = lambda n, hh, ww, device: tape[:max(n, 1)].contiguous()
+    with torch.no_grad():
+        s_dev, sel_dev = m.integrate_latents(hx.cuda(), counts, times, targets, 0.05)
+        s_host, sel_host = m.integrate_latents_streamed(hx.pin_memory(), counts, times, targets, 0.05)
+    torch.cuda.synchronize()
+    assert torch.equal(s_dev, s_host) and torch.equal(sel_dev.cpu(), sel_host)
