@@ -234,7 +234,7 @@ def main():
     value = world * steps_per_rollout * args.steps / (ms_total * 1e-3)
 
     # ---------------- end to end with host buffers
-    sel_host = torch.empty((B, len(TARGETS), 64, hw, hw), dtype=torch.float32).pin_memory()
+    sel_host = torch.empty((len(TARGETS), B, 64, hw, hw), dtype=torch.float32).pin_memory()
 
     def e2e_once():
         with torch.no_grad():

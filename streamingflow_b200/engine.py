@@ -306,11 +306,12 @@ class OdeEngine:
         if lo is not None:
             lo.zero_()
 
-    def unpack_path(self, slots: Sequence[int]) -> torch.Tensor:
+    def unpack_path(self, slots, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Recorded states (NHWC fp32 path buffer) -> NCHW fp32 [len(slots), 64, H, W]."""
-        idx = torch.tensor(list(slots), dtype=torch.int32, device=self.device)
-        out = torch.empty((len(slots), self.C, self.H, self.W), dtype=torch.float32, device=self.device)
-        L.check(self.lib.sf_unpack_nhwc_f32(self.path.data_ptr(), out.data_ptr(), idx.data_ptr(), len(slots), self.C, self.H, self.W,
+        idx = slots if isinstance(slots, torch.Tensor) else torch.tensor(list(slots), dtype=torch.int32, device=self.device)
+        n = idx.numel()
+        out = torch.empty((n, self.C, self.H, self.W), dtype=torch.float32, device=self.device) if out is None else out
+        L.check(self.lib.sf_unpack_nhwc_f32(self.path.data_ptr(), out.data_ptr(), idx.data_ptr(), n, self.C, self.H, self.W,
                                             self._stream()), "sf_unpack_nhwc_f32")
         return out
 

@@ -304,7 +304,7 @@ class NNFOwithBayesianJumps(nn.Module):
 
     def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None):
         """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final
-        states on device, selected latents in the pinned CPU tensor ``out_host`` [B, T, C, h, w]).  Host<->device copies are
+        states on device, selected latents [B, T, C, h, w] as a view of the pinned CPU tensor ``out_host`` [T, B, C, h, w]).  Host<->device copies are
         pipelined against the rollout: observation k of every sample is uploaded on a copy stream while earlier events run
         (a jump only needs its own frame), and each target's selected state is gathered and downloaded as soon as the
         event that produces it has been enqueued."""
@@ -322,7 +322,8 @@ class NNFOwithBayesianJumps(nn.Module):
         eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
         T = len(targets[0])
         if out_host is None:
-            out_host = torch.empty((B, T, c, h, w), dtype=torch.float32).pin_memory()
+            out_host = torch.empty((T, B, c, h, w), dtype=torch.float32).pin_memory()
+        assert tuple(out_host.shape) == (T, B, c, h, w) and out_host.is_contiguous()
         main = torch.cuda.current_stream(dev)
         if "_copy_streams" not in self.__dict__:
             self.__dict__["_copy_streams"] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
@@ -346,6 +347,7 @@ class NNFOwithBayesianJumps(nn.Module):
                 up_done.append(e)
         table, evs = eng.build_table(ro.events)
         tdev = eng.upload_table(table)
+        slots_dev = torch.tensor([[ro.out_slots[b][t] for b in range(B)] for t in range(T)], dtype=torch.int32).to(dev)
         last_writer = {}
         for i, e in enumerate(ro.events):
             for slot in e["rec"]:
@@ -363,17 +365,17 @@ class NNFOwithBayesianJumps(nn.Module):
             launches += eng.run_events(evs[i:i + 1], tdev)
             for t in range(T):
                 if t not in flushed and ready_at[t] <= i:
-                    out_dev[t].copy_(eng.unpack_path([ro.out_slots[b][t] for b in range(B)]))
+                    eng.unpack_path(slots_dev[t], out=out_dev[t])
                     done = torch.cuda.Event()
                     done.record(main)
                     s_out.wait_event(done)
                     with torch.cuda.stream(s_out):
-                        out_host[:, t].copy_(out_dev[t], non_blocking=True)
+                        out_host[t].copy_(out_dev[t], non_blocking=True)      # contiguous pinned destination: one async DMA
                     flushed.add(t)
         main.wait_stream(s_out)
         ro.launches = launches
         self.last_rollout = ro
-        return eng.unpack_f32(eng.state32[0], B), out_host
+        return eng.unpack_f32(eng.state32[0], B), out_host.transpose(0, 1)
 
     def forward(self, times, input, obs, delta_t, T, return_path=True):
         """Reference :479-627.  times: observation times in processing order; input: only its shape is used;
