@@ -140,6 +140,12 @@ int sf_plan_run_events(sf_plan* p, const sf_event* evs, int n_events, const int3
 /* number of kernels the last sf_plan_run_events call launched */
 int sf_plan_last_launches(sf_plan* p);
 
+/* the two halves of an SE layer, for callers that reduce the channel sums across GPUs in between (row sharding):
+   reduce over the pixel window [px0, px1) of each active sample -> returns the number of per-block partial sums written
+   to SF_F32_SE_SUMS[which][sample][partial][2C]; apply with mean = (sum of the first n_partials partials) * inv_n      */
+int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream);
+int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream);
+
 /* layout kernels (HBM-bound, 128-bit vectorised) */
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);
 int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n_out, int C, int H, int W, void* stream);

@@ -48,6 +48,8 @@ EXPORTS = {
     "sf_plan_run_stage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_void_p]),
     "sf_plan_run_events": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_int, C.c_void_p, C.c_void_p]),
     "sf_plan_last_launches": (C.c_int, [C.c_void_p]),
+    "sf_plan_se_reduce": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "sf_plan_se_apply": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "sf_pack_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),

@@ -252,25 +252,50 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   return SF_OK;
 }
 
-int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+constexpr int SE_MAX_PARTIALS = 64;
+
+// SE step 1 over the pixel window [px0, px1) of every active sample; returns the number of per-block partials (> 0) or < 0
+int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, cudaStream_t stream) {
   const SeDef& se = p->se[which];
   if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
-  if (ev->n_active <= 0) return SF_OK;
   const bool x3 = p->g.precision == SF_PREC_BF16X3;
   const int CH = 2 * p->g.C;
   const int hw = p->g.H * p->g.W;
   float* sums = reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]);
   if (!sums) return fail(SF_ERR_STATE, "SE sums buffer not bound");
-  constexpr int SE_MAX_PARTIALS = 64;
+  sums += (size_t)which * p->g.max_images * SE_MAX_PARTIALS * CH;
+  const ActBuf& zi = p->act[se.in_buf];
+  if (!zi.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
+  if (px0 < 0 || px1 > hw || px0 >= px1) return fail(SF_ERR_INVALID, "bad SE pixel window");
+  const int* sid = table + ev->table_off;
+  int bpi = (px1 - px0 + 32 * 4 * 2 - 1) / (32 * 4 * 2);     // ~2 iterations of 4 x 32 pixels per block
+  if (bpi > SE_MAX_PARTIALS) bpi = SE_MAX_PARTIALS;
+  if (bpi < 1) bpi = 1;
+  dim3 grid(bpi, ev->n_active);
+  auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
+  auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
+  if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1);
+  else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1);
+  SF_CUDA(cudaGetLastError());
+  p->last_launches += 1;
+  return bpi;
+}
+
+// SE step 2: mean = (sum of n_partials partial sums) * inv_n; y = z * sigmoid(fc2 relu(fc1 mean))
+int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, cudaStream_t stream) {
+  const SeDef& se = p->se[which];
+  if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
+  const bool x3 = p->g.precision == SF_PREC_BF16X3;
+  const int CH = 2 * p->g.C;
+  const int hw = p->g.H * p->g.W;
+  float* sums = reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]);
+  if (!sums) return fail(SF_ERR_STATE, "SE sums buffer not bound");
   sums += (size_t)which * p->g.max_images * SE_MAX_PARTIALS * CH;
   const ActBuf& zi = p->act[se.in_buf];
   const ActBuf& yo = p->act[se.out_buf];
   if (!zi.hi || !yo.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
+  if (n_partials < 1 || n_partials > SE_MAX_PARTIALS) return fail(SF_ERR_INVALID, "bad SE partial count");
   const int* sid = table + ev->table_off;
-  int bpi = (hw + 32 * 4 * 2 - 1) / (32 * 4 * 2);     // ~2 iterations of 4 x 32 pixels per block
-  if (bpi > SE_MAX_PARTIALS) bpi = SE_MAX_PARTIALS;
-  if (bpi < 1) bpi = 1;
-  dim3 grid(bpi, ev->n_active);
   auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
   auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
   auto yh = reinterpret_cast<__nv_bfloat16*>(yo.hi);
@@ -280,17 +305,19 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   if (bpa > cap) bpa = cap;
   if (bpa < 1) bpa = 1;
   dim3 grid2(bpa, ev->n_active);
-  const float inv_n = 1.0f / (float)hw;
-  if (x3) {
-    se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, 0, hw);
-    se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw, inv_n);
-  } else {
-    se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, 0, hw);
-    se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, bpi, se.fc1, se.fc2, sid, hw, inv_n);
-  }
+  if (x3) se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, n_partials, se.fc1, se.fc2, sid, hw, inv_n);
+  else se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, n_partials, se.fc1, se.fc2, sid, hw, inv_n);
   SF_CUDA(cudaGetLastError());
-  p->last_launches += 2;
+  p->last_launches += 1;
   return SF_OK;
+}
+
+int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  if (ev->n_active <= 0) return SF_OK;
+  const int hw = p->g.H * p->g.W;
+  int n = launch_se_reduce(p, which, ev, table, 0, hw, stream);
+  if (n < 0) return n;
+  return launch_se_apply(p, which, ev, table, n, 1.0f / (float)hw, stream);
 }
 
 int run_item(sf_plan* p, int item, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
@@ -459,6 +486,16 @@ int sf_plan_run_events(sf_plan* p, const sf_event* evs, int n_events, const int3
 }
 
 int sf_plan_last_launches(sf_plan* p) { return p ? p->last_launches : 0; }
+
+int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream) {
+  if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
+  return launch_se_reduce(p, which, ev, table, px0, px1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream) {
+  if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
+  return launch_se_apply(p, which, ev, table, n_partials, inv_n, reinterpret_cast<cudaStream_t>(stream));
+}
 
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream) {
   if (!src || !dst_hi || C % 64 || n_images <= 0) return fail(SF_ERR_INVALID, "bad pack arguments");

@@ -1,0 +1,176 @@
+"""Row sharding of ONE large BEV grid across the GPUs of a node (BASELINE config 5).
+
+Each rank owns a contiguous band of latent rows and keeps HALO = 12 extra rows above and below it:
+  * the dual-GRU cell sees the state within 7 rows and its x input within 6 rows of an output pixel (6x 3x3 + 7x7 + 3x3 in
+    series), the prior network p_model sees the new state within 5 rows; an event therefore yields a correct
+    sampled input x' on a band only if (state, x) were correct within 7 + 5 = 12 rows of it;
+  * per event every rank runs the UNCHANGED stage kernels on its local image (band + halos), then swaps 12 boundary rows of
+    the new state (fp32 master + bf16 operand planes) and of x' with its two neighbours (NCCL send/recv over NVLink):
+    one exchange per event instead of one per conv stage, paid for with (24 / band) redundant rows of compute;
+  * the two squeeze-excite layers need WHOLE-image channel means: each rank reduces over its own band only
+    (sf_plan_se_reduce with a pixel window), the [B, 2C] partial sums are all-reduced (sum), then sf_plan_se_apply runs.
+Zero padding at the true image border comes from TMA's out-of-bounds fill on the first / last rank; on interior ranks the
+local image's outer rows are halo data and whatever the fill corrupts stays inside the discarded part of the halo.
+
+Noise must be identical on all ranks (it is indexed by GLOBAL pixel): rank 0 broadcasts a seed, every rank draws the full
+tensor from a generator seeded with it and keeps its rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .rollout import compile_rollout
+from .schedule import plan_sample
+from .sharding import shard_bounds
+
+HALO = 12          # 7 (cell w.r.t. state) + 5 (p_model w.r.t. the new state)
+
+
+def local_window(h: int, rank: int, world: int, halo: int = HALO) -> Tuple[int, int, int, int]:
+    """(own_lo, own_hi, lo, hi): the rank's band [own_lo, own_hi) and its local image [lo, hi) of global latent rows."""
+    own_lo, own_hi = shard_bounds(h, rank, world)
+    if world > 1 and own_hi - own_lo < halo:
+        raise ValueError(f"band of {own_hi - own_lo} rows is thinner than the {halo}-row halo; use fewer ranks")
+    return own_lo, own_hi, max(0, own_lo - halo), min(h, own_hi + halo)
+
+
+def exchange_halo_rows(t: torch.Tensor, own_lo: int, own_hi: int, lo: int, hi: int, rank: int, world: int, group=None,
+                       halo: int = HALO):
+    """t: [B, hi - lo, W, C] (NHWC local image, any dtype).  Sends the band's first / last ``halo`` rows to the upper / lower
+    neighbour and fills the local halos with theirs.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    if world == 1:
+        return
+    ops, recvs = [], []
+    a, b = own_lo - lo, own_hi - lo              # band inside the local image
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if rank > 0:
+        send_up = t[:, a:a + halo].contiguous()
+        recv_up = torch.empty_like(t[:, a - halo:a].contiguous())
+        ops += [dist.P2POp(dist.isend, send_up, peer(rank - 1), group), dist.P2POp(dist.irecv, recv_up, peer(rank - 1), group)]
+        recvs.append((slice(a - halo, a), recv_up))
+    if rank < world - 1:
+        send_dn = t[:, b - halo:b].contiguous()
+        recv_dn = torch.empty_like(t[:, b:b + halo].contiguous())
+        ops += [dist.P2POp(dist.isend, send_dn, peer(rank + 1), group), dist.P2POp(dist.irecv, recv_dn, peer(rank + 1), group)]
+        recvs.append((slice(b, b + halo), recv_dn))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for rows, buf in recvs:
+        t[:, rows].copy_(buf)
+
+
+class RowShardedOde:
+    """Integrates the latent rollout of a NNFOwithBayesianJumps module with the grid's rows split over the ranks of ``group``."""
+
+    def __init__(self, ode, h: int, w: int, batch: int, group=None):
+        from .engine import OdeEngine
+
+        self.ode, self.h, self.w, self.B, self.group = ode, h, w, batch, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.own_lo, self.own_hi, self.lo, self.hi = local_window(h, self.rank, self.world)
+        dev = next(ode.parameters()).device
+        if ode.training:
+            raise L.SfError("eval mode only")
+        self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev)
+        self.device = dev
+        self.launches = 0
+
+    # ------------------------------------------------------------------ noise shared by all ranks
+    def draw_noise(self, n: int) -> torch.Tensor:
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.broadcast(seed, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        g = torch.Generator(device=self.device).manual_seed(int(seed.item()))
+        rows = self.hi - self.lo
+        eps = torch.empty((max(n, 1), 64, rows, self.w), dtype=torch.float32, device=self.device)
+        full = torch.empty((64, self.h, self.w), dtype=torch.float32, device=self.device)
+        for i in range(n):
+            full.normal_(generator=g)
+            eps[i].copy_(full[:, self.lo:self.hi])
+        return eps
+
+    # ------------------------------------------------------------------ one engine event with the collectives in place
+    def _run_event(self, ev_dict: dict):
+        from .engine import BUF_S0, BUF_X, PRIOR_ITEMS
+
+        eng, lib = self.eng, self.eng.lib
+        table, evs = eng.build_table([ev_dict])
+        tdev = eng.upload_table(table)
+        ev = evs[0]
+        stream = eng._stream()
+        rows_own0, rows_own1 = (self.own_lo - self.lo) * self.w, (self.own_hi - self.lo) * self.w
+        n = ev.n_active
+        with torch.cuda.device(self.device):
+            if ev.run_cell:
+                for st in range(6):
+                    L.check(lib.sf_plan_run_stage(eng.plan, st + 6 * ev.kind, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
+                self.launches += 6
+            if ev.run_prior:
+                for item in PRIOR_ITEMS:
+                    if item < L.SE_ITEM_BASE:
+                        L.check(lib.sf_plan_run_stage(eng.plan, item, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
+                        self.launches += 1
+                        continue
+                    which = item - L.SE_ITEM_BASE
+                    npart = L.check(lib.sf_plan_se_reduce(eng.plan, which, C.byref(ev), tdev.data_ptr(), rows_own0, rows_own1, stream),
+                                    "se_reduce")
+                    flat = eng.se_sums[which].view(-1)                  # kernel layout: [active sample][partial][2C], packed
+                    total = flat[: n * npart * 128].view(n, npart, 128).sum(dim=1)      # this rank's band
+                    if self.world > 1:
+                        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+                    flat[: n * 128].view(n, 128).copy_(total)           # one "partial" per sample = the whole-image sum
+                    L.check(lib.sf_plan_se_apply(eng.plan, which, C.byref(ev), tdev.data_ptr(), 1, C.c_float(1.0 / (self.h * self.w)),
+                                                 stream), "se_apply")
+                    self.launches += 2
+        # halos of everything the next event reads: new state (fp32 master + operand planes) and the sampled input
+        s = ev.s_out
+        xs = [eng.state32[s]] + [p for p in eng.act[BUF_S0 + s] if p is not None]
+        if ev.run_prior:
+            xs += [p for p in eng.act[BUF_X] if p is not None]
+        for t in xs:
+            exchange_halo_rows(t, self.own_lo, self.own_hi, self.lo, self.hi, self.rank, self.world, self.group)
+
+    def integrate(self, hx_obs: torch.Tensor, obs_counts: Sequence[int], times, targets, delta_t: float,
+                  noise: Optional[torch.Tensor] = None):
+        """hx_obs: the FULL [sum(obs_counts), C, h, w] encoded observations (every rank passes the same tensor; only its rows
+        are used).  noise: optional full-size tape [n, C, h, w] (tests).  Returns the selected latents restricted to this
+        rank's band: [B, T, C, own rows, w], plus the Rollout."""
+        ode, eng = self.ode, self.eng
+        B = len(obs_counts)
+        plans = [plan_sample(times[b], targets[b], delta_t, ode.use_variable_ode_step, ode.solver) for b in range(B)]
+        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+        ro = compile_rollout(plans, base, ode.solver, bool(ode.impute))
+        eng.bind_observations(hx_obs[:, :, self.lo:self.hi].contiguous())
+        eng.zero_state(0)
+        eng.ensure_path_slots(ro.n_path)
+        eng.bind_eps(noise[:, :, self.lo:self.hi].contiguous() if noise is not None else self.draw_noise(ro.n_eps))
+        for e in ro.events:
+            # the group's samples are indexed by sample id in the engine; x images of jumps are rows of the bound observations
+            self._run_event(e)
+        T = len(targets[0])
+        flat = [s for slots in ro.out_slots for s in slots]
+        sel = eng.unpack_path(flat).view(B, T, 64, self.hi - self.lo, self.w)
+        ro.launches = self.launches
+        return sel[:, :, :, self.own_lo - self.lo:self.own_hi - self.lo].contiguous(), ro
+
+    def gather_rows(self, band: torch.Tensor) -> torch.Tensor:
+        """all_gather of the bands along the row axis -> the full [B, T, C, h, w] tensor on every rank."""
+        if self.world == 1:
+            return band
+        sizes = [shard_bounds(self.h, r, self.world) for r in range(self.world)]
+        parts = [torch.empty(band.shape[:3] + (b - a, self.w), dtype=band.dtype, device=band.device) for a, b in sizes]
+        if len({b - a for a, b in sizes}) == 1:
+            dist.all_gather(parts, band, group=self.group)
+        else:
+            for r, buf in enumerate(parts):
+                if r == self.rank:
+                    buf.copy_(band)
+                dist.broadcast(buf, src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+        return torch.cat(parts, dim=3)

@@ -69,3 +69,35 @@ def test_two_rank_sharded_forward_equals_single_process(tmp_path):
     assert got.shape == ref.shape
     err = ((got - ref).abs().max() / ref.abs().max()).item()
     assert err < 1e-12, err
+
+
+def _halo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from streamingflow_b200.row_sharding import HALO, exchange_halo_rows, local_window
+
+    h, w, B, C = 60, 5, 2, 3
+    full = torch.arange(B * h * w * C, dtype=torch.float32).view(B, h, w, C)
+    own_lo, own_hi, lo, hi = local_window(h, rank, world)
+    t = torch.full((B, hi - lo, w, C), -1.0)
+    t[:, own_lo - lo:own_hi - lo] = full[:, own_lo:own_hi]          # only the band is valid before the exchange
+    exchange_halo_rows(t, own_lo, own_hi, lo, hi, rank, world)
+    ok = torch.equal(t, full[:, lo:hi])
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(int(ok)))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_fills_the_local_window(tmp_path):
+    """Row sharding host logic on CPU (gloo, 3 ranks): after one exchange every rank's local image (band + 12-row halos)
+    equals the corresponding rows of the global grid."""
+    from streamingflow_b200.row_sharding import local_window
+
+    assert local_window(400, 0, 8) == (0, 50, 0, 62) and local_window(400, 3, 8) == (150, 200, 138, 212)
+    assert local_window(400, 7, 8) == (350, 400, 338, 400)
+    with pytest.raises(ValueError):
+        local_window(50, 1, 8)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_halo_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert all(open(tmp_path / f"ok{r}").read() == "1" for r in range(3))
