@@ -220,6 +220,24 @@ def gen_c64_latent(ref, out_dir):
               f"ref f32-vs-f64 state {res['ref_f32_state_err']:.2e} x {res['ref_f32_x_err']:.2e}")
 
 
+def gen_decoder(ref, out_dir):
+    """The reference Decoder's segmentation branch (models/decoder.py) on a small input: pins oracle.seg_decoder and records
+    the Decoder's parameter shapes so the GPU box can rebuild recipe weights by name."""
+    import importlib
+
+    dec_mod = importlib.import_module("streamingflow.models.decoder")
+    gate = dict(perceive_hdmap=False, predict_pedestrian=False, predict_instance=False, predict_future_flow=False, planning=False)
+    d = dec_mod.Decoder(in_channels=64, n_classes=2, n_present=3, n_hdmap=2, predict_gate=gate).eval().double()
+    shapes = {k: tuple(v.shape) for k, v in d.state_dict().items()}
+    d.load_state_dict(so.recipe_state_dict(shapes, 17, 1.0, torch.float64), strict=True)
+    x = so.recipe_array("dec_in", (1, 2, 64, 32, 32), 17, torch.float64)
+    with torch.no_grad():
+        seg = d(x)["segmentation"]
+    np.savez_compressed(os.path.join(out_dir, "decoder_seg_c64.npz"), seed=17, gain=1.0, seg_f64=seg.numpy(),
+                        shapes_keys=np.array(list(shapes.keys())), shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
+    print("decoder_seg_c64.npz:", tuple(seg.shape), "argmax class-1 fraction", float((seg.argmax(2) == 1).double().mean()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -231,6 +249,7 @@ def main():
     gen_schedules(ref, args.out)
     gen_tiny_full(ref, args.out)
     gen_c64_latent(ref, args.out)
+    gen_decoder(ref, args.out)
 
 
 if __name__ == "__main__":

@@ -445,6 +445,47 @@ def future_prediction_forward(sd: SD, camera_states: Tensor, lidar_states: Optio
 
 
 # --------------------------------------------------------------------------------------------
+# models/decoder.py: the segmentation branch of the BEV decoder ("next" row 3; here only to turn the ODE head's output
+# into occupancy logits / argmax masks for parity tests)
+# --------------------------------------------------------------------------------------------
+def _basic_block(sd: SD, p: str, x: Tensor, stride: int) -> Tensor:
+    """torchvision BasicBlock (resnet18 layers reused by decoder.py:22-31): conv3x3-bn-relu-conv3x3-bn (+ downsample) -relu."""
+    y = F.conv2d(x, sd[p + ".conv1.weight"], None, stride=stride, padding=1)
+    y = torch.relu(_bn_eval(sd, p + ".bn1", y))
+    y = _bn_eval(sd, p + ".bn2", F.conv2d(y, sd[p + ".conv2.weight"], None, stride=1, padding=1))
+    if (p + ".downsample.0.weight") in sd:
+        x = _bn_eval(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride=stride))
+    return torch.relu(x + y)
+
+
+def _upsampling_add(sd: SD, p: str, x: Tensor, skip: Tensor) -> Tensor:
+    """convolutions.py UpsamplingAdd: bilinear x2 -> 1x1 conv -> BN, plus the skip."""
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    x = _bn_eval(sd, p + ".upsample_layer.2", F.conv2d(x, sd[p + ".upsample_layer.1.weight"], None))
+    return x + skip
+
+
+def seg_decoder(sd: SD, p: str, x: Tensor) -> Tensor:
+    """decoder.py:91-140, segmentation output only: x [B,S,C,H,W] -> logits [B,S,n_classes,H,W]."""
+    b, s, c, h, w = x.shape
+    x = x.reshape(b * s, c, h, w)
+    skip1 = x
+    x = torch.relu(_bn_eval(sd, p + ".bn1", F.conv2d(x, sd[p + ".first_conv.weight"], None, stride=2, padding=3)))
+    x = _basic_block(sd, p + ".layer1.1", _basic_block(sd, p + ".layer1.0", x, 1), 1)
+    skip2 = x
+    x = _basic_block(sd, p + ".layer2.1", _basic_block(sd, p + ".layer2.0", x, 2), 1)
+    skip3 = x
+    x = _basic_block(sd, p + ".layer3.1", _basic_block(sd, p + ".layer3.0", x, 2), 1)
+    x = _upsampling_add(sd, p + ".up3_skip", x, skip3)
+    x = _upsampling_add(sd, p + ".up2_skip", x, skip2)
+    x = _upsampling_add(sd, p + ".up1_skip", x, skip1)
+    y = F.conv2d(x, sd[p + ".segmentation_head.0.weight"], None, padding=1)
+    y = torch.relu(_bn_eval(sd, p + ".segmentation_head.1", y))
+    y = F.conv2d(y, sd[p + ".segmentation_head.3.weight"], sd[p + ".segmentation_head.3.bias"])
+    return y.view(b, s, *y.shape[1:])
+
+
+# --------------------------------------------------------------------------------------------
 # deterministic, name-keyed weights and inputs (so fixtures need not ship the tensors)
 # --------------------------------------------------------------------------------------------
 def _rs(seed: int, key: str) -> np.random.RandomState:

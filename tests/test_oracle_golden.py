@@ -127,3 +127,13 @@ def test_operand_rounding_budget():
     e_tf32 = err(run(torch.float32, so.operand_rounding(so.round_tf32)))
     e_x3 = err(run(torch.float32, so.operand_rounding(so.round_bf16, split3=True)))
     assert e_bf16 < 1e-2 and e_x3 < 1e-4 and e_tf32 > 1e-4, (e_bf16, e_tf32, e_x3)
+
+
+def test_decoder_segmentation_branch_matches_reference(golden_dir):
+    """models/decoder.py (segmentation output) -- used by the GPU tests to turn the ODE head's output into occupancy logits."""
+    z = np.load(os.path.join(golden_dir, "decoder_seg_c64.npz"))
+    sd = {"d." + k: v for k, v in so.recipe_state_dict(_shapes(z), int(z["seed"]), float(z["gain"]), torch.float64).items()}
+    x = so.recipe_array("dec_in", (1, 2, 64, 32, 32), int(z["seed"]), torch.float64)
+    with torch.no_grad():
+        seg = so.seg_decoder(sd, "d", x)
+    assert (seg - torch.from_numpy(z["seg_f64"])).abs().max().item() < 1e-11
