@@ -87,7 +87,8 @@ typedef enum {
   SF_F32_A = 2,         /* rnn_state1 (GRU-1 output)                                                      */
   SF_F32_B = 3,         /* rnn_state2 (decoder of GRU-2)                                                  */
   SF_F32_PATH = 4,      /* recorded states [slot][H][W][C]                                                */
-  SF_F32_SE_SUMS = 5,   /* [2][max_images][64][2C] per-block partial channel sums of the two SE layers    */
+  SF_F32_SE_SUMS = 5,   /* SE scratch: partial sums [2][max_images][64][2C] | scales [2][max_images][2C] |
+                           uint32 block counters [2][max_images]; zero-initialised by the caller                */
   SF_F32_EPS = 6,       /* standard-normal noise, NCHW [slot][C][H][W] (torch's generation order)         */
   SF_F32_X = 7,         /* optional fp32 copy of the sampled input x  (infer_state API)                   */
   SF_F32_PARAMS = 8,    /* optional fp32 p_model output [image][H][W][2C] (infer_state API)               */
@@ -142,7 +143,8 @@ int sf_plan_last_launches(sf_plan* p);
 
 /* the two halves of an SE layer, for callers that reduce the channel sums across GPUs in between (row sharding):
    reduce over the pixel window [px0, px1) of each active sample -> returns the number of per-block partial sums written
-   to SF_F32_SE_SUMS[which][sample][partial][2C]; apply with mean = (sum of the first n_partials partials) * inv_n      */
+   to SF_F32_SE_SUMS[which][sample][partial][2C]; apply with mean = (sum of the first n_partials partials) * inv_n
+   (n_partials = 0: the scales were already produced by a whole-image sf_plan_run_* reduce)                          */
 int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream);
 int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream);
 

@@ -276,11 +276,17 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
         load_f32x16(e.a32 + c.pix * 64 + j * 16, a);
         load_f32x16(e.b32 + c.pix * 64 + j * 16, b);
         if (e.kind == 0) {
-          float si[16], sb[16];
+          float si[16];
           load_f32x16(e.s_in + c.pix * 64 + j * 16, si);
-          load_f32x16(e.s_base + c.pix * 64 + j * 16, sb);
+          if (e.s_base == e.s_in) {            // Euler: the update starts from the state the cell read
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = sb[i] + dt * ((b[i] * g0 + a[i] * g1) - si[i]);
+            for (int i = 0; i < 16; ++i) o[i] = si[i] + dt * ((b[i] * g0 + a[i] * g1) - si[i]);
+          } else {                             // midpoint stage 2: base = s, cell state = k
+            float sb[16];
+            load_f32x16(e.s_base + c.pix * 64 + j * 16, sb);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = sb[i] + dt * ((b[i] * g0 + a[i] * g1) - si[i]);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = b[i] * g0 + a[i] * g1;
@@ -442,12 +448,13 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) c
           __syncwarp();
           if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }
           const int tap_rows = ck.n * ck.nrep;                  // weight rows of one tap
-          const int grp_rows = tap_rows * ck.tb;                // rows of one B tile (tb taps)
-          const int ngrp = R / ck.tb;                           // B tiles per dx column (R or 1)
+          const int ngrp = (R + ck.tb - 1) / ck.tb;             // B tiles per dx column; the last one may hold fewer taps
           int dx = rem % R, g0 = (ck.tb == 1) ? (rem / R) % R : 0;     // tap rotation (same formula in the MMA warp)
           for (int i = 0; i < R; ++i) {
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
+              const int ntap = min(ck.tb, R - gi * ck.tb);
+              const int grp_rows = tap_rows * ntap;             // rows of this B tile
               mbar_wait(b_empty0 + sb * 8, pb, p.err, 2);
               if (elect_one()) {
                 mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) c
           const uint32_t idesc = make_idesc_bf16(128, (uint32_t)ck.n);
           const uint32_t d_addr = d_base + ck.col;
           const uint32_t rep_lo = (uint32_t)(ck.n * ROW_BYTES) >> 4;
-          const int ngrp = R / ck.tb;
+          const int ngrp = (R + ck.tb - 1) / ck.tb;
           const int g0 = (ck.tb == 1) ? (rem / R) % R : 0;
           uint32_t accumulate = ck.init ? 0u : 1u;
           mbar_wait(a_full0 + sa * 8, pa, p.err, 4);
@@ -498,14 +505,17 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) c
               uint32_t b_lo = ((b_smem0 + sb * p.b_slot_bytes) & 0x3FFFFu) >> 4;
               // first tap of this group: dy = gi*tb; one pixel row = 128 B = 8 descriptor units
               uint32_t a_lo = a_lo0 + ((uint32_t)(gi * ck.tb) * WP + (uint32_t)dx) * (ROW_BYTES >> 4);
+              const int ntap = min(ck.tb, R - gi * ck.tb);
               if (elect_one()) {
                 uint32_t acc = accumulate;
-                for (int t = 0; t < ck.tb; ++t, a_lo += WP * (ROW_BYTES >> 4)) {
+                for (int t = 0; t < ntap; ++t, a_lo += WP * (ROW_BYTES >> 4)) {
                   for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo) {
+                    // 4 x (K = 16 bf16 = 32 bytes = 2 descriptor units) per 64-channel chunk; the M-tiles alternate so that
+                    // consecutive MMAs hit different accumulators (no back-to-back dependency on one TMEM slot)
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
+                    for (uint32_t k = 0; k < 4; ++k) {
 #pragma unroll
-                      for (uint32_t k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes = 2 descriptor units) per 64-channel chunk
+                      for (int mt = 0; mt < MT; ++mt) {
                         umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_lo + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
                                   ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc, acc | (k > 0 ? 1u : 0u));
                       }

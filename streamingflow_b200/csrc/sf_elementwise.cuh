@@ -5,12 +5,56 @@
 
 namespace sf {
 
+// scale[c] = sigmoid(fc2 . relu(fc1 . mean)), mean[c] = inv_n * sum_k partial[k][c]; one 256-thread block, fixed order.
+template <int CH>
+__device__ __forceinline__ void se_scale_from_partials(const float* partials, int n_partials, float inv_n, const float* fc1,
+                                                       const float* fc2, float* scale_out, float* scratch) {
+  constexpr int HID = CH / 8;
+  float* mean_s = scratch;            // CH
+  float* hid_s = scratch + CH;        // HID
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    float t = 0.0f;
+    for (int k = 0; k < n_partials; ++k) t += partials[(size_t)k * CH + threadIdx.x];
+    mean_s[threadIdx.x] = t * inv_n;
+  }
+  __syncthreads();
+  {   // FC1: HID outputs, 256 / HID = 16 threads each (CH / 16 = 8 inputs per thread), shuffle-reduced
+    constexpr int TPO = 256 / HID;
+    const int o = threadIdx.x / TPO, part = threadIdx.x % TPO;
+    float a = 0.0f;
+    for (int c = part; c < CH; c += TPO) a = fmaf(fc1[o * CH + c], mean_s[c], a);
+#pragma unroll
+    for (int d = TPO / 2; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (part == 0) hid_s[o] = fmaxf(a, 0.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    float a = 0.0f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) a = fmaf(fc2[threadIdx.x * HID + j], hid_s[j], a);
+    scale_out[threadIdx.x] = __fdividef(1.0f, 1.0f + __expf(-a));
+  }
+}
+
+// tiny kernel for the row-sharded path: scales from already all-reduced sums (one "partial" per sample)
+template <int CH>
+__global__ void __launch_bounds__(256) se_scale_kernel(const float* __restrict__ sums, int n_partials, float inv_n,
+                                                       const float* __restrict__ fc1, const float* __restrict__ fc2,
+                                                       float* __restrict__ scale_out) {
+  __shared__ float scratch[CH + CH / 8];
+  se_scale_from_partials<CH>(sums + (size_t)blockIdx.x * n_partials * CH, n_partials, inv_n, fc1, fc2, scale_out + (size_t)blockIdx.x * CH,
+                             scratch);
+}
+
 // ---- SE step 1: per-(sample, channel) sums over the H*W pixels of a [img][H*W][CH] bf16 tensor --------
 // grid = (blocks_per_image, n_active); block = 256 threads = 8 channel groups (16 ch = 32 B, one 256-bit load) x 32 pixel
 // lanes, 4 independent loads in flight per thread.  Optional row window [row0, row1) (row sharding: own rows only).
 template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
-                                                        float* __restrict__ sums, const int* __restrict__ sample_id, int hw, int px0, int px1) {
+                                                        float* __restrict__ sums, const int* __restrict__ sample_id, int hw, int px0, int px1,
+                                                        unsigned int* __restrict__ counters, float* __restrict__ scale_out,
+                                                        const float* __restrict__ fc1, const float* __restrict__ fc2, float inv_n) {
   static_assert(CH == 128, "SE layers of the prior network have 2C = 128 channels");
   constexpr int GROUPS = CH / 16;           // 8
   constexpr int LANES = 256 / GROUPS;       // 32 pixels per block iteration
@@ -58,46 +102,34 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
     float s = 0.0f;
 #pragma unroll
     for (int l = 0; l < LANES; ++l) s += red[l][threadIdx.x];
-    // per-block partial sums, combined in a fixed order by se_apply: deterministic (no float atomics)
+    // per-block partial sums, combined in a fixed order below: deterministic (no float atomics)
     sums[((size_t)bi * gridDim.x + blockIdx.x) * CH + threadIdx.x] = s;
   }
+  if (scale_out == nullptr) return;            // caller combines the partials itself (row sharding: all-reduce in between)
+  // last block of this sample: mean -> FC(2C -> 2C/8) -> ReLU -> FC -> sigmoid, written once for se_apply to stream with
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counters + bi, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  se_scale_from_partials<CH>(sums + (size_t)bi * gridDim.x * CH, gridDim.x, inv_n, fc1, fc2, scale_out + (size_t)bi * CH, &red[0][0]);
+  if (threadIdx.x == 0) counters[bi] = 0;      // ready for the next launch
 }
 
-// ---- SE step 2: scale = sigmoid(fc2 * relu(fc1 * mean)); y = z * scale ---------------------------------
-// every block recomputes the 2 tiny FCs (128x16 each) for its sample, then streams its share of pixels with 256-bit
-// loads / stores, 4 in flight per thread.  n_mean = number of pixels behind the sums (H*W of the WHOLE image).
+// ---- SE step 2: y = z * scale (scale computed by se_reduce's last block / se_scale_kernel) ------------------
+// pure streaming: 256-bit loads / stores, 4 in flight per thread.
 template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
                                                        __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
-                                                       const float* __restrict__ sums, int n_partials, const float* __restrict__ fc1,
-                                                       const float* __restrict__ fc2, const int* __restrict__ sample_id, int hw,
-                                                       float inv_n_mean) {
-  constexpr int HID = CH / 8;               // reduction 8
+                                                       const float* __restrict__ scale, const int* __restrict__ sample_id, int hw) {
   constexpr int GROUPS = CH / 16;
   constexpr int LANES = 256 / GROUPS;
   constexpr int UNROLL = 4;
-  __shared__ float mean_s[CH], hid_s[HID], scale_s[CH];
   const int bi = blockIdx.y;
   const int sid = sample_id[bi];
-  if (threadIdx.x < CH) {
-    float t = 0.0f;
-    for (int k = 0; k < n_partials; ++k) t += sums[((size_t)bi * n_partials + k) * CH + threadIdx.x];
-    mean_s[threadIdx.x] = t * inv_n_mean;
-  }
-  __syncthreads();
-  if (threadIdx.x < HID) {
-    float a = 0.0f;
-    for (int c = 0; c < CH; ++c) a = fmaf(fc1[threadIdx.x * CH + c], mean_s[c], a);
-    hid_s[threadIdx.x] = fmaxf(a, 0.0f);
-  }
-  __syncthreads();
-  if (threadIdx.x < CH) {
-    float a = 0.0f;
-#pragma unroll
-    for (int j = 0; j < HID; ++j) a = fmaf(fc2[threadIdx.x * HID + j], hid_s[j], a);
-    scale_s[threadIdx.x] = __fdividef(1.0f, 1.0f + __expf(-a));
-  }
-  __syncthreads();
+  const float* scale_s = scale + (size_t)bi * CH;
   const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS;
   const size_t base = (size_t)sid * hw * CH;
   float sc[16];

@@ -253,9 +253,19 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
 }
 
 constexpr int SE_MAX_PARTIALS = 64;
+// layout of the caller's SF_F32_SE_SUMS buffer (floats): partial sums [2][max_images][64][2C] | scales [2][max_images][2C] |
+// block counters [2][max_images] (uint32, must start zeroed)
+float* se_scale_ptr(sf_plan* p, int which) {
+  const size_t CH = 2 * p->g.C, B = p->g.max_images;
+  return reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]) + 2 * B * SE_MAX_PARTIALS * CH + (size_t)which * B * CH;
+}
+unsigned int* se_counter_ptr(sf_plan* p, int which) {
+  const size_t CH = 2 * p->g.C, B = p->g.max_images;
+  return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(p->f32[SF_F32_SE_SUMS]) + 2 * B * SE_MAX_PARTIALS * CH + 2 * B * CH) + (size_t)which * B;
+}
 
 // SE step 1 over the pixel window [px0, px1) of every active sample; returns the number of per-block partials (> 0) or < 0
-int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, cudaStream_t stream) {
+int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, bool fused_scale, cudaStream_t stream) {
   const SeDef& se = p->se[which];
   if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
   const bool x3 = p->g.precision == SF_PREC_BF16X3;
@@ -274,8 +284,13 @@ int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* t
   dim3 grid(bpi, ev->n_active);
   auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
   auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
-  if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1);
-  else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1);
+  // scratch behind the partial sums of both layers: [2][max_images][CH] scales, then [2][max_images] block counters (zeroed once)
+  float* scale = se_scale_ptr(p, which);
+  unsigned int* counters = se_counter_ptr(p, which);
+  float* scale_arg = fused_scale ? scale : nullptr;
+  const float inv_n = 1.0f / (float)hw;
+  if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+  else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
   SF_CUDA(cudaGetLastError());
   p->last_launches += 1;
   return bpi;
@@ -294,7 +309,7 @@ int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* ta
   const ActBuf& zi = p->act[se.in_buf];
   const ActBuf& yo = p->act[se.out_buf];
   if (!zi.hi || !yo.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
-  if (n_partials < 1 || n_partials > SE_MAX_PARTIALS) return fail(SF_ERR_INVALID, "bad SE partial count");
+  if (n_partials < 0 || n_partials > SE_MAX_PARTIALS) return fail(SF_ERR_INVALID, "bad SE partial count");
   const int* sid = table + ev->table_off;
   auto zh = reinterpret_cast<const __nv_bfloat16*>(zi.hi);
   auto zl = reinterpret_cast<const __nv_bfloat16*>(zi.lo);
@@ -305,8 +320,13 @@ int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* ta
   if (bpa > cap) bpa = cap;
   if (bpa < 1) bpa = 1;
   dim3 grid2(bpa, ev->n_active);
-  if (x3) se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, n_partials, se.fc1, se.fc2, sid, hw, inv_n);
-  else se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, sums, n_partials, se.fc1, se.fc2, sid, hw, inv_n);
+  float* scale = se_scale_ptr(p, which);
+  if (n_partials > 0) {     // scales not yet computed by the reduce kernel (caller reduced the sums across GPUs)
+    se_scale_kernel<128><<<ev->n_active, 256, 0, stream>>>(sums, n_partials, inv_n, se.fc1, se.fc2, scale);
+    p->last_launches += 1;
+  }
+  if (x3) se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+  else se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
   SF_CUDA(cudaGetLastError());
   p->last_launches += 1;
   return SF_OK;
@@ -315,9 +335,9 @@ int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* ta
 int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
   if (ev->n_active <= 0) return SF_OK;
   const int hw = p->g.H * p->g.W;
-  int n = launch_se_reduce(p, which, ev, table, 0, hw, stream);
+  int n = launch_se_reduce(p, which, ev, table, 0, hw, true, stream);
   if (n < 0) return n;
-  return launch_se_apply(p, which, ev, table, n, 1.0f / (float)hw, stream);
+  return launch_se_apply(p, which, ev, table, 0, 1.0f / (float)hw, stream);
 }
 
 int run_item(sf_plan* p, int item, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
@@ -397,7 +417,10 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
     // a whole dx column of taps travels as ONE weight tile when it is small enough: fewer barrier round trips per MMA
-    const int tb = (c.R * c.n * c.nrep * ROW_BYTES <= B_TILE_MAX) ? c.R : 1;
+    const int tap_bytes = c.n * c.nrep * ROW_BYTES;
+    int tb = B_TILE_MAX / tap_bytes;
+    if (tb < 1) tb = 1;
+    if (tb > c.R) tb = c.R;
     st.tb.push_back(tb);
     const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
     a_slot = a > a_slot ? a : a_slot;
@@ -489,7 +512,7 @@ int sf_plan_last_launches(sf_plan* p) { return p ? p->last_launches : 0; }
 
 int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream) {
   if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
-  return launch_se_reduce(p, which, ev, table, px0, px1, reinterpret_cast<cudaStream_t>(stream));
+  return launch_se_reduce(p, which, ev, table, px0, px1, false, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream) {
