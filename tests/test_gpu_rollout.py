@@ -183,3 +183,46 @@ def test_streamed_host_buffer_rollout_equals_device_rollout():
         s_host, sel_host = m.integrate_latents_streamed(hx.pin_memory(), counts, times, targets, 0.05)
     torch.cuda.synchronize()
     assert torch.equal(s_dev, s_host) and torch.equal(sel_dev.cpu(), sel_host)
+
+
+@pytest.mark.parametrize("config", ["config3_streaming_40_steps", "config4_8s_horizon"])
+def test_long_rollout_configs_match_oracle(config):
+    """BASELINE configs 3 and 4 as parity cases (small grid so the fp64 oracle finishes in seconds): config 3 = streaming
+    evaluation, 3 past + 40 future targets at 0.05 s (46 state-steps / sample); config 4 = 8 s horizon, 16 targets at 0.5 s
+    (22 state-steps / sample).  B = 3 samples, one of them with jittered stamps."""
+    precision = "bf16x3"
+    m = _nnfo("euler", True, True, 31, 1.0, precision)
+    m.record_all = True
+    h = w = 20
+    canon = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
+    jit = sorted([-1.013, -0.492, -0.004, -0.81, -0.6, -0.418, -0.2, 0.011])
+    if config.startswith("config3"):
+        tg = [-1.0, -0.5, 0.0] + [0.05 * i for i in range(1, 41)]
+    else:
+        tg = [-1.0, -0.5, 0.0] + [0.5 * i for i in range(1, 17)]
+    times, targets = [canon, jit, canon], [tg, tg, tg]
+    counts = [8, 8, 8]
+    hx = torch.tanh(so.recipe_array("hx", (24, 64, h, w), 31))
+    n_eps = sum(len(so.build_schedule(t, tg, 0.05, True).events) for t in times)
+    tape = torch.stack([so.recipe_array(f"eps{i}", (64, h, w), 31) for i in range(n_eps)])
+    m._draw_noise = lambda n, hh, ww, device: tape[:max(n, 1)].cuda().contiguous()
+    with torch.no_grad():
+        _, sel = m.integrate_latents(hx.cuda(), counts, times, targets, 0.05)
+    torch.cuda.synchronize()
+    assert m.last_rollout.n_state_steps == sum(sum(e.kind == "step" for e in so.build_schedule(t, tg, 0.05, True).events) for t in times)
+    sd = {"g." + k: v.double() for k, v in m.state_dict().items() if v.is_floating_point()}
+    sd = {k: v.cpu() for k, v in sd.items()}
+    it = iter(tape.double()[:, None])
+    worst = 0.0
+    for b in range(3):
+        sch = so.build_schedule(times[b], tg, 0.05, True)
+        tr = []
+        with torch.no_grad():
+            so.integrate_latent(sd, "g", hx[8 * b:8 * b + 8].double(), sch, it, trace=tr)
+        ref = torch.cat(tr, 0)
+        got = m.last_trace[b].cpu().double()
+        assert got.shape == ref.shape
+        worst = max(worst, max(_rel(got[i], ref[i]) for i in range(ref.shape[0])))
+        want_sel = torch.stack([tr[sch.path_ev[i]][0] for i in sch.select])
+        assert _rel(sel[b].cpu(), want_sel) < TOL[precision]
+    assert worst < TOL[precision], f"{config}: per-event latent error {worst:.3e}"
