@@ -303,9 +303,7 @@ def time_stages(eng, B, hw, peaks, reps=10):
                s_base=0, s_out=0, run_cell=1, run_prior=1, want_f32=0)
     table, evs = eng.build_table([evd])
     tdev = eng.upload_table(table)
-    names = dict(zip(range(6), en.CELL_STAGE_NAMES))
-    names.update({en.ST_Q1: "q1", en.ST_Q2: "q2", en.ST_Q3: "q3", en.ST_Q4: "q4", en.ST_Q5: "q5",
-                  L.SE_ITEM_BASE: "se1", L.SE_ITEM_BASE + 1: "se2"})
+    names = dict(eng.stage_names)          # derivative-cell stages, prior-network stages, the two SE layers
     out = {}
     for slot, name in names.items():
         for _ in range(2):

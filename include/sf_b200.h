@@ -75,7 +75,7 @@ typedef struct {
 typedef struct {
   int32_t max_images;   /* capacity (samples) of the per-sample buffers                                  */
   int32_t H, W;         /* ODE grid (latent) height / width                                               */
-  int32_t C;            /* hidden channels (64)                                                           */
+  int32_t C;            /* hidden channels: 64 or 128                                                     */
   int32_t precision;    /* SF_PREC_*                                                                      */
   int32_t device;       /* CUDA device ordinal                                                            */
 } sf_geometry;
@@ -124,9 +124,12 @@ int sf_plan_destroy(sf_plan* p);
 int sf_plan_bind_act(sf_plan* p, int buf, void* hi, void* lo, int channels, int n_images);
 int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
 /* packed weights: bf16 [w_rows][64] device pointer; vec: fp32 device pointer (bias / LN / gate weights) */
+/* io_bufs / io_choff: the epilogue's activation buffers and the first channel each launch touches in them, in the order
+   the epilogue expects (gates: u_0, gated_0[, u_1, gated_1]; propose: u_0[, u_1], out_0[, out_1]; res_id: residual, out;
+   others: out).  flags bit 0 (propose): also keep the blend in the fp32 tensor SF_F32_A.                            */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
                          const void* w_packed, int w_rows, const float* vec, int n_vec,
-                         const int32_t* io_bufs, int n_io);
+                         const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags);
 /* SE layer weights (fp32 device): fc1 [2C/8][2C], fc2 [2C][2C/8] for the two SE layers */
 int sf_plan_define_se(sf_plan* p, int which, const float* fc1, const float* fc2, int in_buf, int out_buf);
 /* stage slots used by an event: cell stages for kind 0 / kind 1, then the prior-network stages */

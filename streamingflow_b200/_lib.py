@@ -39,7 +39,7 @@ EXPORTS = {
     "sf_plan_bind_act": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "sf_plan_bind_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sf_plan_define_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Chunk), C.c_void_p, C.c_int, C.c_void_p,
-                                       C.c_int, C.POINTER(C.c_int32), C.c_int]),
+                                       C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int]),
     "sf_plan_define_se": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "sf_plan_define_event_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                              C.POINTER(C.c_int32), C.c_int]),

@@ -51,7 +51,9 @@ struct EpiArgs {
   __nv_bfloat16* out_l[4];
   const __nv_bfloat16* in_h[2];
   const __nv_bfloat16* in_l[2];
-  int n_out;      // output channels of the stage's main output (64 or 128)
+  int out_cs[4], out_co[4];   // channel count of each output buffer and the first channel this launch writes
+  int in_cs[2], in_co[2];     // same for the element-wise inputs
+  int n_out;      // output channels written by this launch (64 or 128)
   int kind;       // event kind (0 derivative step, 1 jump)
 };
 
@@ -73,8 +75,10 @@ struct alignas(64) StageParams {
   EpiArgs e;
 };
 
-// M-tiles per CTA tile: 256-column stages get 1, the rest 2 (accumulator slot = 256 / MT columns)
-__host__ __device__ constexpr int mtiles_for(int epi) { return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ) ? 1 : 2; }
+// M-tiles per CTA tile: 256-column launches get 1, the rest 2 (accumulator slot = 256 / MT columns).  CG = hidden channels.
+__host__ __device__ constexpr int mtiles_for(int epi, int CG) {
+  return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ || (CG == 128 && (epi == SF_EPI_MIX || epi == SF_EPI_SAMPLE))) ? 1 : 2;
+}
 constexpr int ACC_STAGES = 2;
 __host__ __device__ constexpr int a_box_bytes(int R, int MT) { return (TILE_H + R - 1) * (TILE_W * MT + R - 1) * ROW_BYTES; }
 
@@ -132,27 +136,28 @@ __device__ __forceinline__ void vec16(const float* vec, int off, float (&v)[16])
   for (int i = 0; i < 4; ++i) { const float4 t = q[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
 }
 
-// LayerNorm statistics over the 64 accumulator columns [col, col+64) of this thread's pixel, two passes over TMEM
+// LayerNorm statistics over the CG accumulator columns [col, col+CG) of this thread's pixel, two passes over TMEM
 // (convolutions.py:299-304: biased variance, eps 1e-6).  Returns mean and 1/sqrt(var + eps).
-__device__ __forceinline__ void ln_stats64(uint32_t taddr, float& mean, float& rstd) {
+template <int CG>
+__device__ __forceinline__ void ln_stats(uint32_t taddr, float& mean, float& rstd) {
   float s = 0.0f;
 #pragma unroll 1
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < CG / 32; ++j) {
     float a[16], b[16];
     tmem_ld16x2(taddr + j * 32, taddr + j * 32 + 16, a, b);
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += a[i] + b[i];
   }
-  mean = s * (1.0f / 64.0f);
+  mean = s * (1.0f / CG);
   float q = 0.0f;
 #pragma unroll 1
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < CG / 32; ++j) {
     float a[16], b[16];
     tmem_ld16x2(taddr + j * 32, taddr + j * 32 + 16, a, b);
 #pragma unroll
     for (int i = 0; i < 16; ++i) { const float da = a[i] - mean, db = b[i] - mean; q = fmaf(da, da, q); q = fmaf(db, db, q); }
   }
-  rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
+  rstd = rsqrtf(q * (1.0f / CG) + 1e-6f);
 }
 
 struct PixelCtx {
@@ -167,18 +172,21 @@ struct PixelCtx {
 // fused epilogues.  taddr = TMEM address of this warp's lane quadrant, column 0 of the accumulator stage.
 // All tcgen05.ld are executed by every lane (they are warp-collective); global traffic is predicated.
 // ------------------------------------------------------------------------------------------------
-template <int EPI, bool X3>
+template <int EPI, bool X3, int CG>
 __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* vec, uint32_t taddr, const PixelCtx& c) {
   const EpiArgs& e = p.e;
+  constexpr int NJ = CG / 16;                      // 16-channel slices of one CG-channel tensor
+  const size_t pc = c.pix * CG;                    // this pixel in a CG-channel NHWC tensor
   if constexpr (EPI == SF_EPI_GATES) {
-    // columns: [0,64) u1 | [64,128) r1 | [128,192) u2 | [192,256) r2 ; vec = the four biases in column order
+    // columns: pair g = [u_g (CG) | r_g (CG)]; CG = 64: two pairs (u1 r1 u2 r2) in one launch, CG = 128: one pair per launch.
+    // vec = biases in column order; out[2g] = u_g, out[2g+1] = (1 - r_g) * s
 #pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-      const int ucol = g * 128, rcol = g * 128 + 64;
+    for (int g = 0; g < 128 / CG; ++g) {
+      const int ucol = g * 2 * CG, rcol = ucol + CG;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         float u[16], r[16], s[16], bu[16], br[16];
-        if (c.valid) load_f32x16(e.s_in + c.pix * 64 + j * 16, s); else zero16(s);
+        if (c.valid) load_f32x16(e.s_in + pc + j * 16, s); else zero16(s);
         tmem_ld16x2(taddr + ucol + j * 16, taddr + rcol + j * 16, u, r);
         vec16(vec, ucol + j * 16, bu);
         vec16(vec, rcol + j * 16, br);
@@ -188,76 +196,74 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
           r[i] = (1.0f - sigmoidf_(r[i] + br[i])) * s[i];
         }
         if (c.valid) {
-          store_act16<X3>(e.out_h[g], e.out_l[g], c.pix * 64 + j * 16, u);           // u1 / u2
-          store_act16<X3>(e.out_h[2 + g], e.out_l[2 + g], c.pix * 64 + j * 16, r);   // (1-r1)*s / (1-r2)*s
+          store_act16<X3>(e.out_h[2 * g], e.out_l[2 * g], pc + j * 16, u);
+          store_act16<X3>(e.out_h[2 * g + 1], e.out_l[2 * g + 1], pc + j * 16, r);
         }
       }
     }
   } else if constexpr (EPI == SF_EPI_PROPOSE) {
-    // columns: [0,64) s~1 | [64,128) s~2 ; vec = [bias~1, bias~2]; in[0]=u1, in[1]=u2; out[0]=a, out[1]=h
+    // columns: proposal k = [s~_k (CG)]; CG = 64: both GRUs in one launch, CG = 128: one per launch.  vec = biases;
+    // in[k] = u_k; out[k] = (1-u_k) s + u_k s~_k; the first GRU's blend is also kept in fp32 (a32) when bound.
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      float t1[16], t2[16], s[16], u1[16], u2[16], b1[16], b2[16];
-      if (c.valid) {
-        load_f32x16(e.s_in + c.pix * 64 + j * 16, s);
-        load_act16<X3>(e.in_h[0], e.in_l[0], c.pix * 64 + j * 16, u1);
-        load_act16<X3>(e.in_h[1], e.in_l[1], c.pix * 64 + j * 16, u2);
-      } else {
-        zero16(s); zero16(u1); zero16(u2);
-      }
-      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, t1, t2);
-      vec16(vec, j * 16, b1);
-      vec16(vec, 64 + j * 16, b2);
+    for (int k = 0; k < 128 / CG; ++k) {
+#pragma unroll 1
+      for (int j = 0; j < NJ; ++j) {
+        float t[16], s[16], u[16], b[16];
+        if (c.valid) {
+          load_f32x16(e.s_in + pc + j * 16, s);
+          load_act16<X3>(e.in_h[k], e.in_l[k], pc + j * 16, u);
+        } else {
+          zero16(s); zero16(u);
+        }
+        tmem_ld16(taddr + k * CG + j * 16, t);
+        vec16(vec, k * CG + j * 16, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        t1[i] = (1.0f - u1[i]) * s[i] + u1[i] * (t1[i] + b1[i]);
-        t2[i] = (1.0f - u2[i]) * s[i] + u2[i] * (t2[i] + b2[i]);
-      }
-      if (c.valid) {
-        store_f32x16(e.a32 + c.pix * 64 + j * 16, t1);
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, t1);
-        store_act16<X3>(e.out_h[1], e.out_l[1], c.pix * 64 + j * 16, t2);
+        for (int i = 0; i < 16; ++i) t[i] = (1.0f - u[i]) * s[i] + u[i] * (t[i] + b[i]);
+        if (c.valid) {
+          if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
+          store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);
+        }
       }
     }
   } else if constexpr (EPI == SF_EPI_DECODE) {
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       float b[16], bb[16];
       tmem_ld16(taddr + j * 16, b);
       vec16(vec, j * 16, bb);
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) b[i] += bb[i];
-        store_f32x16(e.b32 + c.pix * 64 + j * 16, b);
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, b);
+        store_f32x16(e.b32 + pc + j * 16, b);
+        store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, b);
       }
     }
   } else if constexpr (EPI == SF_EPI_LNGELU) {
     float mean, rstd;
-    ln_stats64(taddr, mean, rstd);
+    ln_stats<CG>(taddr, mean, rstd);
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       float v[16], w[16], b[16];
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, w);
-      vec16(vec, 64 + j * 16, b);
+      vec16(vec, CG + j * 16, b);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
-      if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, v);
+      if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, v);
     }
   } else if constexpr (EPI == SF_EPI_MIX) {
-    // columns: [0,64) 3x3 trunk conv | [64,128) 1x1 projection of cat[a,b];
-    // vec = [LN w (64), LN b (64), gate row 0 (64), gate row 1 (64)]
+    // columns: [0,CG) 3x3 trunk conv | [CG,2CG) 1x1 projection of cat[a,b];
+    // vec = [LN w (CG), LN b (CG), gate row 0 (CG), gate row 1 (CG)]
     float mean, rstd, l0 = 0.0f, l1 = 0.0f;
-    ln_stats64(taddr, mean, rstd);
+    ln_stats<CG>(taddr, mean, rstd);
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       float v[16], pr[16], w[16], b[16], g0w[16], g1w[16];
-      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, v, pr);
+      tmem_ld16x2(taddr + j * 16, taddr + CG + j * 16, v, pr);
       vec16(vec, j * 16, w);
-      vec16(vec, 64 + j * 16, b);
-      vec16(vec, 128 + j * 16, g0w);
-      vec16(vec, 192 + j * 16, g1w);
+      vec16(vec, CG + j * 16, b);
+      vec16(vec, 2 * CG + j * 16, g0w);
+      vec16(vec, 3 * CG + j * 16, g1w);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float yv = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i])) + gelu_erf(pr[i]);
@@ -271,19 +277,19 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       const float dt = p.dt[c.bi];
       const int slot = p.rec_slot ? p.rec_slot[c.bi] : -1;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         float a[16], b[16], o[16];
-        load_f32x16(e.a32 + c.pix * 64 + j * 16, a);
-        load_f32x16(e.b32 + c.pix * 64 + j * 16, b);
+        load_f32x16(e.a32 + pc + j * 16, a);
+        load_f32x16(e.b32 + pc + j * 16, b);
         if (e.kind == 0) {
           float si[16];
-          load_f32x16(e.s_in + c.pix * 64 + j * 16, si);
+          load_f32x16(e.s_in + pc + j * 16, si);
           if (e.s_base == e.s_in) {            // Euler: the update starts from the state the cell read
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = si[i] + dt * ((b[i] * g0 + a[i] * g1) - si[i]);
           } else {                             // midpoint stage 2: base = s, cell state = k
             float sb[16];
-            load_f32x16(e.s_base + c.pix * 64 + j * 16, sb);
+            load_f32x16(e.s_base + pc + j * 16, sb);
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = sb[i] + dt * ((b[i] * g0 + a[i] * g1) - si[i]);
           }
@@ -291,14 +297,15 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = b[i] * g0 + a[i] * g1;
         }
-        store_f32x16(e.s_out + c.pix * 64 + j * 16, o);
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, o);
+        store_f32x16(e.s_out + pc + j * 16, o);
+        store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, o);
         if (slot >= 0)
-          store_f32x16(e.path + ((size_t)slot * p.H * p.W + (size_t)c.y * p.W + c.x) * 64 + j * 16, o);
+          store_f32x16(e.path + ((size_t)slot * p.H * p.W + (size_t)c.y * p.W + c.x) * CG + j * 16, o);
       }
     }
   } else if constexpr (EPI == SF_EPI_BIAS_LRELU) {
     const int n = e.n_out;
+    const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0];
 #pragma unroll 1
     for (int j = 0; j < n / 16; ++j) {
       float v[16], b[16];
@@ -307,11 +314,13 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]);
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * n + j * 16, v);
+        store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_RES_PROJ) {
-    // columns: [0,128) conv_2 (BN folded) | [128,256) 1x1 projection ; vec = [bn bias (128), proj bias (128)]
+    // columns: [0,128) conv_2 (BN folded) | [128,256) 1x1 projection, for 128 output channels starting at out_co;
+    // vec = [bn bias (128), proj bias (128)]
+    const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0];
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       float v[16], q[16], b[16], pb[16];
@@ -321,29 +330,30 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + (q[i] + pb[i]);
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 128 + j * 16, v);
+        store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_RES_ID) {
+    const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       float v[16], r[16], b[16];
-      if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], c.pix * 128 + j * 16, r); else zero16(r);
+      if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], i0 + j * 16, r); else zero16(r);
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + r[i];
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 128 + j * 16, v);
+        store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_SAMPLE) {
-    // columns: [0,64) loc | [64,128) raw scale ; vec = conv bias (128); eps is NCHW [slot][64][H][W]
+    // columns: [0,CG) loc | [CG,2CG) raw scale ; vec = conv bias (2CG); eps is NCHW [slot][CG][H][W]
     const size_t hw = (size_t)p.H * p.W;
     const float* eps = nullptr;
-    if (c.valid) eps = e.eps + (size_t)p.eps_slot[c.bi] * 64 * hw + (size_t)c.y * p.W + c.x;
+    if (c.valid) eps = e.eps + (size_t)p.eps_slot[c.bi] * CG * hw + (size_t)c.y * p.W + c.x;
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       float loc[16], raw[16], bl[16], br[16], ep[16];
       if (c.valid) {
 #pragma unroll
@@ -351,9 +361,9 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       } else {
         zero16(ep);
       }
-      tmem_ld16x2(taddr + j * 16, taddr + 64 + j * 16, loc, raw);
+      tmem_ld16x2(taddr + j * 16, taddr + CG + j * 16, loc, raw);
       vec16(vec, j * 16, bl);
-      vec16(vec, 64 + j * 16, br);
+      vec16(vec, CG + j * 16, br);
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -361,13 +371,13 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
           raw[i] = lrelu01(raw[i] + br[i]);
         }
         if (e.params32) {
-          store_f32x16(e.params32 + c.pix * 128 + j * 16, loc);
-          store_f32x16(e.params32 + c.pix * 128 + 64 + j * 16, raw);
+          store_f32x16(e.params32 + c.pix * 2 * CG + j * 16, loc);
+          store_f32x16(e.params32 + c.pix * 2 * CG + CG + j * 16, raw);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) loc[i] = loc[i] + (softplus_(raw[i]) + 1e-8f) * ep[i];
-        store_act16<X3>(e.out_h[0], e.out_l[0], c.pix * 64 + j * 16, loc);
-        if (e.x32) store_f32x16(e.x32 + c.pix * 64 + j * 16, loc);
+        store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, loc);
+        if (e.x32) store_f32x16(e.x32 + pc + j * 16, loc);
       }
     }
   }
@@ -376,10 +386,10 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
 // ------------------------------------------------------------------------------------------------
 // the stage kernel
 // ------------------------------------------------------------------------------------------------
-template <int EPI, bool X3>
-__global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
+template <int EPI, bool X3, int CG>
+__global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
   constexpr int S = ACC_STAGES;
-  constexpr int MT = mtiles_for(EPI);
+  constexpr int MT = mtiles_for(EPI, CG);
   constexpr int NGROUPS = S * MT;                       // epilogue warpgroups = accumulator slots
   constexpr uint32_t STAGE_COLS = TMEM_COLS / S;        // 256
   constexpr uint32_t SLOT_COLS = STAGE_COLS / MT;       // 256 or 128
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI), 1) c
       c.pix = ((size_t)c.sid * p.H + c.y) * p.W + c.x;
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
-      run_epilogue<EPI, X3>(p, vec_s, taddr, c);
+      run_epilogue<EPI, X3, CG>(p, vec_s, taddr, c);
       tc_fence_before();
       mbar_arrive(smem_u32(acc_empty + st));
     }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
                                                         float* __restrict__ sums, const int* __restrict__ sample_id, int hw, int px0, int px1,
                                                         unsigned int* __restrict__ counters, float* __restrict__ scale_out,
                                                         const float* __restrict__ fc1, const float* __restrict__ fc2, float inv_n) {
-  static_assert(CH == 128, "SE layers of the prior network have 2C = 128 channels");
+  static_assert(CH == 128 || CH == 256, "SE layers of the prior network have 2C = 128 or 256 channels");
   constexpr int GROUPS = CH / 16;           // 8
   constexpr int LANES = 256 / GROUPS;       // 32 pixels per block iteration
   constexpr int UNROLL = 4;

@@ -53,7 +53,8 @@ struct Stage {
   int w_rows = 0;
   const float* vec = nullptr;
   int n_vec = 0;
-  std::vector<int> io;
+  std::vector<int> io, io_off;
+  int flags = 0, n_out = 0;
   CUtensorMap wmap;
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
   std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
@@ -130,22 +131,25 @@ int encode_weight_map(const void* w, int rows, CUtensorMap* out) {
 }
 
 typedef void (*StageKernel)(const StageParams);
-template <bool X3>
+template <bool X3, int CG>
 StageKernel kernel_for(int epi) {
   switch (epi) {
-    case SF_EPI_GATES: return conv_stage_kernel<SF_EPI_GATES, X3>;
-    case SF_EPI_PROPOSE: return conv_stage_kernel<SF_EPI_PROPOSE, X3>;
-    case SF_EPI_DECODE: return conv_stage_kernel<SF_EPI_DECODE, X3>;
-    case SF_EPI_LNGELU: return conv_stage_kernel<SF_EPI_LNGELU, X3>;
-    case SF_EPI_MIX: return conv_stage_kernel<SF_EPI_MIX, X3>;
-    case SF_EPI_BIAS_LRELU: return conv_stage_kernel<SF_EPI_BIAS_LRELU, X3>;
-    case SF_EPI_RES_PROJ: return conv_stage_kernel<SF_EPI_RES_PROJ, X3>;
-    case SF_EPI_RES_ID: return conv_stage_kernel<SF_EPI_RES_ID, X3>;
-    case SF_EPI_SAMPLE: return conv_stage_kernel<SF_EPI_SAMPLE, X3>;
+    case SF_EPI_GATES: return conv_stage_kernel<SF_EPI_GATES, X3, CG>;
+    case SF_EPI_PROPOSE: return conv_stage_kernel<SF_EPI_PROPOSE, X3, CG>;
+    case SF_EPI_DECODE: return conv_stage_kernel<SF_EPI_DECODE, X3, CG>;
+    case SF_EPI_LNGELU: return conv_stage_kernel<SF_EPI_LNGELU, X3, CG>;
+    case SF_EPI_MIX: return conv_stage_kernel<SF_EPI_MIX, X3, CG>;
+    case SF_EPI_BIAS_LRELU: return conv_stage_kernel<SF_EPI_BIAS_LRELU, X3, CG>;
+    case SF_EPI_RES_PROJ: return conv_stage_kernel<SF_EPI_RES_PROJ, X3, CG>;
+    case SF_EPI_RES_ID: return conv_stage_kernel<SF_EPI_RES_ID, X3, CG>;
+    case SF_EPI_SAMPLE: return conv_stage_kernel<SF_EPI_SAMPLE, X3, CG>;
   }
   return nullptr;
 }
-StageKernel kernel_for(int epi, bool x3) { return x3 ? kernel_for<true>(epi) : kernel_for<false>(epi); }
+StageKernel kernel_for(int epi, bool x3, int C) {
+  if (C == 128) return x3 ? kernel_for<true, 128>(epi) : kernel_for<false, 128>(epi);
+  return x3 ? kernel_for<true, 64>(epi) : kernel_for<false, 64>(epi);
+}
 
 int state_act_buf(int which) { return which; }   // activation buffers 0 and 1 mirror fp32 state buffers 0 and 1
 
@@ -167,7 +171,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   for (int c = 0; c < sp.nchunk; ++c) {
     const sf_chunk& ck = st.chunks[c];
     const int buf = resolve_buf(ev, ck.buf);
-    int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.epi), &sp.amap[c]);
+    int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.epi, p->g.C), &sp.amap[c]);
     if (rc) return rc;
     if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
     sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c]};
@@ -175,7 +179,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.wmap = st.wmap;
   sp.H = p->g.H;
   sp.W = p->g.W;
-  const int MT = sf::mtiles_for(st.epi);
+  const int MT = sf::mtiles_for(st.epi, p->g.C);
   sp.tiles_x = (p->g.W + TILE_W * MT - 1) / (TILE_W * MT);
   sp.tiles_y = (p->g.H + TILE_H - 1) / TILE_H;
   sp.n_active = ev->n_active;
@@ -204,39 +208,50 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   e.eps = reinterpret_cast<const float*>(p->f32[SF_F32_EPS]);
   e.x32 = ev->want_f32 ? reinterpret_cast<float*>(p->f32[SF_F32_X]) : nullptr;
   e.params32 = ev->want_f32 ? reinterpret_cast<float*>(p->f32[SF_F32_PARAMS]) : nullptr;
-  auto out = [&](int slot, int buf) {
+  auto out = [&](int slot, int k) {
+    const int buf = st.io[k];
     e.out_h[slot] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].hi);
     e.out_l[slot] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].lo);
+    e.out_cs[slot] = p->act[buf].channels;
+    e.out_co[slot] = st.io_off[k];
   };
-  auto in = [&](int slot, int buf) {
+  auto in = [&](int slot, int k) {
+    const int buf = st.io[k];
     e.in_h[slot] = reinterpret_cast<const __nv_bfloat16*>(p->act[buf].hi);
     e.in_l[slot] = reinterpret_cast<const __nv_bfloat16*>(p->act[buf].lo);
+    e.in_cs[slot] = p->act[buf].channels;
+    e.in_co[slot] = st.io_off[k];
   };
   auto need_io = [&](size_t k) { return st.io.size() >= k; };
   for (int b : st.io)
     if (b < 0 || b >= SF_MAX_ACT_BUFS || !p->act[b].hi || (x3 && !p->act[b].lo))
       return fail(SF_ERR_STATE, "stage io buffer not bound");
+  const int pairs = 128 / p->g.C;          // gate pairs / proposals handled by one launch
   switch (st.epi) {
-    case SF_EPI_GATES:
-      if (!need_io(4)) return fail(SF_ERR_INVALID, "gates stage needs 4 io buffers");
-      for (int i = 0; i < 4; ++i) out(i, st.io[i]);
+    case SF_EPI_GATES:                      // io = [u_0, gated_0, (u_1, gated_1)]
+      if (!need_io(2 * pairs)) return fail(SF_ERR_INVALID, "gates stage needs 2 io buffers per gate pair");
+      for (int i = 0; i < 2 * pairs; ++i) out(i, i);
       break;
-    case SF_EPI_PROPOSE:
-      if (!need_io(4)) return fail(SF_ERR_INVALID, "propose stage needs 4 io buffers");
-      in(0, st.io[0]); in(1, st.io[1]); out(0, st.io[2]); out(1, st.io[3]);
+    case SF_EPI_PROPOSE:                    // io = [u_0, (u_1,) out_0, (out_1)]
+      if (!need_io(2 * pairs)) return fail(SF_ERR_INVALID, "propose stage needs 2 io buffers per proposal");
+      for (int i = 0; i < pairs; ++i) { in(i, i); out(i, pairs + i); }
+      if (!(st.flags & 1)) e.a32 = nullptr;   // only the first GRU's blend is kept in fp32
       break;
-    case SF_EPI_MIX:
-      out(0, state_act_buf(ev->s_out));
+    case SF_EPI_MIX: {
+      const int buf = state_act_buf(ev->s_out);
+      e.out_h[0] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].hi);
+      e.out_l[0] = reinterpret_cast<__nv_bfloat16*>(p->act[buf].lo);
       break;
+    }
     case SF_EPI_RES_ID:
       if (!need_io(2)) return fail(SF_ERR_INVALID, "residual stage needs 2 io buffers");
-      in(0, st.io[0]); out(0, st.io[1]);
-      e.n_out = p->act[st.io[1]].channels;
+      in(0, 0); out(0, 1);
+      e.n_out = 128;
       break;
     default:
       if (!need_io(1)) return fail(SF_ERR_INVALID, "stage needs an output buffer");
-      out(0, st.io[0]);
-      e.n_out = p->act[st.io[0]].channels;
+      out(0, 0);
+      e.n_out = (st.epi == SF_EPI_BIAS_LRELU) ? st.n_out : p->act[st.io[0]].channels;
       break;
   }
   if (st.epi == SF_EPI_MIX || st.epi == SF_EPI_GATES || st.epi == SF_EPI_PROPOSE)
@@ -244,10 +259,10 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   if (st.epi == SF_EPI_SAMPLE && !e.eps) return fail(SF_ERR_STATE, "eps buffer not bound");
   const int ntiles = n * sp.tiles_x * sp.tiles_y;
   const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
-  StageKernel k = kernel_for(st.epi, x3);
+  StageKernel k = kernel_for(st.epi, x3, p->g.C);
   if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
   void* args[] = {&sp};
-  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::ACC_STAGES * sf::mtiles_for(st.epi)), args, (size_t)st.smem, stream));
+  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::ACC_STAGES * MT), args, (size_t)st.smem, stream));
   p->last_launches += 1;
   return SF_OK;
 }
@@ -289,8 +304,13 @@ int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* t
   unsigned int* counters = se_counter_ptr(p, which);
   float* scale_arg = fused_scale ? scale : nullptr;
   const float inv_n = 1.0f / (float)hw;
-  if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
-  else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+  if (CH == 256) {
+    if (x3) se_reduce_kernel<256, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+    else se_reduce_kernel<256, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+  } else {
+    if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+    else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+  }
   SF_CUDA(cudaGetLastError());
   p->last_launches += 1;
   return bpi;
@@ -322,11 +342,17 @@ int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* ta
   dim3 grid2(bpa, ev->n_active);
   float* scale = se_scale_ptr(p, which);
   if (n_partials > 0) {     // scales not yet computed by the reduce kernel (caller reduced the sums across GPUs)
-    se_scale_kernel<128><<<ev->n_active, 256, 0, stream>>>(sums, n_partials, inv_n, se.fc1, se.fc2, scale);
+    if (CH == 256) se_scale_kernel<256><<<ev->n_active, 256, 0, stream>>>(sums, n_partials, inv_n, se.fc1, se.fc2, scale);
+    else se_scale_kernel<128><<<ev->n_active, 256, 0, stream>>>(sums, n_partials, inv_n, se.fc1, se.fc2, scale);
     p->last_launches += 1;
   }
-  if (x3) se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
-  else se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+  if (CH == 256) {
+    if (x3) se_apply_kernel<256, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+    else se_apply_kernel<256, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+  } else {
+    if (x3) se_apply_kernel<128, true><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+    else se_apply_kernel<128, false><<<grid2, 256, 0, stream>>>(zh, zl, yh, yl, scale, sid, hw);
+  }
   SF_CUDA(cudaGetLastError());
   p->last_launches += 1;
   return SF_OK;
@@ -365,7 +391,7 @@ int sf_device_supported(int device) {
 
 int sf_plan_create(const sf_geometry* g, sf_plan** out) {
   if (!g || !out) return fail(SF_ERR_INVALID, "null argument");
-  if (g->C != 64) return fail(SF_ERR_INVALID, "only C = 64 hidden channels is built (got " + std::to_string(g->C) + ")");
+  if (g->C != 64 && g->C != 128) return fail(SF_ERR_INVALID, "hidden channels must be 64 or 128 (got " + std::to_string(g->C) + ")");
   if (g->H <= 0 || g->W <= 0 || g->max_images <= 0) return fail(SF_ERR_INVALID, "bad geometry");
   if (g->precision != SF_PREC_BF16 && g->precision != SF_PREC_BF16X3) return fail(SF_ERR_INVALID, "bad precision mode");
   int rc = sf_device_supported(g->device);
@@ -402,7 +428,7 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr) {
 }
 
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks, const void* w_packed,
-                         int w_rows, const float* vec, int n_vec, const int32_t* io_bufs, int n_io) {
+                         int w_rows, const float* vec, int n_vec, const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags) {
   if (!p || stage < 0 || stage >= SF_MAX_STAGES) return fail(SF_ERR_INVALID, "bad stage id");
   if (n_chunks <= 0 || n_chunks > SF_MAX_CHUNKS) return fail(SF_ERR_INVALID, "bad chunk count");
   if (n_vec > sf::VEC_MAX) return fail(SF_ERR_INVALID, "stage vector too long");
@@ -413,7 +439,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   int a_slot = 0, b_slot = 0;
   for (const sf_chunk& c : st.chunks) {
     if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
-    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(epilogue)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
+    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(epilogue, p->g.C)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
     // a whole dx column of taps travels as ONE weight tile when it is small enough: fewer barrier round trips per MMA
@@ -422,7 +448,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
     if (tb < 1) tb = 1;
     if (tb > c.R) tb = c.R;
     st.tb.push_back(tb);
-    const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
+    const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
     a_slot = a > a_slot ? a : a_slot;
     b_slot = b > b_slot ? b : b_slot;
   }
@@ -431,6 +457,10 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.vec = vec;
   st.n_vec = n_vec;
   st.io.assign(io_bufs, io_bufs + n_io);
+  if (io_choff) st.io_off.assign(io_choff, io_choff + n_io); else st.io_off.assign(n_io, 0);
+  st.flags = flags;
+  st.n_out = 0;
+  for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
   const int fixed = 1024 + sf::VEC_MAX * 4 + BAR_AREA;
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
   // activation ring: one slot = one chunk's tile + halo (3 slots when they leave room for >= 2 weight slots);
@@ -470,7 +500,7 @@ int sf_plan_finalize(sf_plan* p) {
     if (st.defined && st.smem > max_smem) max_smem = st.smem;
   for (int epi = 0; epi <= SF_EPI_SAMPLE; ++epi)
     for (int x3 = 0; x3 < 2; ++x3)
-      SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel_for(epi, x3 != 0)), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+      SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel_for(epi, x3 != 0, p->g.C)), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   p->finalized = true;
   return SF_OK;
 }

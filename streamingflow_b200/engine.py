@@ -26,13 +26,9 @@ from . import _lib as L
  BUF_Z1, BUF_Y1, BUF_Q3, BUF_Z2, BUF_Y2) = range(20)
 _BUF_CHANNELS = {BUF_S0: 1, BUF_S1: 1, BUF_X: 1, BUF_U1: 1, BUF_U2: 1, BUF_G1: 1, BUF_G2: 1, BUF_A: 1, BUF_B: 1, BUF_HH: 1,
                  BUF_T1: 1, BUF_T2: 1, BUF_Q1: 1, BUF_Z1: 2, BUF_Y1: 2, BUF_Q3: 2, BUF_Z2: 2, BUF_Y2: 2}
-# stage slots
-ST_G, ST_P, ST_D, ST_T7, ST_T1, ST_T3 = range(6)          # + 6 * weight_set (0: gru_c, 1: gru_obs.gru_d)
-ST_Q1, ST_Q2, ST_Q3, ST_Q4, ST_Q5 = 12, 13, 14, 15, 16
-CELL_STAGE_NAMES = ("gates", "propose", "decode", "trunk7", "trunk1", "mix")
-PRIOR_ITEMS = [ST_Q1, ST_Q2, L.SE_ITEM_BASE + 0, ST_Q3, ST_Q4, L.SE_ITEM_BASE + 1, ST_Q5]
-
 KIND_STEP, KIND_JUMP = 0, 1
+CELL_STAGE_NAMES = {64: ("gates", "propose", "decode", "trunk7", "trunk1", "mix"),
+                    128: ("gates_1", "gates_2", "propose_1", "propose_2", "decode", "trunk7", "trunk1", "mix")}
 
 
 def _bn_fold(sd, p):
@@ -44,63 +40,91 @@ def _bn_fold(sd, p):
 
 
 class StageDef:
-    """Logical description of a stage before packing: chunks of (source buffer, first channel, weights [n,64,R,R], column, init)."""
+    """Logical description of a stage before packing: chunks of (source buffer, first channel, weights [n,64,R,R], column, init)
+    plus the epilogue's io buffers (with the first channel each launch touches) and flags."""
 
-    def __init__(self, epilogue, vec, io):
-        self.epilogue, self.vec, self.io = epilogue, vec, list(io)
+    def __init__(self, name, epilogue, vec, io, io_off=None, flags=0):
+        self.name, self.epilogue, self.vec, self.io, self.flags = name, epilogue, vec, list(io), flags
+        self.io_off = list(io_off) if io_off is not None else [0] * len(self.io)
         self.chunks: List[Tuple[int, int, torch.Tensor, int, int]] = []
 
-    def add(self, buf, c0, w, col, init):
-        assert w.shape[1] == 64 and w.shape[2] == w.shape[3]
-        self.chunks.append((buf, c0, w, col, init))
+    def add(self, buf, w, col, init, c0=0):
+        """w: [n, cin, R, R] with cin a multiple of 64: one chunk per 64 input channels of buffer ``buf`` starting at c0."""
+        assert w.shape[1] % 64 == 0 and w.shape[2] == w.shape[3]
+        for i in range(w.shape[1] // 64):
+            self.chunks.append((buf, c0 + 64 * i, w[:, 64 * i:64 * i + 64], col, int(init and i == 0)))
         return self
 
 
 def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
-    """The six conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters."""
+    """The conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters; C = 64 or 128."""
     g = lambda k: sd[f"{p}.{k}"].float()
     C_ = g("conv_update_1.weight").shape[0]
-    assert C_ == 64
+    assert C_ in (64, 128)
     wu1, wr1, wt1 = g("conv_update_1.weight"), g("conv_reset_1.weight"), g("conv_state_tilde_1.weight")
     wu2, wr2, wt2 = g("conv_update_2.weight"), g("conv_reset_2.weight"), g("conv_state_tilde_2.weight")
-    fold = lambda w: w[:, :64] + w[:, 64:]        # gru_cell_2 sees cat[state, state] (tob:118): one 64-ch operand
-    gates = StageDef(L.EPI_GATES, torch.cat([g("conv_update_1.bias"), g("conv_reset_1.bias"), g("conv_update_2.bias"),
-                                              g("conv_reset_2.bias")]), [BUF_U1, BUF_U2, BUF_G1, BUF_G2])
-    gates.add(L.SRC_STATE_IN, 0, torch.cat([wu1[:, 64:], wr1[:, 64:], fold(wu2), fold(wr2)], 0), 0, 1)
-    gates.add(L.SRC_X, 0, torch.cat([wu1[:, :64], wr1[:, :64]], 0), 0, 0)
-    prop = StageDef(L.EPI_PROPOSE, torch.cat([g("conv_state_tilde_1.bias"), g("conv_state_tilde_2.bias")]),
-                    [BUF_U1, BUF_U2, BUF_A, BUF_HH])
-    prop.add(L.SRC_X, 0, wt1[:, :64], 0, 1).add(BUF_G1, 0, wt1[:, 64:], 0, 0)
-    prop.add(L.SRC_STATE_IN, 0, wt2[:, :64], 64, 1).add(BUF_G2, 0, wt2[:, 64:], 64, 0)
-    dec = StageDef(L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B]).add(BUF_HH, 0, g("conv_decoder_2.weight"), 0, 1)
+    bu1, br1, bu2, br2 = g("conv_update_1.bias"), g("conv_reset_1.bias"), g("conv_update_2.bias"), g("conv_reset_2.bias")
+    fold = lambda w: w[:, :C_] + w[:, C_:]        # gru_cell_2 sees cat[state, state] (tob:118): one C-channel operand
+    SX, SS = L.SRC_X, L.SRC_STATE_IN
+    out = []
+    if C_ == 64:        # all four gates in one 256-column launch
+        st = StageDef("gates", L.EPI_GATES, torch.cat([bu1, br1, bu2, br2]), [BUF_U1, BUF_G1, BUF_U2, BUF_G2])
+        st.add(SS, torch.cat([wu1[:, C_:], wr1[:, C_:], fold(wu2), fold(wr2)], 0), 0, 1).add(SX, torch.cat([wu1[:, :C_], wr1[:, :C_]], 0), 0, 0)
+        out.append(st)
+        st = StageDef("propose", L.EPI_PROPOSE, torch.cat([g("conv_state_tilde_1.bias"), g("conv_state_tilde_2.bias")]),
+                      [BUF_U1, BUF_U2, BUF_A, BUF_HH], flags=1)
+        st.add(SX, wt1[:, :C_], 0, 1).add(BUF_G1, wt1[:, C_:], 0, 0).add(SS, wt2[:, :C_], 64, 1).add(BUF_G2, wt2[:, C_:], 64, 0)
+        out.append(st)
+    else:               # 128 channels: one gate pair / one proposal per launch
+        st = StageDef("gates_1", L.EPI_GATES, torch.cat([bu1, br1]), [BUF_U1, BUF_G1])
+        st.add(SS, torch.cat([wu1[:, C_:], wr1[:, C_:]], 0), 0, 1).add(SX, torch.cat([wu1[:, :C_], wr1[:, :C_]], 0), 0, 0)
+        out.append(st)
+        out.append(StageDef("gates_2", L.EPI_GATES, torch.cat([bu2, br2]), [BUF_U2, BUF_G2]).add(SS, torch.cat([fold(wu2), fold(wr2)], 0), 0, 1))
+        out.append(StageDef("propose_1", L.EPI_PROPOSE, g("conv_state_tilde_1.bias"), [BUF_U1, BUF_A], flags=1)
+                   .add(SX, wt1[:, :C_], 0, 1).add(BUF_G1, wt1[:, C_:], 0, 0))
+        out.append(StageDef("propose_2", L.EPI_PROPOSE, g("conv_state_tilde_2.bias"), [BUF_U2, BUF_HH])
+                   .add(SS, wt2[:, :C_], 0, 1).add(BUF_G2, wt2[:, C_:], 0, 0))
+    out.append(StageDef("decode", L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B]).add(BUF_HH, g("conv_decoder_2.weight"), 0, 1))
     t = "trusting_gate.0."
     w7 = g(t + "layers.0.weight")
-    trunk7 = StageDef(L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1])
-    trunk7.add(BUF_A, 0, w7[:, :64], 0, 1).add(BUF_B, 0, w7[:, 64:], 0, 0)
-    trunk1 = StageDef(L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
-    trunk1.add(BUF_T1, 0, g(t + "layers.3.weight"), 0, 1)
+    out.append(StageDef("trunk7", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1])
+               .add(BUF_A, w7[:, :C_], 0, 1).add(BUF_B, w7[:, C_:], 0, 0))
+    out.append(StageDef("trunk1", L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
+               .add(BUF_T1, g(t + "layers.3.weight"), 0, 1))
     wp = g(t + "projection.0.weight")
     wg = g("trusting_gate.1.weight")[:, :, 0, 0]
-    mix = StageDef(L.EPI_MIX, torch.cat([g(t + "layers.7.weight"), g(t + "layers.7.bias"), wg[0], wg[1]]), [])
-    mix.add(BUF_T2, 0, g(t + "layers.6.weight"), 0, 1).add(BUF_A, 0, wp[:, :64], 64, 1).add(BUF_B, 0, wp[:, 64:], 64, 0)
-    return [gates, prop, dec, trunk7, trunk1, mix]
+    out.append(StageDef("mix", L.EPI_MIX, torch.cat([g(t + "layers.7.weight"), g(t + "layers.7.bias"), wg[0], wg[1]]), [])
+               .add(BUF_T2, g(t + "layers.6.weight"), 0, 1).add(BUF_A, wp[:, :C_], C_, 1).add(BUF_B, wp[:, C_:], C_, 0))
+    return out
 
 
-def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
-    """The five conv stages of p_model = ConvNet(64, 128) with BatchNorm folded (res_models.py:168-180)."""
+def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[object]:
+    """p_model = ConvNet(C, 2C) with BatchNorm folded (res_models.py:168-180), as a list of StageDefs and the two SE markers
+    'se0' / 'se1'.  Outputs wider than 128 channels are produced 128 channels per launch."""
     m = p + ".model."
     w1, b1 = _bn_fold(sd, m + "0.layers.conv_1")
     w2, b2 = _bn_fold(sd, m + "0.layers.conv_2")
-    q1 = StageDef(L.EPI_BIAS_LRELU, b1, [BUF_Q1]).add(L.SRC_STATE_OUT, 0, w1, 0, 1)
-    q2 = StageDef(L.EPI_RES_PROJ, torch.cat([b2, sd[m + "0.projection.bias"].float()]), [BUF_Z1])
-    q2.add(BUF_Q1, 0, w2, 0, 1).add(L.SRC_STATE_OUT, 0, sd[m + "0.projection.weight"].float(), 128, 1)
+    C_ = w1.shape[0]
+    halves = (2 * C_) // 128
+    SO = L.SRC_STATE_OUT
+    items: List[object] = [StageDef("q1", L.EPI_BIAS_LRELU, b1, [BUF_Q1]).add(SO, w1, 0, 1)]
+    wpj, bpj = sd[m + "0.projection.weight"].float(), sd[m + "0.projection.bias"].float()
+    for h in range(halves):
+        r = slice(128 * h, 128 * h + 128)
+        items.append(StageDef(f"q2{'ab'[h] if halves > 1 else ''}", L.EPI_RES_PROJ, torch.cat([b2[r], bpj[r]]), [BUF_Z1], [128 * h])
+                     .add(BUF_Q1, w2[r], 0, 1).add(SO, wpj[r], 128, 1))
+    items.append("se0")
     w3, b3 = _bn_fold(sd, m + "2.layers.conv_1")
     w4, b4 = _bn_fold(sd, m + "2.layers.conv_2")
-    q3 = StageDef(L.EPI_BIAS_LRELU, b3, [BUF_Q3]).add(BUF_Y1, 0, w3[:, :64], 0, 1).add(BUF_Y1, 64, w3[:, 64:], 0, 0)
-    q4 = StageDef(L.EPI_RES_ID, b4, [BUF_Y1, BUF_Z2]).add(BUF_Q3, 0, w4[:, :64], 0, 1).add(BUF_Q3, 64, w4[:, 64:], 0, 0)
-    w5 = sd[m + "4.conv.weight"].float()
-    q5 = StageDef(L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(BUF_Y2, 0, w5[:, :64], 0, 1).add(BUF_Y2, 64, w5[:, 64:], 0, 0)
-    return [q1, q2, q3, q4, q5]
+    for h in range(halves):
+        r = slice(128 * h, 128 * h + 128)
+        items.append(StageDef(f"q3{'ab'[h] if halves > 1 else ''}", L.EPI_BIAS_LRELU, b3[r], [BUF_Q3], [128 * h]).add(BUF_Y1, w3[r], 0, 1))
+    for h in range(halves):
+        r = slice(128 * h, 128 * h + 128)
+        items.append(StageDef(f"q4{'ab'[h] if halves > 1 else ''}", L.EPI_RES_ID, b4[r], [BUF_Y1, BUF_Z2], [128 * h, 128 * h]).add(BUF_Q3, w4[r], 0, 1))
+    items.append("se1")
+    items.append(StageDef("q5", L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(BUF_Y2, sd[m + "4.conv.weight"].float(), 0, 1))
+    return items
 
 
 def pack_stage(sdef: StageDef, x3: bool):
@@ -173,7 +197,10 @@ class OdeEngine:
             raise L.SfError("the ODE engine runs on a CUDA (B200) device only; there is no CPU path")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-        self.device, self.H, self.W, self.C = dev, int(H), int(W), 64
+        self.C = int(next(v for k, v in sd.items() if k.endswith("gru_c.conv_decoder_2.weight")).shape[0])
+        if self.C not in (64, 128):
+            raise L.SfError("the CUDA ODE engine is built for 64 or 128 hidden channels")
+        self.device, self.H, self.W = dev, int(H), int(W)
         self.max_images = int(max_images)
         self.precision = precision
         self.x3 = precision == "bf16x3"
@@ -232,7 +259,7 @@ class OdeEngine:
 
     def bind_eps(self, eps: torch.Tensor):
         """eps: fp32 NCHW [slots, 64, H, W] standard-normal noise (torch's own generation order)."""
-        assert eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape[1:]) == (self.C, self.H, self.W)
+        assert eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape[1:]) == (self.C, self.H, self.W), eps.shape
         self.eps = eps
         self._bind_f32(L.F32_EPS, eps)
 
@@ -244,27 +271,44 @@ class OdeEngine:
         pre = prefix
         self._keep = []
         self.stage_defs: Dict[int, StageDef] = {}
-        for ws, cell in enumerate((pre + "gru_c", pre + "gru_obs.gru_d")):
-            for i, sdef in enumerate(cell_stage_defs(sd, cell)):
-                self.stage_defs[i + 6 * ws] = sdef
-        for slot, sdef in zip((ST_Q1, ST_Q2, ST_Q3, ST_Q4, ST_Q5), prior_stage_defs(sd, pre + "p_model")):
-            self.stage_defs[slot] = sdef
+        self.stage_names: Dict[int, str] = {}
+        cells = [cell_stage_defs(sd, pre + "gru_c"), cell_stage_defs(sd, pre + "gru_obs.gru_d")]
+        n_cell = len(cells[0])
+        cell_slots = [list(range(ws * n_cell, (ws + 1) * n_cell)) for ws in range(2)]
+        for ws in range(2):
+            for slot, sdef in zip(cell_slots[ws], cells[ws]):
+                self.stage_defs[slot] = sdef
+                if ws == 0:
+                    self.stage_names[slot] = sdef.name
+        prior_items, slot = [], 2 * n_cell
+        for it in prior_stage_defs(sd, pre + "p_model"):
+            if isinstance(it, str):
+                prior_items.append(L.SE_ITEM_BASE + int(it[2]))
+                self.stage_names[prior_items[-1]] = "se" + str(int(it[2]) + 1)
+            else:
+                self.stage_defs[slot] = it
+                self.stage_names[slot] = it.name
+                prior_items.append(slot)
+                slot += 1
+        self.cell_slots, self.prior_items = cell_slots, prior_items
         for slot, sdef in self.stage_defs.items():
             chunks, wp = pack_stage(sdef, self.x3)
             vec = sdef.vec.to(torch.float32).contiguous()
             arr = (L.Chunk * len(chunks))(*[L.Chunk(**c) for c in chunks])
             io = (C.c_int32 * max(1, len(sdef.io)))(*sdef.io)
+            io_off = (C.c_int32 * max(1, len(sdef.io)))(*sdef.io_off)
             self._keep += [wp, vec]
             L.check(self.lib.sf_plan_define_stage(self.plan, slot, sdef.epilogue, len(chunks), arr, wp.data_ptr(), wp.shape[0],
-                                                  vec.data_ptr(), vec.numel(), io, len(sdef.io)), f"sf_plan_define_stage({slot})")
+                                                  vec.data_ptr(), vec.numel(), io, io_off, len(sdef.io), sdef.flags),
+                    f"sf_plan_define_stage({slot}:{sdef.name})")
         for which, (idx, zin, yout) in enumerate(((1, BUF_Z1, BUF_Y1), (3, BUF_Z2, BUF_Y2))):
             fc1 = sd[f"{pre}p_model.model.{idx}.fc.0.weight"].float().contiguous()
             fc2 = sd[f"{pre}p_model.model.{idx}.fc.2.weight"].float().contiguous()
             self._keep += [fc1, fc2]
             L.check(self.lib.sf_plan_define_se(self.plan, which, fc1.data_ptr(), fc2.data_ptr(), zin, yout), "sf_plan_define_se")
         i32 = lambda v: (C.c_int32 * len(v))(*v)
-        L.check(self.lib.sf_plan_define_event_graph(self.plan, i32(list(range(0, 6))), i32(list(range(6, 12))), 6,
-                                                    i32(PRIOR_ITEMS), len(PRIOR_ITEMS)), "sf_plan_define_event_graph")
+        L.check(self.lib.sf_plan_define_event_graph(self.plan, i32(cell_slots[0]), i32(cell_slots[1]), n_cell,
+                                                    i32(prior_items), len(prior_items)), "sf_plan_define_event_graph")
         with torch.cuda.device(self.device):
             L.check(self.lib.sf_plan_finalize(self.plan), "sf_plan_finalize")
 

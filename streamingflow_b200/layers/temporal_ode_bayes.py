@@ -160,8 +160,8 @@ class NNFOwithBayesianJumps(nn.Module):
         else:
             if device.type != "cuda":
                 raise L.SfError("streamingflow_b200 integrates the ODE on a B200 GPU only; got a tensor on " + str(device))
-            if self.hidden_size != 64 or self.input_size != 64:
-                raise L.SfError("the CUDA ODE engine is built for 64 hidden channels")
+            if self.hidden_size not in (64, 128) or self.input_size != self.hidden_size:
+                raise L.SfError("the CUDA ODE engine is built for 64 or 128 hidden (= input) channels")
             from ..engine import OdeEngine
 
             eng = OdeEngine(self._hot_state_dict(), "", h, w, n_images, self.precision, device)

@@ -89,8 +89,8 @@ class RowShardedOde:
             dist.broadcast(seed, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
         g = torch.Generator(device=self.device).manual_seed(int(seed.item()))
         rows = self.hi - self.lo
-        eps = torch.empty((max(n, 1), 64, rows, self.w), dtype=torch.float32, device=self.device)
-        full = torch.empty((64, self.h, self.w), dtype=torch.float32, device=self.device)
+        eps = torch.empty((max(n, 1), self.eng.C, rows, self.w), dtype=torch.float32, device=self.device)
+        full = torch.empty((self.eng.C, self.h, self.w), dtype=torch.float32, device=self.device)
         for i in range(n):
             full.normal_(generator=g)
             eps[i].copy_(full[:, self.lo:self.hi])
@@ -98,7 +98,7 @@ class RowShardedOde:
 
     # ------------------------------------------------------------------ one engine event with the collectives in place
     def _run_event(self, ev_dict: dict):
-        from .engine import BUF_S0, BUF_X, PRIOR_ITEMS
+        from .engine import BUF_S0, BUF_X
 
         eng, lib = self.eng, self.eng.lib
         table, evs = eng.build_table([ev_dict])
@@ -107,13 +107,14 @@ class RowShardedOde:
         stream = eng._stream()
         rows_own0, rows_own1 = (self.own_lo - self.lo) * self.w, (self.own_hi - self.lo) * self.w
         n = ev.n_active
+        ch = 2 * eng.C
         with torch.cuda.device(self.device):
             if ev.run_cell:
-                for st in range(6):
-                    L.check(lib.sf_plan_run_stage(eng.plan, st + 6 * ev.kind, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
-                self.launches += 6
+                for st in eng.cell_slots[ev.kind]:
+                    L.check(lib.sf_plan_run_stage(eng.plan, st, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
+                self.launches += len(eng.cell_slots[ev.kind])
             if ev.run_prior:
-                for item in PRIOR_ITEMS:
+                for item in eng.prior_items:
                     if item < L.SE_ITEM_BASE:
                         L.check(lib.sf_plan_run_stage(eng.plan, item, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
                         self.launches += 1
@@ -122,10 +123,10 @@ class RowShardedOde:
                     npart = L.check(lib.sf_plan_se_reduce(eng.plan, which, C.byref(ev), tdev.data_ptr(), rows_own0, rows_own1, stream),
                                     "se_reduce")
                     flat = eng.se_sums[which].view(-1)                  # kernel layout: [active sample][partial][2C], packed
-                    total = flat[: n * npart * 128].view(n, npart, 128).sum(dim=1)      # this rank's band
+                    total = flat[: n * npart * ch].view(n, npart, ch).sum(dim=1)      # this rank's band
                     if self.world > 1:
                         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
-                    flat[: n * 128].view(n, 128).copy_(total)           # one "partial" per sample = the whole-image sum
+                    flat[: n * ch].view(n, ch).copy_(total)           # one "partial" per sample = the whole-image sum
                     L.check(lib.sf_plan_se_apply(eng.plan, which, C.byref(ev), tdev.data_ptr(), 1, C.c_float(1.0 / (self.h * self.w)),
                                                  stream), "se_apply")
                     self.launches += 2
@@ -156,7 +157,7 @@ class RowShardedOde:
             self._run_event(e)
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
-        sel = eng.unpack_path(flat).view(B, T, 64, self.hi - self.lo, self.w)
+        sel = eng.unpack_path(flat).view(B, T, eng.C, self.hi - self.lo, self.w)
         ro.launches = self.launches
         return sel[:, :, :, self.own_lo - self.lo:self.own_hi - self.lo].contiguous(), ro
 

@@ -89,10 +89,10 @@ def test_layout_kernels_roundtrip():
 
 
 # ------------------------------------------------------------------------------------------------ one event, every buffer
-def _engine(H, W, B, precision, seed=5):
+def _engine(H, W, B, precision, seed=5, C=64):
     from streamingflow_b200.engine import OdeEngine
 
-    sd = so.recipe_state_dict(nnfo_shapes(64), seed, 1.0, torch.float32)
+    sd = so.recipe_state_dict(nnfo_shapes(C), seed, 1.0, torch.float32)
     hot = {k: v.cuda() for k, v in sd.items() if k.startswith(("gru_c", "gru_obs", "p_model"))}
     return OdeEngine(hot, "", H, W, B, precision, torch.device("cuda")), {"g." + k: v.double() for k, v in sd.items()}
 
@@ -111,18 +111,18 @@ def _act(eng, buf, n):
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("kind", ["step", "jump"])
-@pytest.mark.parametrize("H,W", [(20, 13), (50, 50)])
-def test_one_event_every_intermediate_matches_oracle(precision, kind, H, W):
+@pytest.mark.parametrize("H,W,C", [(20, 13, 64), (50, 50, 64), (20, 13, 128), (36, 40, 128)])
+def test_one_event_every_intermediate_matches_oracle(precision, kind, H, W, C):
     """Runs ONE event (6 cell stages + 5 prior stages + 2 SE layers) and checks every buffer a stage writes against the
     oracle's corresponding tensor.  Sizes with ragged tiles (20x13: partial 16x8 tiles in both directions)."""
     from streamingflow_b200 import engine as en
 
     B = 3
-    eng, sd = _engine(H, W, B, precision)
+    eng, sd = _engine(H, W, B, precision, C=C)
     g = torch.Generator().manual_seed(11)
-    state = 0.5 * torch.randn(B, 64, H, W, generator=g)
-    x = torch.tanh(torch.randn(B, 64, H, W, generator=g))
-    eps = torch.randn(B, 64, H, W, generator=g)
+    state = 0.5 * torch.randn(B, C, H, W, generator=g)
+    x = torch.tanh(torch.randn(B, C, H, W, generator=g))
+    eps = torch.randn(B, C, H, W, generator=g)
     dts = [0.05, 0.2, 0.45]
     eng.set_state(0, state.cuda())
     eng.pack_into(en.BUF_X, x.cuda())

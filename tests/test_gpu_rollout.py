@@ -226,3 +226,36 @@ def test_long_rollout_configs_match_oracle(config):
         want_sel = torch.stack([tr[sch.path_ev[i]][0] for i in sch.select])
         assert _rel(sel[b].cpu(), want_sel) < TOL[precision]
     assert worst < TOL[precision], f"{config}: per-event latent error {worst:.3e}"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_c128_rollout_matches_oracle(precision):
+    """The 128-channel network of BASELINE config 5 (in_channels = latent_dim = 128): NNFOwithBayesianJumps.forward on CUDA vs the
+    fp64 oracle, BEV 96x80 -> 24x20 latent, 8 observations, 4 targets."""
+    from streamingflow_b200.layers.temporal_ode_bayes import NNFOwithBayesianJumps
+
+    C, H, W, seed = 128, 96, 80, 41
+    m = NNFOwithBayesianJumps(C, C, make_cfg(C)).eval()
+    sd32 = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed, 1.0)
+    m.load_state_dict(sd32, strict=True)
+    m = m.cuda()
+    m.precision, m.record_all = precision, True
+    times = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
+    targets = [-0.5, 0.0, 1.0, 2.0]
+    obs = so.recipe_array("obs", (1, 8, C, H, W), seed).cuda()
+    tape = torch.stack([so.recipe_array(f"eps{i}", (C, H // 4, W // 4), seed) for i in range(24)]).cuda()
+    m._draw_noise = lambda n, h, w, device: tape[:max(n, 1)].contiguous()
+    with torch.no_grad():
+        state, aux, x = m(torch.tensor(times, dtype=torch.float64), torch.zeros(1, 1, C, H, W, device="cuda"), obs, 0.05,
+                          torch.tensor(targets, dtype=torch.float64))
+    torch.cuda.synchronize()
+    sd64 = {"g." + k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd32.items()}
+    tr = []
+    with torch.no_grad():
+        st_o, sel_o, x_o = so.nnfo_forward(sd64, "g", times, obs.double(), targets, 0.05, iter(tape.double()[:, None]), trace=tr)
+    ref = torch.cat(tr, 0)
+    got = m.last_trace[0]
+    assert got.shape == ref.shape
+    errs = [_rel(got[i], ref[i]) for i in range(ref.shape[0])]
+    assert max(errs) < TOL[precision], f"C=128 per-event latent error {max(errs):.3e} ({precision})"
+    assert _rel(x, x_o) < 5 * TOL[precision]

@@ -108,7 +108,8 @@ def test_packed_stage_plans_reproduce_the_convolutions(x3):
                      conv(torch.cat([a, b], 1), "gru_c.trusting_gate.0.projection.0.weight", 0)])
     assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 10
     prior = en.prior_stage_defs(sd, "p_model")
-    acc = en.emulate_stage(prior[3], x3, src)           # q4: 128 -> 128 with BN folded
+    acc = en.emulate_stage(prior[4], x3, src)           # q4: 128 -> 128 with BN folded
+    assert prior[2] == 'se0' and prior[5] == 'se1' and prior[4].name == 'q4'
     w4, b4 = en._bn_fold(sd, "p_model.model.2.layers.conv_2")
     ref = F.conv2d((src[en.BUF_Q3] if x3 else q(src[en.BUF_Q3])).double(), (w4 if x3 else q(w4)).double(), None, padding=1)[0]
     assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 30
@@ -180,3 +181,42 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.sf_abi_version.restype = ctypes.c_int
     assert lib.sf_abi_version() == _lib.SF_ABI_VERSION
+
+
+def test_packed_stage_plans_c128():
+    """The 128-channel stage split (one gate pair / proposal / 128 output channels per launch) replayed on the host."""
+    from streamingflow_b200 import engine as en
+    import torch.nn.functional as F
+
+    torch.manual_seed(1)
+    C = 128
+    sd = so.recipe_state_dict(nnfo_shapes(C), 6, 1.0, torch.float32)
+    H, W = 4, 5
+    rnd = lambda c: torch.randn(1, c, H, W)
+    q = lambda t: t.to(torch.bfloat16).float()
+    x, s, g1, a, b, t2 = (rnd(C) for _ in range(6))
+    y1, q1 = rnd(2 * C), rnd(C)
+    src = {-1: x, -2: s, -3: s, en.BUF_G1: g1, en.BUF_G2: g1, en.BUF_A: a, en.BUF_B: b, en.BUF_HH: a, en.BUF_T1: g1, en.BUF_T2: t2,
+           en.BUF_Q1: q1, en.BUF_Y1: y1, en.BUF_Q3: y1, en.BUF_Y2: y1}
+    conv = lambda inp, w, pad: F.conv2d(q(inp).double(), q(w).double(), None, padding=pad)[0]
+    cell = {d.name: d for d in en.cell_stage_defs(sd, "gru_c")}
+    assert list(cell) == list(en.CELL_STAGE_NAMES[128])
+    xs = torch.cat([x, s], 1)
+    acc = en.emulate_stage(cell["gates_1"], False, src)
+    ref = torch.cat([conv(xs, sd["gru_c.conv_update_1.weight"], 1), conv(xs, sd["gru_c.conv_reset_1.weight"], 1)])
+    assert (acc - ref).abs().max() < 1e-9
+    acc = en.emulate_stage(cell["propose_1"], False, src)
+    assert (acc[:C] - conv(torch.cat([x, g1], 1), sd["gru_c.conv_state_tilde_1.weight"], 1)).abs().max() < 1e-9
+    acc = en.emulate_stage(cell["mix"], False, src)
+    ref = torch.cat([conv(t2, sd["gru_c.trusting_gate.0.layers.6.weight"], 1),
+                     conv(torch.cat([a, b], 1), sd["gru_c.trusting_gate.0.projection.0.weight"], 0)])
+    assert (acc - ref).abs().max() < 1e-9
+    prior = {d.name: d for d in en.prior_stage_defs(sd, "p_model") if not isinstance(d, str)}
+    assert list(prior) == ["q1", "q2a", "q2b", "q3a", "q3b", "q4a", "q4b", "q5"]
+    w2, _ = en._bn_fold(sd, "p_model.model.0.layers.conv_2")
+    for h, name in enumerate(("q2a", "q2b")):
+        acc = en.emulate_stage(prior[name], False, src)
+        ref = torch.cat([conv(q1, w2[128 * h:128 * h + 128], 1), conv(s, sd["p_model.model.0.projection.weight"][128 * h:128 * h + 128], 0)])
+        assert (acc - ref).abs().max() < 1e-9 and prior[name].io_off == [128 * h]
+    acc = en.emulate_stage(prior["q5"], False, src)
+    assert (acc - conv(y1, sd["p_model.model.4.conv.weight"], 1)).abs().max() < 1e-9
