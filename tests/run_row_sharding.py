@@ -1,5 +1,5 @@
 """torchrun worker: row-sharded rollout on WORLD_SIZE GPUs vs the unsharded engine on rank 0's GPU.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_row_sharding.py [H W B precision]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_row_sharding.py [H W B precision C]
 Prints one JSON line from rank 0 (max relative error of the gathered latents, timing)."""
 import json
 import os
@@ -18,12 +18,13 @@ from streamingflow_b200.row_sharding import RowShardedOde  # noqa: E402
 
 H, W, B = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (96, 80, 2)))
 precision = sys.argv[4] if len(sys.argv) > 4 else "bf16x3"
+C = int(sys.argv[5]) if len(sys.argv) > 5 else 64
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 seed = 13
-m = NNFOwithBayesianJumps(64, 64, ode_cfg(64)).eval()
+m = NNFOwithBayesianJumps(C, C, ode_cfg(C)).eval()
 m.load_state_dict(so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed, 1.0), strict=True)
 m = m.to(dev)
 m.precision = precision
@@ -31,8 +32,8 @@ times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])] * B
 targets = [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]] * B
 counts = [8] * B
 g = torch.Generator().manual_seed(seed)
-hx = torch.tanh(torch.randn(sum(counts), 64, H, W, generator=g)).to(dev)
-tape = torch.randn(18 * B, 64, H, W, generator=g).to(dev)
+hx = torch.tanh(torch.randn(sum(counts), C, H, W, generator=g)).to(dev)
+tape = torch.randn(18 * B, C, H, W, generator=g).to(dev)
 sharded = RowShardedOde(m, H, W, B)
 with torch.no_grad():
     band, ro = sharded.integrate(hx, counts, times, targets, 0.05, noise=tape)
@@ -53,7 +54,7 @@ with torch.no_grad():
         torch.cuda.synchronize()
         dt_single = time.perf_counter() - t0
         err = ((full.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
-        print(json.dumps(dict(test="row_sharding", world=world, H=H, W=W, B=B, precision=precision, max_rel_err=err,
+        print(json.dumps(dict(test="row_sharding", world=world, H=H, W=W, B=B, C=C, precision=precision, max_rel_err=err,
                               ms_sharded=1e3 * dt_sharded, ms_single_gpu=1e3 * dt_single, events=len(ro.events),
                               halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo)), flush=True)
 dist.destroy_process_group()
