@@ -40,29 +40,43 @@ def local_window(h: int, rank: int, world: int, halo: int = HALO) -> Tuple[int, 
     return own_lo, own_hi, max(0, own_lo - halo), min(h, own_hi + halo)
 
 
-def exchange_halo_rows(t: torch.Tensor, own_lo: int, own_hi: int, lo: int, hi: int, rank: int, world: int, group=None,
-                       halo: int = HALO):
-    """t: [B, hi - lo, W, C] (NHWC local image, any dtype).  Sends the band's first / last ``halo`` rows to the upper / lower
-    neighbour and fills the local halos with theirs.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+def exchange_halo_rows(ts, own_lo: int, own_hi: int, lo: int, hi: int, rank: int, world: int, group=None, halo: int = HALO):
+    """ts: one tensor or a list of tensors [B, hi - lo, W, C] (NHWC local images, any dtypes).  Sends the band's first / last
+    ``halo`` rows of ALL of them to the upper / lower neighbour in ONE message per direction (byte-packed) and fills the
+    local halos with the neighbours' rows.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
     if world == 1:
         return
-    ops, recvs = [], []
+    if isinstance(ts, torch.Tensor):
+        ts = [ts]
     a, b = own_lo - lo, own_hi - lo              # band inside the local image
     peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+
+    def pack(rows):
+        return torch.cat([t[:, rows].contiguous().view(torch.uint8).reshape(-1) for t in ts])
+
+    def unpack(buf, rows):
+        off = 0
+        for t in ts:
+            dst = t[:, rows]
+            n = dst.numel() * dst.element_size()
+            dst.copy_(buf[off:off + n].view(t.dtype).view(dst.shape))
+            off += n
+
+    ops, recvs = [], []
     if rank > 0:
-        send_up = t[:, a:a + halo].contiguous()
-        recv_up = torch.empty_like(t[:, a - halo:a].contiguous())
+        send_up = pack(slice(a, a + halo))
+        recv_up = torch.empty_like(send_up)
         ops += [dist.P2POp(dist.isend, send_up, peer(rank - 1), group), dist.P2POp(dist.irecv, recv_up, peer(rank - 1), group)]
         recvs.append((slice(a - halo, a), recv_up))
     if rank < world - 1:
-        send_dn = t[:, b - halo:b].contiguous()
-        recv_dn = torch.empty_like(t[:, b:b + halo].contiguous())
+        send_dn = pack(slice(b - halo, b))
+        recv_dn = torch.empty_like(send_dn)
         ops += [dist.P2POp(dist.isend, send_dn, peer(rank + 1), group), dist.P2POp(dist.irecv, recv_dn, peer(rank + 1), group)]
         recvs.append((slice(b, b + halo), recv_dn))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     for rows, buf in recvs:
-        t[:, rows].copy_(buf)
+        unpack(buf, rows)
 
 
 class RowShardedOde:
@@ -97,13 +111,10 @@ class RowShardedOde:
         return eps
 
     # ------------------------------------------------------------------ one engine event with the collectives in place
-    def _run_event(self, ev_dict: dict):
+    def _run_event(self, ev, tdev):
         from .engine import BUF_S0, BUF_X
 
         eng, lib = self.eng, self.eng.lib
-        table, evs = eng.build_table([ev_dict])
-        tdev = eng.upload_table(table)
-        ev = evs[0]
         stream = eng._stream()
         rows_own0, rows_own1 = (self.own_lo - self.lo) * self.w, (self.own_hi - self.lo) * self.w
         n = ev.n_active
@@ -135,8 +146,7 @@ class RowShardedOde:
         xs = [eng.state32[s]] + [p for p in eng.act[BUF_S0 + s] if p is not None]
         if ev.run_prior:
             xs += [p for p in eng.act[BUF_X] if p is not None]
-        for t in xs:
-            exchange_halo_rows(t, self.own_lo, self.own_hi, self.lo, self.hi, self.rank, self.world, self.group)
+        exchange_halo_rows(xs, self.own_lo, self.own_hi, self.lo, self.hi, self.rank, self.world, self.group)
 
     def integrate(self, hx_obs: torch.Tensor, obs_counts: Sequence[int], times, targets, delta_t: float,
                   noise: Optional[torch.Tensor] = None):
@@ -152,9 +162,10 @@ class RowShardedOde:
         eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
         eng.bind_eps(noise[:, :, self.lo:self.hi].contiguous() if noise is not None else self.draw_noise(ro.n_eps))
-        for e in ro.events:
-            # the group's samples are indexed by sample id in the engine; x images of jumps are rows of the bound observations
-            self._run_event(e)
+        table, evs = eng.build_table(ro.events)          # one upload for the whole rollout
+        tdev = eng.upload_table(table)
+        for ev in evs:
+            self._run_event(ev, tdev)
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
         sel = eng.unpack_path(flat).view(B, T, eng.C, self.hi - self.lo, self.w)
