@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--no-module-level", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -274,22 +275,69 @@ def main():
                     share_of_event=d["ms_per_event"] / total,
                     event_tflops=FLOPS_PER_STATE_STEP_PX * hw * hw * B / (total * 1e-3) / 1e12)
 
-    cpu = gpu_eager = None
+    cpu = gpu_eager = module_level = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(hw)
         gpu_eager = gpu_eager_baseline(hw, dev)
+    if rank == 0 and world == 1 and args.grid == "cell" and not args.no_module_level:
+        module_level = module_level_numbers(model, dev, B)
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
                     ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic", config=workload_config(args, hw, B), clocks=clocks.summary(), e2e=e2e, gpu_launches=launches,
-                    roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=gpu_eager, stages=stages,
+                    roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=gpu_eager, module_level=module_level, stages=stages,
                     events_per_sec=world * (ro.n_state_steps + ro.n_jumps) * args.steps / (ms_total * 1e-3),
                     tflops=world * (ro.n_cell_evals * 2 * (227 * 4096 + 128) + ro.n_prior_evals * 2 * 137 * 4096) * hw * hw * args.steps
                     / (ms_total * 1e-3) / 1e12)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def module_level_numbers(model, dev, B, reps=3):
+    """The reference-faithful grid: FuturePredictionODE.forward on a 200x200x64 BEV (-> 50x50x64 latent), same
+    observation / target schedule, B samples.  ode_loop = the CUDA rollout alone on the 50x50 latents; forward = the whole
+    module call (torch encoder / decoder / refinement around it) with HOST buffers (pinned H2D of the BEV states, D2H of x)."""
+    import torch
+
+    H = 200
+    g = torch.Generator().manual_seed(3)
+    cam_h = torch.randn(B, 3, 64, H, H, generator=g).pin_memory()
+    lid_h = torch.randn(B, 5, 64, H, H, generator=g).pin_memory()
+    ct = torch.tensor([CAM_T] * B, dtype=torch.float64)
+    lt = torch.tensor([LIDAR_T] * B, dtype=torch.float64)
+    tt = torch.tensor([TARGETS] * B, dtype=torch.float64)
+    fpi = torch.zeros(B, 1, 64, H, H, device=dev)
+    out_h = torch.empty((B, len(TARGETS), 64, H, H), dtype=torch.float32).pin_memory()
+    ode = model.gru_ode
+    times = sorted(CAM_T + LIDAR_T)
+
+    def forward_host():
+        with torch.no_grad():
+            x, _ = model(fpi, cam_h.to(dev, non_blocking=True), lid_h.to(dev, non_blocking=True), ct, lt, tt)
+            out_h.copy_(x, non_blocking=True)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms_fwd = timed(forward_host)
+    n_steps = ode.last_rollout.n_state_steps
+    with torch.no_grad():
+        hx = torch.tanh(torch.randn(B * len(times), 64, H // 4, H // 4, device=dev))
+        ms_ode = timed(lambda: ode.integrate_latents(hx, [len(times)] * B, [times] * B, [TARGETS] * B, 0.05))
+    return dict(grid="50x50x64 latent of a 200x200x64 BEV", batch=B, ode_loop_ms=ms_ode, ode_loop_value=n_steps / (ms_ode * 1e-3),
+                forward_host_buffers_ms=ms_fwd, forward_value=n_steps / (ms_fwd * 1e-3), unit=UNIT,
+                note="forward = torch SmallEncoder + CUDA ODE loop + torch SmallDecoder + torch SpatialGRU/Block/DeepLabHead refinement; "
+                     "the torch parts are 'next' rows (DESIGN.md)")
 
 
 def time_stages(eng, B, hw, peaks, reps=10):
