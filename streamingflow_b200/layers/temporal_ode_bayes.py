@@ -133,6 +133,8 @@ class NNFOwithBayesianJumps(nn.Module):
         self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
         self.noise = "reference"
         self.noise_skip = 0                             # draws to discard first (batch sharding: samples of earlier ranks)
+        self.cuda_graph = os.environ.get("SF_B200_CUDA_GRAPH", "0") == "1"   # capture / replay the whole rollout as one CUDA graph
+        self.__dict__["_graphs"] = {}
         self.record_all = False                         # debug: keep the state after every event (last_trace)
         self.last_trace = None
         self.__dict__["_engines"] = {}
@@ -289,18 +291,61 @@ class NNFOwithBayesianJumps(nn.Module):
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
         ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all)
         eng = self._engine_for(h, w, B, dev)
+        T = len(targets[0])
+        flat = [s for slots in ro.out_slots for s in slots]
+        self.last_rollout = ro
+        if self.cuda_graph and not self.record_all and dev.type == "cuda" and self._engine_factory is None:
+            return self._graph_rollout(eng, ro, hx_obs, flat, B, T)
         eng.bind_observations(hx_obs)
         eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
         eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
         ro.launches = eng.run_rollout(ro.events)
-        self.last_rollout = ro
-        T = len(targets[0])
-        flat = [s for slots in ro.out_slots for s in slots]
         sel = eng.unpack_path(flat).view(B, T, c, h, w)
         if self.record_all:
             self.last_trace = [eng.unpack_path(slots) for slots in ro.trace_slots]
         return eng.unpack_f32(eng.state32[0], B), sel
+
+    def _graph_rollout(self, eng, ro, hx_obs, flat, B, T):
+        """The whole step loop as ONE CUDA graph (north star): layout pack, noise draws (torch's graph-safe Philox state, so the
+        stream stays identical to eager mode), every stage launch and the output gather are captured once per (engine,
+        schedule, shapes) and replayed; only the observation copy into the graph's static input is issued per call."""
+        _, c, h, w = hx_obs.shape
+        sig = (id(eng), eng.max_images, tuple(hx_obs.shape), self.noise, self.noise_skip, eng.precision,
+               tuple((e["kind"], e["x_buf"], e["s_in"], e["s_base"], e["s_out"], e["run_prior"], tuple(e["samples"]), tuple(e["x_img"]),
+                      tuple(e["rec"]), tuple(e["eps"]), tuple(e["dt"])) for e in ro.events), tuple(flat), self._weights_fingerprint())
+        ent = self._graphs.get(sig)
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            dev = hx_obs.device
+            static_hx = hx_obs.clone()
+            eng.bind_observations(static_hx)            # allocations happen here, outside the capture
+            eng.ensure_path_slots(ro.n_path)
+            table, evs = eng.build_table(ro.events)
+            tdev = eng.upload_table(table)
+            slots_dev = torch.tensor(flat, dtype=torch.int32).to(dev)
+            skip = self.noise_skip
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                eng.pack_into(3, static_hx)
+                eng.zero_state(0)
+                self.noise_skip = skip
+                eps = self._draw_noise(ro.n_eps, h, w, dev)
+                eng.bind_eps(eps)
+                n_launch = eng.run_events(evs, tdev)
+                sel = eng.unpack_path(slots_dev)
+                final = eng.unpack_f32(eng.state32[0], B)
+            ent = dict(graph=graph, hx=static_hx, eps=eps, sel=sel, final=final, keep=(tdev, slots_dev, evs), launches=n_launch)
+            self._graphs[sig] = ent
+            self.noise_skip = 0
+        else:
+            ent["hx"].copy_(hx_obs)
+            eng.bind_eps(ent["eps"])
+        ent["graph"].replay()
+        ro.launches = ent["launches"]
+        return ent["final"].clone(), ent["sel"].clone().view(B, T, c, h, w)
 
     def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None):
         """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final

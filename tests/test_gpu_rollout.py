@@ -259,3 +259,29 @@ def test_c128_rollout_matches_oracle(precision):
     errs = [_rel(got[i], ref[i]) for i in range(ref.shape[0])]
     assert max(errs) < TOL[precision], f"C=128 per-event latent error {max(errs):.3e} ({precision})"
     assert _rel(x, x_o) < 5 * TOL[precision]
+
+
+def test_cuda_graph_rollout_equals_eager_including_the_noise_stream():
+    """cuda_graph = True captures pack + noise + all stage launches + gather once and replays them: same bits as eager
+    mode, on the first (capture) call, on replays with new observations, and with torch's RNG advancing identically."""
+    m = _nnfo("euler", True, True, 5, 1.0, "bf16")
+    h = w = 24
+    times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])] * 2
+    targets = [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]] * 2
+    hx1 = torch.tanh(so.recipe_array("hx1", (16, 64, h, w), 5)).cuda()
+    hx2 = torch.tanh(so.recipe_array("hx2", (16, 64, h, w), 5)).cuda()
+    outs = {}
+    for mode in (False, True):
+        m.cuda_graph = mode
+        torch.manual_seed(77)
+        with torch.no_grad():
+            a = m.integrate_latents(hx1, [8, 8], times, targets, 0.05)
+            b = m.integrate_latents(hx2, [8, 8], times, targets, 0.05)       # replay in graph mode
+            c = m.integrate_latents(hx1, [8, 8], times, targets, 0.05)       # same input, later point of the noise stream
+        torch.cuda.synchronize()
+        outs[mode] = [t.clone() for pair in (a, b, c) for t in pair]
+        tail = torch.randn(4, device="cuda")                                  # the generator ends in the same state
+        outs[mode].append(tail)
+    for x, y in zip(outs[False], outs[True]):
+        assert torch.equal(x, y)
+    assert not torch.equal(outs[True][1], outs[True][5])                      # a and c saw different noise
