@@ -153,6 +153,7 @@ def workload_config(args, hw, batch):
                          f"observations (8 jumps + 10 variable Euler state-steps per sample), ODE grid {hw}x{hw}x64 "
                          f"({'cell-level: the literal 200x200x64 state' if args.grid == 'cell' else 'module-level latent of a 200x200x64 BEV'})",
                 grid=args.grid, batch_per_gpu=batch, precision=args.precision, solver="euler", variable_step=True, impute=True,
+                launch="eager" if getattr(args, "no_graph", True) else "one CUDA graph per rollout (pack + noise + stages + gather)",
                 l2="inputs + workspace (>1 GB at 200x200, B=8) exceed the 126 MB L2; no explicit flush" if hw >= 200 else
                    "working set fits L2 (module-level latent): L2 flushed by a 256 MB memset between steps",
                 parallelism=f"batch-sharded x{args.gpus}, no collective in the data path")
@@ -170,6 +171,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-timing", action="store_true")
     ap.add_argument("--no-module-level", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the stages eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -191,6 +193,7 @@ def main():
     model = make_model(dev)
     ode = model.gru_ode
     ode.precision = args.precision
+    ode.cuda_graph = not args.no_graph       # the whole step loop is one captured CUDA graph (eager launches with --no-graph)
     times = sorted(CAM_T + LIDAR_T)
     n_obs = len(times)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -226,7 +229,7 @@ def main():
             b.record()
         barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    launches = (eng.launches - launches0) // args.steps + 2      # + pack + gather kernels per rollout
+    launches = ro.launches + 2               # stage kernels of one rollout + layout pack + path gather
     eng.check_errflag()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -333,8 +336,14 @@ def module_level_numbers(model, dev, B, reps=3):
     n_steps = ode.last_rollout.n_state_steps
     with torch.no_grad():
         hx = torch.tanh(torch.randn(B * len(times), 64, H // 4, H // 4, device=dev))
+        was = ode.cuda_graph
+        ode.cuda_graph = False
+        ms_eager = timed(lambda: ode.integrate_latents(hx, [len(times)] * B, [times] * B, [TARGETS] * B, 0.05))
+        ode.cuda_graph = True
         ms_ode = timed(lambda: ode.integrate_latents(hx, [len(times)] * B, [times] * B, [TARGETS] * B, 0.05))
+        ode.cuda_graph = was
     return dict(grid="50x50x64 latent of a 200x200x64 BEV", batch=B, ode_loop_ms=ms_ode, ode_loop_value=n_steps / (ms_ode * 1e-3),
+                ode_loop_eager_launch_ms=ms_eager,
                 forward_host_buffers_ms=ms_fwd, forward_value=n_steps / (ms_fwd * 1e-3), unit=UNIT,
                 note="forward = torch SmallEncoder + CUDA ODE loop + torch SmallDecoder + torch SpatialGRU/Block/DeepLabHead refinement; "
                      "the torch parts are 'next' rows (DESIGN.md)")
