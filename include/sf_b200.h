@@ -68,7 +68,7 @@ typedef struct {
   int32_t init;     /* 1: the chunk's first MMA overwrites its columns instead of accumulating           */
 } sf_chunk;
 
-#define SF_MAX_CHUNKS 12
+#define SF_MAX_CHUNKS 16
 #define SF_MAX_ACT_BUFS 32
 #define SF_MAX_STAGES 32
 
@@ -94,6 +94,8 @@ typedef enum {
   SF_F32_PARAMS = 8,    /* optional fp32 p_model output [image][H][W][2C] (infer_state API)               */
   SF_F32_COUNT = 9
 } sf_f32_slot;
+#define SF_F32_ERRFLAG 9   /* int32 device word: a bounded pipeline wait that times out stores a code here before trapping */
+#define SF_F32_OUT 10      /* optional fp32 NHWC copy of a bias_act stage's output (stage flag bit 4)                       */
 
 /* One event = one pass of {cell stages} + optional {prior-network stages} over the listed samples. */
 typedef struct {
@@ -126,7 +128,8 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
 /* packed weights: bf16 [w_rows][64] device pointer; vec: fp32 device pointer (bias / LN / gate weights) */
 /* io_bufs / io_choff: the epilogue's activation buffers and the first channel each launch touches in them, in the order
    the epilogue expects (gates: u_0, gated_0[, u_1, gated_1]; propose: u_0[, u_1], out_0[, out_1]; res_id: residual, out;
-   others: out).  flags bit 0 (propose): also keep the blend in the fp32 tensor SF_F32_A.                            */
+   others: out).  flags: bit 0 (propose) also keep the blend in the fp32 tensor SF_F32_A; bits 1-3 (bias_act) activation:
+   0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity; bit 4 (bias_act) also write the output to SF_F32_OUT in fp32.          */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
                          const void* w_packed, int w_rows, const float* vec, int n_vec,
                          const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags);
@@ -154,6 +157,11 @@ int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* t
 /* layout kernels (HBM-bound, 128-bit vectorised) */
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);
 int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n_out, int C, int H, int W, void* stream);
+/* SmallEncoder / SmallDecoder glue on NHWC bf16 planes: 2x2 max-pool (res_models.py:96-104), nearest x2 up-sampling
+   (:134-147; call once per plane), fp32 NHWC (gathered by slot) -> bf16 hi [+ lo] */
+int sf_maxpool2(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int n_images, int H, int W, int C, void* stream);
+int sf_upsample2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream);
+int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void* dst_lo, int n_out, int C, int H, int W, void* stream);
 
 /* self-test kernels for bring-up: TMA tile dump and a single UMMA tile product */
 int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0,

@@ -12,7 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libsf_b200.so")
 SF_ABI_VERSION = 1
 PREC_BF16, PREC_BF16X3 = 0, 1
 (EPI_GATES, EPI_PROPOSE, EPI_DECODE, EPI_LNGELU, EPI_MIX, EPI_BIAS_LRELU, EPI_RES_PROJ, EPI_RES_ID, EPI_SAMPLE) = range(9)
-(F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG) = range(10)
+(F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT) = range(11)
+ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE = 0, 1, 2, 3
+FLAG_KEEP_A32, FLAG_OUT32 = 1, 16
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
 SE_ITEM_BASE = 1000
 
@@ -52,6 +54,9 @@ EXPORTS = {
     "sf_plan_se_apply": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "sf_pack_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_upsample2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_cast_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "sf_diag_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_umma_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -55,6 +55,8 @@ struct EpiArgs {
   int in_cs[2], in_co[2];     // same for the element-wise inputs
   int n_out;      // output channels written by this launch (64 or 128)
   int kind;       // event kind (0 derivative step, 1 jump)
+  int act;        // bias_act / residual epilogues: 0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity
+  float* out32;   // optional fp32 NHWC copy of the bias_act output [image][H][W][n_out]
 };
 
 struct alignas(64) StageParams {
@@ -124,6 +126,14 @@ __device__ __forceinline__ void store_f32x16(float* p, const float (&v)[16]) {
   for (int i = 0; i < 8; ++i) { a[i] = __float_as_uint(v[i]); b[i] = __float_as_uint(v[8 + i]); }
   stg256(p, a);
   stg256(p + 8, b);
+}
+__device__ __forceinline__ float activate(float x, int act) {
+  switch (act) {
+    case 0: return lrelu01(x);
+    case 1: return tanhf(x);
+    case 2: return fmaxf(x, 0.0f);
+    default: return x;
+  }
 }
 __device__ __forceinline__ void zero16(float (&v)[16]) {
 #pragma unroll
@@ -312,21 +322,24 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
       if (c.valid) {
+        const int act = e.act;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]);
+        for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + b[i], act);
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
+        if (e.out32) store_f32x16(e.out32 + c.pix * n + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_RES_PROJ) {
-    // columns: [0,128) conv_2 (BN folded) | [128,256) 1x1 projection, for 128 output channels starting at out_co;
-    // vec = [bn bias (128), proj bias (128)]
+    // columns: [0,n) conv_2 (BN folded) | [n,2n) 1x1 projection, for n = n_out (64 or 128) output channels starting at
+    // out_co; vec = [bn bias (n), proj bias (n)]
+    const int n = e.n_out;
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0];
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < n / 16; ++j) {
       float v[16], q[16], b[16], pb[16];
-      tmem_ld16x2(taddr + j * 16, taddr + 128 + j * 16, v, q);
+      tmem_ld16x2(taddr + j * 16, taddr + n + j * 16, v, q);
       vec16(vec, j * 16, b);
-      vec16(vec, 128 + j * 16, pb);
+      vec16(vec, n + j * 16, pb);
       if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + (q[i] + pb[i]);
@@ -336,7 +349,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
   } else if constexpr (EPI == SF_EPI_RES_ID) {
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < e.n_out / 16; ++j) {
       float v[16], r[16], b[16];
       if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], i0 + j * 16, r); else zero16(r);
       tmem_ld16(taddr + j * 16, v);

@@ -205,6 +205,95 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
   }
 }
 
+// ---- 2x2 max-pool and nearest 2x up-sampling on NHWC bf16 (hi [+ lo]) activations (SmallEncoder / SmallDecoder) -----------
+// one thread = 8 channels (16 B) of one output pixel
+template <bool X3>
+__global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                       __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl, int n_img, int H,
+                                                       int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, G = C / 8;
+  const size_t total = (size_t)n_img * Ho * Wo * G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    size_t r = idx / G;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const size_t off = (((size_t)img * H + 2 * yo + dy) * W + 2 * xo + dx) * C + g * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(sh + off);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo_f(w[i]); f[2 * i + 1] = bf16_hi_f(w[i]); }
+        if (X3) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sl + off);
+          const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { f[2 * i] += bf16_lo_f(x[i]); f[2 * i + 1] += bf16_hi_f(x[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+      }
+    const size_t o = (((size_t)img * Ho + yo) * Wo + xo) * C + g * 8;
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(m[2 * i], m[2 * i + 1]);
+    *reinterpret_cast<uint4*>(dh + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(m[2 * i] - bf16_lo_f(h[i]), m[2 * i + 1] - bf16_hi_f(h[i]));
+      *reinterpret_cast<uint4*>(dl + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// nearest-neighbour x2: pure copy of 16-byte channel groups (works per plane)
+__global__ void __launch_bounds__(256) upsample2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_img, int H, int W, int G) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)n_img * Ho * Wo * G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    size_t r = idx / G;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    dst[idx] = src[(((size_t)img * H + yo / 2) * W + xo / 2) * G + g];
+  }
+}
+
+// fp32 NHWC (recorded path states, gathered by slot) -> bf16 NHWC hi [+ lo]: the decoder's input
+template <bool X3>
+__global__ void __launch_bounds__(256) cast_nhwc_kernel(const float* __restrict__ src, const int* __restrict__ slots, __nv_bfloat16* __restrict__ dh,
+                                                        __nv_bfloat16* __restrict__ dl, int n_out, size_t per_img) {   // per_img = H*W*C, multiple of 8
+  const size_t groups = per_img / 8, total = (size_t)n_out * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(idx / groups);
+    const size_t g = idx % groups;
+    const int slot = slots ? slots[o] : o;
+    const float4* q = reinterpret_cast<const float4*>(src + (size_t)slot * per_img + g * 8);
+    const float4 a = q[0], b = q[1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(dh + (size_t)o * per_img + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
+      *reinterpret_cast<uint4*>(dl + (size_t)o * per_img + g * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
 // ---- NHWC fp32 (recorded path states) -> NCHW fp32 (decoder input), gathered by slot ----------------------
 __global__ void __launch_bounds__(256) unpack_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                           const int* __restrict__ slots, int C, int hw) {

@@ -1,5 +1,6 @@
 // sf_plan.cu -- host side of libsf_b200.so: the plan object (buffer bindings, stage definitions, TMA
 // descriptors), kernel launches and the extern "C" ABI declared in include/sf_b200.h.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -77,7 +78,7 @@ struct sf_plan {
   int num_sms = 148;
   bool finalized = false;
   ActBuf act[SF_MAX_ACT_BUFS];
-  void* f32[SF_F32_COUNT + 1] = {};
+  void* f32[SF_F32_COUNT + 2] = {};
   Stage stage[SF_MAX_STAGES];
   SeDef se[2];
   std::vector<int> cell[2], prior;
@@ -246,14 +247,17 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
     case SF_EPI_RES_ID:
       if (!need_io(2)) return fail(SF_ERR_INVALID, "residual stage needs 2 io buffers");
       in(0, 0); out(0, 1);
-      e.n_out = 128;
+      e.n_out = st.n_out;
       break;
     default:
       if (!need_io(1)) return fail(SF_ERR_INVALID, "stage needs an output buffer");
       out(0, 0);
-      e.n_out = (st.epi == SF_EPI_BIAS_LRELU) ? st.n_out : p->act[st.io[0]].channels;
+      e.n_out = (st.epi == SF_EPI_BIAS_LRELU || st.epi == SF_EPI_RES_PROJ) ? st.n_out : p->act[st.io[0]].channels;
       break;
   }
+  e.act = (st.flags >> 1) & 7;                                        // bias_act activation code
+  e.out32 = (st.flags & 16) ? reinterpret_cast<float*>(p->f32[SF_F32_OUT]) : nullptr;
+  if ((st.flags & 16) && !e.out32) return fail(SF_ERR_STATE, "fp32 output requested but SF_F32_OUT is not bound");
   if (st.epi == SF_EPI_MIX || st.epi == SF_EPI_GATES || st.epi == SF_EPI_PROPOSE)
     if (!e.s_in || !e.s_out || !e.s_base) return fail(SF_ERR_STATE, "state buffers not bound");
   if (st.epi == SF_EPI_SAMPLE && !e.eps) return fail(SF_ERR_STATE, "eps buffer not bound");
@@ -422,7 +426,7 @@ int sf_plan_bind_act(sf_plan* p, int buf, void* hi, void* lo, int channels, int 
 }
 
 int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr) {
-  if (!p || slot < 0 || slot > SF_F32_COUNT) return fail(SF_ERR_INVALID, "bad fp32 slot");   // slot SF_F32_COUNT = int32 error flag
+  if (!p || slot < 0 || slot > SF_F32_COUNT + 1) return fail(SF_ERR_INVALID, "bad fp32 slot");   // COUNT = int32 error flag, COUNT+1 = SF_F32_OUT
   p->f32[slot] = ptr;
   return SF_OK;
 }
@@ -559,6 +563,40 @@ int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images,
     pack_nchw_kernel<true><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), C, hw);
   else
     pack_nchw_kernel<false><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), nullptr, C, hw);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_maxpool2(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int n_images, int H, int W, int C, void* stream) {
+  if (!src_hi || !dst_hi || C % 8 || (H & 1) || (W & 1) || n_images <= 0) return fail(SF_ERR_INVALID, "bad maxpool arguments");
+  const size_t total = (size_t)n_images * (H / 2) * (W / 2) * (C / 8);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
+  auto dh = reinterpret_cast<__nv_bfloat16*>(dst_hi); auto dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
+  if (src_lo && dst_lo) maxpool2_kernel<true><<<grid, 256, 0, s>>>(sh, sl, dh, dl, n_images, H, W, C);
+  else maxpool2_kernel<false><<<grid, 256, 0, s>>>(sh, sl, dh, dl, n_images, H, W, C);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_upsample2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream) {
+  if (!src || !dst || C % 8 || n_images <= 0) return fail(SF_ERR_INVALID, "bad upsample arguments");
+  const size_t total = (size_t)n_images * (2 * H) * (2 * W) * (C / 8);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  upsample2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+                                                                           n_images, H, W, C / 8);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void* dst_lo, int n_out, int C, int H, int W, void* stream) {
+  if (!src || !dst_hi || C % 8 || n_out <= 0) return fail(SF_ERR_INVALID, "bad cast arguments");
+  const size_t per = (size_t)H * W * C, total = (size_t)n_out * per / 8;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_lo) cast_nhwc_kernel<true><<<grid, 256, 0, s>>>(src, slots, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), n_out, per);
+  else cast_nhwc_kernel<false><<<grid, 256, 0, s>>>(src, slots, reinterpret_cast<__nv_bfloat16*>(dst_hi), nullptr, n_out, per);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -339,6 +339,16 @@ class OdeEngine:
         self.pack_into(BUF_OBS, hx_nchw)
         self.n_obs_images = n
 
+    def bind_observation_planes(self, hi: torch.Tensor, lo: Optional[torch.Tensor]):
+        """Use already-encoded NHWC bf16 planes [n, H, W, C] (the fused encoder's output buffer) as the observation buffer."""
+        assert tuple(hi.shape[1:]) == (self.H, self.W, self.C) and hi.dtype == torch.bfloat16 and hi.is_contiguous()
+        if self.x3 and lo is None:
+            raise L.SfError("bf16x3 needs the residual plane of the observations")
+        self.act[BUF_OBS] = (hi, lo)
+        L.check(self.lib.sf_plan_bind_act(self.plan, BUF_OBS, hi.data_ptr(), lo.data_ptr() if lo is not None else None, self.C, hi.shape[0]),
+                "sf_plan_bind_act")
+        self.n_obs_images = hi.shape[0]
+
     def set_state(self, which: int, state_nchw: torch.Tensor):
         n = state_nchw.shape[0]
         nhwc = state_nchw.float().permute(0, 2, 3, 1).contiguous()

@@ -134,6 +134,8 @@ class NNFOwithBayesianJumps(nn.Module):
         self.noise = "reference"
         self.noise_skip = 0                             # draws to discard first (batch sharding: samples of earlier ranks)
         self.cuda_graph = os.environ.get("SF_B200_CUDA_GRAPH", "0") == "1"   # capture / replay the whole rollout as one CUDA graph
+        self.fused_codec = os.environ.get("SF_B200_FUSED_CODEC", "1") == "1"  # SmallEncoder / SmallDecoder on the conv-stage kernels
+        self.__dict__["_codecs"] = {}
         self.__dict__["_graphs"] = {}
         self.record_all = False                         # debug: keep the state after every event (last_trace)
         self.last_trace = None
@@ -278,15 +280,41 @@ class NNFOwithBayesianJumps(nn.Module):
         return eng.unpack_f32(eng.state32[0], n), eng.unpack_f32(eng.x32, n), current_time, eval_times, eval_ps
 
     # ------------------------------------------------------------------ the rollout
+    def codec_available(self, H, W, device) -> bool:
+        """The fused encoder / decoder covers the shipped configuration: 64 channels everywhere, no skip connections."""
+        return (self.fused_codec and device.type == "cuda" and not self.training and not self.skipco and self._engine_factory is None
+                and self.hidden_size == 64 and self.input_size == 64 and H % 4 == 0 and W % 4 == 0
+                and self.srvp_encoder.blocks[0].layers.conv_1.conv.weight.shape[0] == 64
+                and self.srvp_encoder.blocks[0].layers.conv_2.conv.weight.shape[0] == 64)
+
+    def _codec_for(self, H, W, n_enc, n_dec, device):
+        from ..codec_engine import CodecEngine
+
+        key = (str(device), H, W, self.precision)
+        fp = tuple((p.data_ptr(), p._version) for mod in (self.srvp_encoder, self.srvp_decoder)
+                   for p in list(mod.parameters()) + list(mod.buffers()))
+        ent = self._codecs.get(key)
+        if ent is None or ent["fp"] != fp or ent["codec"].n_enc < n_enc or ent["codec"].n_dec < n_dec:
+            sd = {f"{name}.{k}": v for name in ("srvp_encoder", "srvp_decoder") for k, v in getattr(self, name).state_dict().items()}
+            ent = dict(codec=CodecEngine(sd, H, W, n_enc, n_dec, self.precision, device), fp=fp)
+            self._codecs[key] = ent
+        return ent["codec"]
+
     def integrate_latents(self, hx_obs, obs_counts: Sequence[int], times: Sequence[Sequence[float]],
-                          targets: Sequence[Sequence[float]], delta_t: float):
+                          targets: Sequence[Sequence[float]], delta_t: float, obs_planes=None, return_slots: bool = False):
         """Batched jump / integrate loop on already-encoded observations.
 
-        hx_obs: [sum(obs_counts), C, h, w] fp32 latents, sample-major, each sample's frames in processing order.
-        times[b] / targets[b]: python floats.  Returns (final states [B,C,h,w], selected latents [B,T,C,h,w])."""
+        hx_obs: [sum(obs_counts), C, h, w] fp32 latents, sample-major, each sample's frames in processing order -- or None
+        with obs_planes = (hi, lo) NHWC bf16 planes [n, h, w, C] from the fused encoder.
+        times[b] / targets[b]: python floats.  Returns (final states [B,C,h,w], selected latents [B,T,C,h,w]); with
+        return_slots the second value is (engine, flat path slots) so a fused decoder can read the path buffer directly."""
         B = len(obs_counts)
-        _, c, h, w = hx_obs.shape
-        dev = hx_obs.device
+        if obs_planes is not None:
+            _, h, w, c = obs_planes[0].shape
+            dev = obs_planes[0].device
+        else:
+            _, c, h, w = hx_obs.shape
+            dev = hx_obs.device
         plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
         ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all)
@@ -294,16 +322,22 @@ class NNFOwithBayesianJumps(nn.Module):
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
         self.last_rollout = ro
-        if self.cuda_graph and not self.record_all and dev.type == "cuda" and self._engine_factory is None:
+        if self.cuda_graph and not self.record_all and dev.type == "cuda" and self._engine_factory is None and obs_planes is None \
+                and not return_slots:
             return self._graph_rollout(eng, ro, hx_obs, flat, B, T)
-        eng.bind_observations(hx_obs)
+        if obs_planes is not None:
+            eng.bind_observation_planes(*obs_planes)
+        else:
+            eng.bind_observations(hx_obs)
         eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
         eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
         ro.launches = eng.run_rollout(ro.events)
-        sel = eng.unpack_path(flat).view(B, T, c, h, w)
         if self.record_all:
             self.last_trace = [eng.unpack_path(slots) for slots in ro.trace_slots]
+        if return_slots:
+            return eng.unpack_f32(eng.state32[0], B), (eng, flat)
+        sel = eng.unpack_path(flat).view(B, T, c, h, w)
         return eng.unpack_f32(eng.state32[0], B), sel
 
     def _graph_rollout(self, eng, ro, hx_obs, flat, B, T):
@@ -429,7 +463,25 @@ class NNFOwithBayesianJumps(nn.Module):
             raise NotImplementedError("the reference calls gru_ode with one sample (obs batch 1); use FuturePredictionODE for batches")
         t_list = times.tolist() if isinstance(times, torch.Tensor) else [float(t) for t in times]
         T_list = T.tolist() if isinstance(T, torch.Tensor) else [float(t) for t in T]
+        n_obs, H, W = obs.shape[1], obs.shape[3], obs.shape[4]
+        if self.codec_available(H, W, obs.device):
+            state, x = self.encode_integrate_decode(obs[0], [n_obs], [t_list], [T_list], delta_t)
+            return state, 0, x
         hx_obs, _ = self.srvp_encode(obs)
-        state, sel = self.integrate_latents(hx_obs[0], [hx_obs.shape[1]], [t_list], [T_list], delta_t)
+        state, sel = self.integrate_latents(hx_obs[0], [n_obs], [t_list], [T_list], delta_t)
         x = self.srvp_decode(sel)
         return state, 0, x
+
+    def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t):
+        """SmallEncoder -> jump / integrate loop -> SmallDecoder entirely on the conv-stage kernels: frames [n, C, H, W] (all
+        samples' observation frames, sample-major, processing order) -> (final latent states, decoded frames [B, T, C, H, W])."""
+        n, c, H, W = frames.shape
+        B, T = len(obs_counts), len(targets[0])
+        codec = self._codec_for(H, W, n, B * T, frames.device)
+        planes = codec.encode(frames)
+        state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True)
+        slots = torch.tensor(flat, dtype=torch.int32).to(frames.device)
+        x = codec.decode(eng.path, slots).view(B, T, c, H, W)
+        self.last_rollout.launches += codec.launches
+        codec.launches = 0
+        return state, x

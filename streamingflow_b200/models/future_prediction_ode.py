@@ -49,9 +49,13 @@ class FuturePredictionODE(nn.Module):
             counts.append(len(order))
             times.append([t for t, _, _ in order])
         ode = self.gru_ode
-        hx = ode.srvp_encoder(torch.stack(frames, dim=0))
-        _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t)
-        x = ode.srvp_decode(sel)                                       # [B, T, C, H, W]
+        stacked = torch.stack(frames, dim=0)
+        if ode.codec_available(stacked.shape[2], stacked.shape[3], stacked.device):
+            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t)      # all three parts on the CUDA engine
+        else:
+            hx = ode.srvp_encoder(stacked)
+            _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t)
+            x = ode.srvp_decode(sel)                                   # [B, T, C, H, W]
         hidden_state = x[:, 0]
         for gru, block in zip(self.spatial_grus, self.res_blocks):
             x = gru(x, hidden_state)

@@ -11,6 +11,7 @@ import torch
 from oracle import sf_oracle as so
 from oracle._refimport import make_cfg
 from oracle.shapes import nnfo_shapes
+from oracle.shapes import nnfo_shapes
 
 pytestmark = pytest.mark.gpu
 TOL = {"bf16": 1e-2, "bf16x3": 1e-4}
@@ -285,3 +286,27 @@ def test_cuda_graph_rollout_equals_eager_including_the_noise_stream():
     for x, y in zip(outs[False], outs[True]):
         assert torch.equal(x, y)
     assert not torch.equal(outs[True][1], outs[True][5])                      # a and c saw different noise
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_fused_encoder_and_decoder_match_oracle(precision):
+    """SmallEncoder / SmallDecoder on the conv-stage kernels (codec_engine.py) vs the fp64 oracle, ragged BEV size 72x56."""
+    from streamingflow_b200.codec_engine import CodecEngine
+
+    seed, H, W, n = 23, 72, 56, 3
+    sd32 = so.recipe_state_dict(nnfo_shapes(64), seed, 1.0)
+    sd64 = {"g." + k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd32.items()}
+    codec = CodecEngine({k: v.cuda() for k, v in sd32.items()}, H, W, n, n, precision, torch.device("cuda", torch.cuda.current_device()))
+    frames = so.recipe_array("frames", (n, 64, H, W), seed).cuda()
+    hi, lo = codec.encode(frames)
+    got = hi.float() + (lo.float() if lo is not None else 0)
+    with torch.no_grad():
+        want = so.small_encoder(sd64, "g.srvp_encoder", frames.double())
+    tol = 2e-2 if precision == "bf16" else 1e-4
+    assert _rel(got.permute(0, 3, 1, 2), want) < tol
+    z = torch.tanh(so.recipe_array("z", (5, H // 4, W // 4, 64), seed)).cuda().contiguous()     # a "path buffer" with 5 slots
+    slots = torch.tensor([4, 0, 2], dtype=torch.int32, device="cuda")
+    out = codec.decode(z, slots)
+    with torch.no_grad():
+        want = so.small_decoder(sd64, "g.srvp_decoder", z[[4, 0, 2]].permute(0, 3, 1, 2).double())
+    assert out.shape == want.shape and _rel(out, want) < tol

@@ -220,3 +220,60 @@ def test_packed_stage_plans_c128():
         assert (acc - ref).abs().max() < 1e-9 and prior[name].io_off == [128 * h]
     acc = en.emulate_stage(prior["q5"], False, src)
     assert (acc - conv(y1, sd["p_model.model.4.conv.weight"], 1)).abs().max() < 1e-9
+
+
+def _interpret_codec_graph(graph, bufs_spec, x_in, in_key, out_key, dims):
+    """Host interpreter of a codec op list: replays each stage's packed GEMM plan (engine.emulate_stage) and applies the
+    epilogue's arithmetic in torch, so the stage graph / weight packing of codec_engine.py is pinned on CPU."""
+    from streamingflow_b200 import _lib as L, engine as en
+    import torch.nn.functional as F
+
+    bufs = {lvl: {b: torch.zeros(1, ch, *dims[lvl], dtype=torch.float64) for b, ch in chans.items()} for lvl, chans in bufs_spec.items()}
+    bufs[in_key[0]][in_key[1]] = x_in.double()
+    out32 = None
+    for op in graph:
+        if op[0] == "pool":
+            bufs[op[2][0]][op[2][1]] = F.max_pool2d(bufs[op[1][0]][op[1][1]], 2, 2)
+            continue
+        if op[0] == "up":
+            bufs[op[2][0]][op[2][1]] = F.interpolate(bufs[op[1][0]][op[1][1]], scale_factor=2, mode="nearest")
+            continue
+        _, lvl, sdef = op
+        acc = en.emulate_stage(sdef, True, {b: t.float() for b, t in bufs[lvl].items()})      # split-bf16 replay ~ fp32 accurate
+        vec = sdef.vec.double()
+        n = max(c[2].shape[0] for c in sdef.chunks if c[3] == 0)
+        if sdef.epilogue == L.EPI_BIAS_LRELU:
+            v = acc[:n] + vec[:n, None, None]
+            act = (sdef.flags >> 1) & 7
+            v = F.leaky_relu(v, 0.1) if act == 0 else torch.tanh(v) if act == 1 else v
+            dst, off = sdef.io[0], sdef.io_off[0]
+        elif sdef.epilogue == L.EPI_RES_ID:
+            v = F.leaky_relu(acc[:n] + vec[:n, None, None], 0.1) + bufs[lvl][sdef.io[0]][0, sdef.io_off[0]:sdef.io_off[0] + n]
+            dst, off = sdef.io[1], sdef.io_off[1]
+        else:
+            assert sdef.epilogue == L.EPI_RES_PROJ
+            v = F.leaky_relu(acc[:n] + vec[:n, None, None], 0.1) + acc[n:2 * n] + vec[n:2 * n, None, None]
+            dst, off = sdef.io[0], sdef.io_off[0]
+        bufs[lvl][dst][0, off:off + n] = v
+    return bufs[out_key[0]][out_key[1]]
+
+
+def test_codec_stage_graphs_reproduce_encoder_and_decoder():
+    """SmallEncoder / SmallDecoder as conv-stage graphs (BatchNorm folded, ConvTranspose as flipped conv, 128-channel output
+    groups, residual / projection epilogues) == the oracle's encoder / decoder."""
+    from streamingflow_b200 import codec_engine as ce
+
+    sd = so.recipe_state_dict(nnfo_shapes(64), 9, 1.0, torch.float32)
+    H, W = 16, 24
+    dims = {"A": (H, W), "B": (H // 2, W // 2), "C": (H // 4, W // 4)}
+    x = so.recipe_array("bev", (1, 64, H, W), 9, torch.float32)
+    sd64 = {"g." + k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        want = so.small_encoder(sd64, "g.srvp_encoder", x.double())
+        got = _interpret_codec_graph(ce.encoder_graph(sd), ce.ENC_BUFS, x, ce.ENC_IN, ce.ENC_OUT, dims)
+    assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
+    z = torch.tanh(so.recipe_array("lat", (1, 64, H // 4, W // 4), 9, torch.float32))
+    with torch.no_grad():
+        want = so.small_decoder(sd64, "g.srvp_decoder", z.double())
+        got = _interpret_codec_graph(ce.decoder_graph(sd), ce.DEC_BUFS, z, ce.DEC_IN, ce.DEC_OUT, dims)
+    assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
