@@ -180,6 +180,10 @@ class CodecEngine:
         self.lib = L.load()
         self.H, self.W, self.h, self.w = H, W, H // 4, W // 4
         self.device = device
+        # The encoder always runs in the accurate split-bf16 mode: its output feeds every observation jump, and bf16 operands
+        # through its 11 convolutions would alone spend the hidden state's 1e-2 budget (measured 1.5e-2 on the reference
+        # fixtures).  The decoder only shapes the output frames and follows the requested precision.
+        self.enc_x3 = True
         self.x3 = precision == "bf16x3"
         self.n_enc, self.n_dec = n_enc, n_dec
         sd = {k: v.detach().to(device) for k, v in sd.items() if k.startswith(("srvp_encoder", "srvp_decoder"))}
@@ -188,15 +192,15 @@ class CodecEngine:
         self.launches = 0
         dims = {"A": (H, W), "B": (H // 2, W // 2), "C": (H // 4, W // 4)}
         self.dims = dims
-        self.enc, self.enc_ops = self._build(encoder_graph(sd), ENC_BUFS, n_enc, dims)
-        self.dec, self.dec_ops = self._build(decoder_graph(sd), DEC_BUFS, n_dec, dims)
+        self.enc, self.enc_ops = self._build(encoder_graph(sd), ENC_BUFS, n_enc, dims, self.enc_x3)
+        self.dec, self.dec_ops = self._build(decoder_graph(sd), DEC_BUFS, n_dec, dims, self.x3)
         self.dec_out32 = torch.empty((n_dec, H, W, 64), dtype=torch.float32, device=device)
         self.dec["A"].bind_out32(self.dec_out32)
 
-    def _build(self, graph, bufs, n, dims):
+    def _build(self, graph, bufs, n, dims, x3):
         plans = {}
         for lvl, chans in bufs.items():
-            plans[lvl] = LevelPlan(self.lib, dims[lvl][0], dims[lvl][1], n, self.x3, self.device)
+            plans[lvl] = LevelPlan(self.lib, dims[lvl][0], dims[lvl][1], n, x3, self.device)
             for b, ch in chans.items():
                 plans[lvl].buf(b, ch)
         ops = []

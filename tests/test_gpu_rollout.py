@@ -11,7 +11,6 @@ import torch
 from oracle import sf_oracle as so
 from oracle._refimport import make_cfg
 from oracle.shapes import nnfo_shapes
-from oracle.shapes import nnfo_shapes
 
 pytestmark = pytest.mark.gpu
 TOL = {"bf16": 1e-2, "bf16x3": 1e-4}
@@ -303,7 +302,7 @@ def test_fused_encoder_and_decoder_match_oracle(precision):
     with torch.no_grad():
         want = so.small_encoder(sd64, "g.srvp_encoder", frames.double())
     tol = 2e-2 if precision == "bf16" else 1e-4
-    assert _rel(got.permute(0, 3, 1, 2), want) < tol
+    assert _rel(got.permute(0, 3, 1, 2), want) < 1e-4          # the encoder always runs in the accurate mode
     z = torch.tanh(so.recipe_array("z", (5, H // 4, W // 4, 64), seed)).cuda().contiguous()     # a "path buffer" with 5 slots
     slots = torch.tensor([4, 0, 2], dtype=torch.int32, device="cuda")
     out = codec.decode(z, slots)
