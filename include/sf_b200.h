@@ -66,9 +66,10 @@ typedef struct {
   int32_t wrow;     /* first row of this chunk in the packed weight matrix; tap (dx,dy) rep r starts at
                        wrow + ((dx*R+dy)*nrep + r)*n                                                     */
   int32_t init;     /* 1: the chunk's first MMA overwrites its columns instead of accumulating           */
+  int32_t ox, oy;   /* pixel offset of the chunk's input window (dilated taps are R = 1 chunks at (kx-1)*d, (ky-1)*d) */
 } sf_chunk;
 
-#define SF_MAX_CHUNKS 16
+#define SF_MAX_CHUNKS 24
 #define SF_MAX_ACT_BUFS 32
 #define SF_MAX_STAGES 32
 
@@ -96,6 +97,7 @@ typedef enum {
 } sf_f32_slot;
 #define SF_F32_ERRFLAG 9   /* int32 device word: a bounded pipeline wait that times out stores a code here before trapping */
 #define SF_F32_OUT 10      /* optional fp32 NHWC copy of a bias_act stage's output (stage flag bit 4)                       */
+#define SF_F32_IMG_BIAS 11 /* optional per-image bias [image][n_out] added by a bias_act stage (stage flag bit 6)            */
 
 /* One event = one pass of {cell stages} + optional {prior-network stages} over the listed samples. */
 typedef struct {
@@ -129,7 +131,9 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
 /* io_bufs / io_choff: the epilogue's activation buffers and the first channel each launch touches in them, in the order
    the epilogue expects (gates: u_0, gated_0[, u_1, gated_1]; propose: u_0[, u_1], out_0[, out_1]; res_id: residual, out;
    others: out).  flags: bit 0 (propose) also keep the blend in the fp32 tensor SF_F32_A; bits 1-3 (bias_act) activation:
-   0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity; bit 4 (bias_act) also write the output to SF_F32_OUT in fp32.          */
+   0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU(erf); bit 4 (bias_act) also write the output to SF_F32_OUT in fp32;
+   bit 5 (gates / propose at C = 64) a single gate pair / proposal (plain ConvGRU of the refinement) instead of two;
+   bit 6 (bias_act) add the per-image bias SF_F32_IMG_BIAS[image][n_out] (ASPP pooling branch).                          */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
                          const void* w_packed, int w_rows, const float* vec, int n_vec,
                          const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags);
@@ -162,6 +166,13 @@ int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n
 int sf_maxpool2(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int n_images, int H, int W, int C, void* stream);
 int sf_upsample2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream);
 int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void* dst_lo, int n_out, int C, int H, int W, void* stream);
+/* post-ODE refinement glue: ConvNeXt depthwise 7x7 conv + bias + channels-last LayerNorm (convolutions.py:327-333) on 64-channel
+   NHWC bf16 planes; ASPP image-pooling branch folded into a per-image bias of the projection conv (convolutions.py:198-240):
+   out[img][128] = proj_w[128][128] . relu(pool_w[128][64] . mean(img) + pool_b) + proj_b                              */
+int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, const float* dw_w, const float* dw_b,
+                  const float* ln_w, const float* ln_b, int n_images, int H, int W, void* stream);
+int sf_aspp_pool_bias(const void* src_hi, const void* src_lo, const float* pool_w, const float* pool_b, const float* proj_w,
+                      const float* proj_b, float* scratch, float* out, int n_images, int H, int W, void* stream);
 
 /* self-test kernels for bring-up: TMA tile dump and a single UMMA tile product */
 int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0,

@@ -12,15 +12,15 @@ LIB_PATH = os.path.join(_HERE, "libsf_b200.so")
 SF_ABI_VERSION = 1
 PREC_BF16, PREC_BF16X3 = 0, 1
 (EPI_GATES, EPI_PROPOSE, EPI_DECODE, EPI_LNGELU, EPI_MIX, EPI_BIAS_LRELU, EPI_RES_PROJ, EPI_RES_ID, EPI_SAMPLE) = range(9)
-(F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT) = range(11)
-ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE = 0, 1, 2, 3
-FLAG_KEEP_A32, FLAG_OUT32 = 1, 16
+(F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT, F32_IMG_BIAS) = range(12)
+ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE, ACT_GELU = 0, 1, 2, 3, 4
+FLAG_KEEP_A32, FLAG_OUT32, FLAG_SINGLE, FLAG_IMG_BIAS = 1, 16, 32, 64
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
 SE_ITEM_BASE = 1000
 
 
 class Chunk(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("buf", "plane", "c0", "R", "n", "nrep", "col", "wrow", "init")]
+    _fields_ = [(n, C.c_int32) for n in ("buf", "plane", "c0", "R", "n", "nrep", "col", "wrow", "init", "ox", "oy")]
 
 
 class Geometry(C.Structure):
@@ -57,6 +57,8 @@ EXPORTS = {
     "sf_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_upsample2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_cast_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_dwconv7_ln": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_aspp_pool_bias": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "sf_diag_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_umma_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -253,15 +253,20 @@ class CodecEngine:
         hi, lo = self.enc[ENC_OUT[0]].bufs[ENC_OUT[1]]
         return hi[:n], (lo[:n] if lo is not None else None)
 
-    def decode(self, path_nhwc_f32: torch.Tensor, slots_dev: torch.Tensor) -> torch.Tensor:
+    def decode(self, path_nhwc_f32: torch.Tensor, slots_dev: torch.Tensor, unpack: bool = True):
         """Recorded latent states (the ODE engine's fp32 NHWC path buffer), gathered by slot -> decoded frames
-        [n, 64, H, W] fp32 NCHW."""
+        [n, 64, H, W] fp32 NCHW; with unpack=False the engine-layout result instead: ((hi, lo) NHWC bf16 planes, fp32 NHWC),
+        views of the decoder's output buffers for the fused refinement."""
         n = slots_dev.numel()
         assert n <= self.n_dec
         z = self.dec[DEC_IN[0]].bufs[DEC_IN[1]]
         L.check(self.lib.sf_cast_nhwc_f32(path_nhwc_f32.data_ptr(), slots_dev.data_ptr(), z[0].data_ptr(), z[1].data_ptr() if z[1] is not None else None,
                                           n, 64, self.h, self.w, self._stream()), "cast")
         k = self._run(self.dec, self.dec_ops, n)
+        if not unpack:
+            self.launches += k + 1
+            hi, lo = self.dec[DEC_OUT[0]].bufs[DEC_OUT[1]]
+            return (hi[:n], lo[:n] if lo is not None else None), self.dec_out32[:n]
         out = torch.empty((n, 64, self.H, self.W), dtype=torch.float32, device=self.device)
         L.check(self.lib.sf_unpack_nhwc_f32(self.dec_out32.data_ptr(), out.data_ptr(), None, n, 64, self.H, self.W, self._stream()), "unpack")
         self.launches += k + 2

@@ -35,6 +35,7 @@ constexpr int MAX_RING = 16;
 struct ChunkK {
   int R, n, nrep, col, wrow, init, c0, img_sel;   // img_sel: 0 = sample id, 1 = the event's x image index
   int tb;                                         // taps (along dy) per B tile: 1 or R
+  int ox, oy;                                     // pixel offset of the input window (dilated taps)
 };
 
 struct EpiArgs {
@@ -55,8 +56,10 @@ struct EpiArgs {
   int in_cs[2], in_co[2];     // same for the element-wise inputs
   int n_out;      // output channels written by this launch (64 or 128)
   int kind;       // event kind (0 derivative step, 1 jump)
-  int act;        // bias_act / residual epilogues: 0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity
+  int act;        // bias_act / residual epilogues: 0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU
+  int pairs;      // gate pairs / proposals handled by this launch (2 at C = 64 in the dual cell, else 1)
   float* out32;   // optional fp32 NHWC copy of the bias_act output [image][H][W][n_out]
+  const float* img_bias;   // optional per-image bias [image][n_out] (bias_act)
 };
 
 struct alignas(64) StageParams {
@@ -132,6 +135,7 @@ __device__ __forceinline__ float activate(float x, int act) {
     case 0: return lrelu01(x);
     case 1: return tanhf(x);
     case 2: return fmaxf(x, 0.0f);
+    case 4: return gelu_erf(x);
     default: return x;
   }
 }
@@ -191,7 +195,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     // columns: pair g = [u_g (CG) | r_g (CG)]; CG = 64: two pairs (u1 r1 u2 r2) in one launch, CG = 128: one pair per launch.
     // vec = biases in column order; out[2g] = u_g, out[2g+1] = (1 - r_g) * s
 #pragma unroll 1
-    for (int g = 0; g < 128 / CG; ++g) {
+    for (int g = 0; g < e.pairs; ++g) {
       const int ucol = g * 2 * CG, rcol = ucol + CG;
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
@@ -215,7 +219,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
     // columns: proposal k = [s~_k (CG)]; CG = 64: both GRUs in one launch, CG = 128: one per launch.  vec = biases;
     // in[k] = u_k; out[k] = (1-u_k) s + u_k s~_k; the first GRU's blend is also kept in fp32 (a32) when bound.
 #pragma unroll 1
-    for (int k = 0; k < 128 / CG; ++k) {
+    for (int k = 0; k < e.pairs; ++k) {
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
         float t[16], s[16], u[16], b[16];
@@ -323,6 +327,12 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       vec16(vec, j * 16, b);
       if (c.valid) {
         const int act = e.act;
+        if (e.img_bias) {
+          float ib[16];
+          load_f32x16(e.img_bias + (size_t)c.sid * n + j * 16, ib);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) b[i] += ib[i];
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + b[i], act);
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
@@ -356,7 +366,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       vec16(vec, j * 16, b);
       if (c.valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]) + r[i];
+        for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + b[i], e.act) + r[i];
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
@@ -466,7 +476,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
           mbar_wait(a_empty0 + sa * 8, pa, p.err, 1);
           if (elect_one()) {
             mbar_expect_tx(a_full0 + sa * 8, (uint32_t)a_box_bytes(R, MT));
-            tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 - pad, y0 - pad, img);
+            tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 - pad + ck.ox, y0 - pad + ck.oy, img);
           }
           __syncwarp();
           if (++sa == (uint32_t)nA) { sa = 0; pa ^= 1; }

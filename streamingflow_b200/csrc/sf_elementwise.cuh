@@ -294,6 +294,134 @@ __global__ void __launch_bounds__(256) cast_nhwc_kernel(const float* __restrict_
   }
 }
 
+// ---- ConvNeXt front end: depthwise 7x7 conv + bias, then LayerNorm over the 64 channels (channels_last, eps 1e-6) --------
+// block = 256 threads = 32 pixels (8 wide x 4 high) x 8 channel groups of 8; the 7x7x64 filter lives in shared memory;
+// inputs come straight from global / L1 (each pixel's 16-byte group is re-read by the 49 neighbours of the tile).
+constexpr int DW_TILE_W = 8, DW_TILE_H = 4;
+template <bool X3>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                         __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl,
+                                                         const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                         const float* __restrict__ ln_w, const float* __restrict__ ln_b, int H, int W) {
+  __shared__ float wsm[49][64];            // [tap][channel]
+  for (int i = threadIdx.x; i < 49 * 64; i += 256) { const int c = i / 49, t = i % 49; wsm[t][c] = dw_w[c * 49 + t]; }   // weight [64][1][7][7]
+  __syncthreads();
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;                 // channel group, pixel in tile
+  const int x = blockIdx.x * DW_TILE_W + (pl & 7), y = blockIdx.y * DW_TILE_H + (pl >> 3), img = blockIdx.z;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  const bool inside = (x < W) && (y < H);
+  if (inside) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = dw_b[g * 8 + i];
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xx = x + kx - 3;
+        if (xx < 0 || xx >= W) continue;
+        const size_t off = (((size_t)img * H + yy) * W + xx) * 64 + g * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(sh + off);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo_f(w4[i]); f[2 * i + 1] = bf16_hi_f(w4[i]); }
+        if (X3) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sl + off);
+          const uint32_t x4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { f[2 * i] += bf16_lo_f(x4[i]); f[2 * i + 1] += bf16_hi_f(x4[i]); }
+        }
+        const float* wt = &wsm[ky * 7 + kx][g * 8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt[i], f[i], acc[i]);
+      }
+    }
+  }
+  // LayerNorm across the pixel's 64 channels = 8 consecutive lanes (two-pass, biased variance)
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s * (1.0f / 64.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float dlt = acc[i] - mean; q = fmaf(dlt, dlt, q); }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
+  if (inside) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(ln_w[g * 8 + i], (acc[i] - mean) * rstd, ln_b[g * 8 + i]);
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+    const size_t off = (((size_t)img * H + y) * W + x) * 64 + g * 8;
+    *reinterpret_cast<uint4*>(dh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (X3) {
+      uint32_t l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(o[2 * i] - bf16_lo_f(h[i]), o[2 * i + 1] - bf16_hi_f(h[i]));
+      *reinterpret_cast<uint4*>(dl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---- ASPP image pooling: per-image channel means of a 64-channel NHWC tensor (two deterministic levels), then
+// bias[img] = proj_w . relu(pool_w . mean + pool_b) + proj_b  (BatchNorms folded on the host) -------------------------------
+constexpr int POOL_PARTS = 32;
+template <bool X3>
+__global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                           float* __restrict__ partial, int hw) {   // partial [img][POOL_PARTS][64]
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3, img = blockIdx.y;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int px = blockIdx.x * 32 + pl; px < hw; px += POOL_PARTS * 32) {
+    const size_t off = ((size_t)img * hw + px) * 64 + g * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(sh + off);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(w4[i]); acc[2 * i + 1] += bf16_hi_f(w4[i]); }
+    if (X3) {
+      const uint4 u = *reinterpret_cast<const uint4*>(sl + off);
+      const uint32_t x4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(x4[i]); acc[2 * i + 1] += bf16_hi_f(x4[i]); }
+    }
+  }
+  __shared__ float red[32][65];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[pl][g * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
+    partial[((size_t)img * POOL_PARTS + blockIdx.x) * 64 + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(128) pool_bias_kernel(const float* __restrict__ partial, float inv_n, const float* __restrict__ pool_w,
+                                                        const float* __restrict__ pool_b, const float* __restrict__ proj_w,
+                                                        const float* __restrict__ proj_b, float* __restrict__ out) {
+  __shared__ float mean_s[64], v_s[128];
+  const int img = blockIdx.x, t = threadIdx.x;
+  if (t < 64) {
+    float a = 0.0f;
+    for (int k = 0; k < POOL_PARTS; ++k) a += partial[((size_t)img * POOL_PARTS + k) * 64 + t];
+    mean_s[t] = a * inv_n;
+  }
+  __syncthreads();
+  float a = pool_b[t];
+  for (int c = 0; c < 64; ++c) a = fmaf(pool_w[t * 64 + c], mean_s[c], a);
+  v_s[t] = fmaxf(a, 0.0f);
+  __syncthreads();
+  float b = proj_b[t];
+  for (int c = 0; c < 128; ++c) b = fmaf(proj_w[t * 128 + c], v_s[c], b);
+  out[(size_t)img * 128 + t] = b;
+}
+
 // ---- NHWC fp32 (recorded path states) -> NCHW fp32 (decoder input), gathered by slot ----------------------
 __global__ void __launch_bounds__(256) unpack_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                           const int* __restrict__ slots, int C, int hw) {

@@ -78,7 +78,7 @@ struct sf_plan {
   int num_sms = 148;
   bool finalized = false;
   ActBuf act[SF_MAX_ACT_BUFS];
-  void* f32[SF_F32_COUNT + 2] = {};
+  void* f32[SF_F32_COUNT + 3] = {};
   Stage stage[SF_MAX_STAGES];
   SeDef se[2];
   std::vector<int> cell[2], prior;
@@ -175,7 +175,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
     int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.epi, p->g.C), &sp.amap[c]);
     if (rc) return rc;
     if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
-    sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c]};
+    sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c], ck.ox, ck.oy};
   }
   sp.wmap = st.wmap;
   sp.H = p->g.H;
@@ -227,7 +227,8 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   for (int b : st.io)
     if (b < 0 || b >= SF_MAX_ACT_BUFS || !p->act[b].hi || (x3 && !p->act[b].lo))
       return fail(SF_ERR_STATE, "stage io buffer not bound");
-  const int pairs = 128 / p->g.C;          // gate pairs / proposals handled by one launch
+  const int pairs = (st.flags & 32) ? 1 : 128 / p->g.C;          // gate pairs / proposals handled by one launch
+  e.pairs = pairs;
   switch (st.epi) {
     case SF_EPI_GATES:                      // io = [u_0, gated_0, (u_1, gated_1)]
       if (!need_io(2 * pairs)) return fail(SF_ERR_INVALID, "gates stage needs 2 io buffers per gate pair");
@@ -257,6 +258,8 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   }
   e.act = (st.flags >> 1) & 7;                                        // bias_act activation code
   e.out32 = (st.flags & 16) ? reinterpret_cast<float*>(p->f32[SF_F32_OUT]) : nullptr;
+  e.img_bias = (st.flags & 64) ? reinterpret_cast<const float*>(p->f32[SF_F32_IMG_BIAS]) : nullptr;
+  if ((st.flags & 64) && !e.img_bias) return fail(SF_ERR_STATE, "per-image bias requested but SF_F32_IMG_BIAS is not bound");
   if ((st.flags & 16) && !e.out32) return fail(SF_ERR_STATE, "fp32 output requested but SF_F32_OUT is not bound");
   if (st.epi == SF_EPI_MIX || st.epi == SF_EPI_GATES || st.epi == SF_EPI_PROPOSE)
     if (!e.s_in || !e.s_out || !e.s_base) return fail(SF_ERR_STATE, "state buffers not bound");
@@ -426,7 +429,7 @@ int sf_plan_bind_act(sf_plan* p, int buf, void* hi, void* lo, int channels, int 
 }
 
 int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr) {
-  if (!p || slot < 0 || slot > SF_F32_COUNT + 1) return fail(SF_ERR_INVALID, "bad fp32 slot");   // COUNT = int32 error flag, COUNT+1 = SF_F32_OUT
+  if (!p || slot < 0 || slot > SF_F32_COUNT + 2) return fail(SF_ERR_INVALID, "bad fp32 slot");   // + error flag, SF_F32_OUT, SF_F32_IMG_BIAS
   p->f32[slot] = ptr;
   return SF_OK;
 }
@@ -597,6 +600,32 @@ int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dst_lo) cast_nhwc_kernel<true><<<grid, 256, 0, s>>>(src, slots, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), n_out, per);
   else cast_nhwc_kernel<false><<<grid, 256, 0, s>>>(src, slots, reinterpret_cast<__nv_bfloat16*>(dst_hi), nullptr, n_out, per);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, const float* dw_w, const float* dw_b,
+                  const float* ln_w, const float* ln_b, int n_images, int H, int W, void* stream) {
+  if (!src_hi || !dst_hi || !dw_w || !dw_b || !ln_w || !ln_b || n_images <= 0) return fail(SF_ERR_INVALID, "bad dwconv arguments");
+  dim3 grid((W + DW_TILE_W - 1) / DW_TILE_W, (H + DW_TILE_H - 1) / DW_TILE_H, n_images);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
+  auto dh = reinterpret_cast<__nv_bfloat16*>(dst_hi); auto dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
+  if (src_lo && dst_lo) dwconv7_ln_kernel<true><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
+  else dwconv7_ln_kernel<false><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_aspp_pool_bias(const void* src_hi, const void* src_lo, const float* pool_w, const float* pool_b, const float* proj_w,
+                      const float* proj_b, float* scratch, float* out, int n_images, int H, int W, void* stream) {
+  if (!src_hi || !pool_w || !pool_b || !proj_w || !proj_b || !scratch || !out || n_images <= 0) return fail(SF_ERR_INVALID, "bad pool arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
+  dim3 grid(POOL_PARTS, n_images);
+  if (src_lo) pool_partial_kernel<true><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+  else pool_partial_kernel<false><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+  pool_bias_kernel<<<n_images, 128, 0, s>>>(scratch, 1.0f / (float)(H * W), pool_w, pool_b, proj_w, proj_b, out);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

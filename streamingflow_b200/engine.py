@@ -46,13 +46,24 @@ class StageDef:
     def __init__(self, name, epilogue, vec, io, io_off=None, flags=0):
         self.name, self.epilogue, self.vec, self.io, self.flags = name, epilogue, vec, list(io), flags
         self.io_off = list(io_off) if io_off is not None else [0] * len(self.io)
-        self.chunks: List[Tuple[int, int, torch.Tensor, int, int]] = []
+        self.chunks: List[Tuple[int, int, torch.Tensor, int, int, int, int]] = []
 
-    def add(self, buf, w, col, init, c0=0):
-        """w: [n, cin, R, R] with cin a multiple of 64: one chunk per 64 input channels of buffer ``buf`` starting at c0."""
+    def add(self, buf, w, col, init, c0=0, ox=0, oy=0):
+        """w: [n, cin, R, R] with cin a multiple of 64: one chunk per 64 input channels of buffer ``buf`` starting at c0.
+        (ox, oy) shifts the chunk's input window (used for dilated taps)."""
         assert w.shape[1] % 64 == 0 and w.shape[2] == w.shape[3]
         for i in range(w.shape[1] // 64):
-            self.chunks.append((buf, c0 + 64 * i, w[:, 64 * i:64 * i + 64], col, int(init and i == 0)))
+            self.chunks.append((buf, c0 + 64 * i, w[:, 64 * i:64 * i + 64], col, int(init and i == 0), ox, oy))
+        return self
+
+    def add_dilated(self, buf, w, col, init, dilation):
+        """3x3 convolution with dilation d (padding d): nine 1x1 chunks whose windows are shifted by ((kx-1) d, (ky-1) d)."""
+        assert w.shape[2] == 3 and w.shape[3] == 3
+        first = True
+        for ky in range(3):
+            for kx in range(3):
+                self.add(buf, w[:, :, ky:ky + 1, kx:kx + 1], col, init and first, ox=(kx - 1) * dilation, oy=(ky - 1) * dilation)
+                first = False
         return self
 
 
@@ -131,21 +142,21 @@ def pack_stage(sdef: StageDef, x3: bool):
     """Packs a stage's weights into the [rows, 64] bf16 matrix the TMA weight ring streams, in consumption order:
     chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed)."""
     chunks, blocks, row = [], [], 0
-    for buf, c0, w, col, init in sdef.chunks:
+    for buf, c0, w, col, init, ox, oy in sdef.chunks:
         n, _, R, _ = w.shape
         taps = w.permute(3, 2, 0, 1).contiguous()                  # [dx, dy, n, 64]
         hi = taps.to(torch.bfloat16)
         if not x3:
-            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=init))
+            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=init, ox=ox, oy=oy))
             blocks.append(hi.reshape(-1, 64))
             row += R * R * n
         else:
             lo = (taps - hi.float()).to(torch.bfloat16)
             both = torch.stack([hi, lo], dim=2)                     # [dx, dy, rep, n, 64]
-            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=2, col=col, wrow=row, init=init))
+            chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=2, col=col, wrow=row, init=init, ox=ox, oy=oy))
             blocks.append(both.reshape(-1, 64))
             row += R * R * 2 * n
-            chunks.append(dict(buf=buf, plane=1, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=0))
+            chunks.append(dict(buf=buf, plane=1, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=0, ox=ox, oy=oy))
             blocks.append(hi.reshape(-1, 64))
             row += R * R * n
     return chunks, torch.cat(blocks, 0).contiguous()
@@ -171,6 +182,10 @@ def emulate_stage(sdef: StageDef, x3: bool, sources: Dict[int, torch.Tensor]) ->
             x = x.to(torch.bfloat16).double()
         R, n, nrep = ck["R"], ck["n"], ck["nrep"]
         pad = (R - 1) // 2
+        ox, oy = ck.get("ox", 0), ck.get("oy", 0)
+        if ox or oy:                                               # window shifted by (ox, oy), zero outside the image
+            big = F.pad(x, (abs(ox), abs(ox), abs(oy), abs(oy)))
+            x = big[:, abs(oy) + oy:abs(oy) + oy + H, abs(ox) + ox:abs(ox) + ox + W]
         xp = F.pad(x, (pad, pad, pad, pad))
         out = torch.zeros(n, H, W, dtype=torch.float64)
         for dx in range(R):

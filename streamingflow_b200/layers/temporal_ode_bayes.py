@@ -472,16 +472,19 @@ class NNFOwithBayesianJumps(nn.Module):
         x = self.srvp_decode(sel)
         return state, 0, x
 
-    def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t):
+    def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t, raw: bool = False):
         """SmallEncoder -> jump / integrate loop -> SmallDecoder entirely on the conv-stage kernels: frames [n, C, H, W] (all
-        samples' observation frames, sample-major, processing order) -> (final latent states, decoded frames [B, T, C, H, W])."""
+        samples' observation frames, sample-major, processing order) -> (final latent states, decoded frames [B, T, C, H, W]).
+        raw=True returns the decoded frames in engine layout ((hi, lo) NHWC bf16 planes, fp32 NHWC) for the fused refinement."""
         n, c, H, W = frames.shape
         B, T = len(obs_counts), len(targets[0])
         codec = self._codec_for(H, W, n, B * T, frames.device)
         planes = codec.encode(frames)
         state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True)
         slots = torch.tensor(flat, dtype=torch.int32).to(frames.device)
-        x = codec.decode(eng.path, slots).view(B, T, c, H, W)
+        x = codec.decode(eng.path, slots, unpack=not raw)
+        if not raw:
+            x = x.view(B, T, c, H, W)
         self.last_rollout.launches += codec.launches
         codec.launches = 0
         return state, x

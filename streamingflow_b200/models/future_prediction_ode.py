@@ -7,6 +7,8 @@ engine: all observation frames of all samples are encoded together, every sample
 and the samples advance event by event (rollout.py).  The result is the same as the reference's loop because
 samples are independent and the noise is drawn in the reference's sample-major order.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -30,6 +32,24 @@ class FuturePredictionODE(nn.Module):
                           else nn.Sequential(*[Block(in_channels) for _ in range(n_res_layers)]))
         self.spatial_grus = nn.ModuleList(grus)
         self.res_blocks = nn.ModuleList(blocks)
+        self.in_channels, self.n_res_layers = in_channels, n_res_layers
+        self.fused_refine = os.environ.get("SF_B200_FUSED_REFINE", "1") == "1"   # SpatialGRU / Block / DeepLabHead on the CUDA engine
+        self.__dict__["_refiners"] = {}
+
+    def _refine_for(self, H, W, B, T, device):
+        from ..refine_engine import RefineEngine
+
+        prec = self.gru_ode.precision
+        key = (str(device), H, W, B, T, prec)
+        fp = tuple((p.data_ptr(), p._version) for mod in (self.spatial_grus, self.res_blocks) for p in list(mod.parameters()) + list(mod.buffers()))
+        ent = self._refiners.get(key)
+        if ent is None or ent["fp"] != fp:
+            if len(self._refiners) >= 2:
+                self._refiners.clear()
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith(("spatial_grus", "res_blocks"))}
+            ent = dict(engine=RefineEngine(sd, H, W, B, T, prec, device), fp=fp)
+            self._refiners[key] = ent
+        return ent["engine"]
 
     @staticmethod
     def _host_times(t):
@@ -50,8 +70,19 @@ class FuturePredictionODE(nn.Module):
             times.append([t for t, _, _ in order])
         ode = self.gru_ode
         stacked = torch.stack(frames, dim=0)
-        if ode.codec_available(stacked.shape[2], stacked.shape[3], stacked.device):
-            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t)      # all three parts on the CUDA engine
+        H, W = stacked.shape[2], stacked.shape[3]
+        fused = ode.codec_available(H, W, stacked.device)
+        if fused and self.fused_refine and self.n_spatial_gru == 2 and self.n_res_layers == 1 and self.in_channels == 64:
+            # encoder -> ODE loop -> decoder -> SpatialGRU / Block / SpatialGRU / DeepLabHead, all on the CUDA engine
+            T = len(tgt_t[0])
+            _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True)
+            refine = self._refine_for(H, W, B, T, stacked.device)
+            x = refine.run(planes, x32)
+            ode.last_rollout.launches += refine.launches
+            refine.launches = 0
+            return x, 0
+        if fused:
+            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t)      # encoder / loop / decoder on the CUDA engine
         else:
             hx = ode.srvp_encoder(stacked)
             _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t)

@@ -241,7 +241,7 @@ def _interpret_codec_graph(graph, bufs_spec, x_in, in_key, out_key, dims):
         _, lvl, sdef = op
         acc = en.emulate_stage(sdef, True, {b: t.float() for b, t in bufs[lvl].items()})      # split-bf16 replay ~ fp32 accurate
         vec = sdef.vec.double()
-        n = max(c[2].shape[0] for c in sdef.chunks if c[3] == 0)
+        n = max(ck[2].shape[0] for ck in sdef.chunks if ck[3] == 0)
         if sdef.epilogue == L.EPI_BIAS_LRELU:
             v = acc[:n] + vec[:n, None, None]
             act = (sdef.flags >> 1) & 7
@@ -277,3 +277,83 @@ def test_codec_stage_graphs_reproduce_encoder_and_decoder():
         want = so.small_decoder(sd64, "g.srvp_decoder", z.double())
         got = _interpret_codec_graph(ce.decoder_graph(sd), ce.DEC_BUFS, z, ce.DEC_IN, ce.DEC_OUT, dims)
     assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
+
+
+def test_refinement_stage_graph_reproduces_reference_refinement():
+    """SpatialGRU x2 + ConvNeXt Block + DeepLabHead as conv-stage graphs (refine_engine.refine_graph), interpreted on the host,
+    == the oracle's refinement (future_prediction_ode.py:56-62)."""
+    from streamingflow_b200 import _lib as L, engine as en, refine_engine as rf
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+    import torch.nn.functional as F
+
+    m = FuturePredictionODE(64, 64, 4, make_cfg(64)).eval()
+    sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 12, 1.0)
+    g = rf.refine_graph(sd)
+    B, T, H, W = 1, 2, 48, 40
+    x = so.recipe_array("x", (B, T, 64, H, W), 12)
+    emu = lambda sdef, src: en.emulate_stage(sdef, True, {k: v.float() for k, v in src.items()})
+    sig = torch.sigmoid
+
+    def run_gru(i, frames):          # frames [T, 64, H, W]
+        gi = g[f"gru{i}"]
+        state = x[0, 0].double()
+        outs = []
+        for t in range(T):
+            xt = frames[t][None].double()
+            acc = emu(gi["gates"], {rf.R_S: state[None], -1: xt})
+            vec = gi["gates"].vec.double()
+            u = sig(acc[:64] + vec[:64, None, None])
+            r = sig(acc[64:128] + vec[64:, None, None])
+            acc = emu(gi["propose"], {-1: xt, rf.R_G: ((1 - r) * state)[None]})
+            state = (1 - u) * state + u * (acc[:64] + gi["propose"].vec.double()[:, None, None])
+            outs.append(emu(gi["dec"], {-1: state[None]})[:64])
+        return torch.stack(outs)
+
+    def run_stage(sdef, bufs, img_bias=None):
+        acc = emu(sdef, {k: v[None] for k, v in bufs.items()})
+        n = max(ck[2].shape[0] for ck in sdef.chunks if ck[3] == 0)
+        v = acc[:n] + sdef.vec.double()[:n, None, None]
+        if img_bias is not None:
+            v = v + img_bias[:, None, None]
+        act = (sdef.flags >> 1) & 7
+        v = F.gelu(v) if act == 4 else torch.relu(v) if act == 2 else v
+        if sdef.epilogue == L.EPI_RES_ID:
+            v = v + bufs[sdef.io[0]][sdef.io_off[0]:sdef.io_off[0] + n]
+            return sdef.io[1], sdef.io_off[1], v
+        return sdef.io[0], sdef.io_off[0], v
+
+    o0 = run_gru(0, x[0])
+    blk = g["block"]
+    out_frames = []
+    o1_in = []
+    for t in range(T):
+        dw = F.conv2d(o0[t][None], blk["dw_w"].double(), blk["dw_b"].double(), padding=3, groups=64)[0]
+        dw = F.layer_norm(dw.permute(1, 2, 0), (64,), blk["ln_w"].double(), blk["ln_b"].double(), 1e-6).permute(2, 0, 1)
+        bufs = {rf.R_O0: o0[t], rf.R_DW: dw, rf.R_P1: torch.zeros(256, H, W, dtype=torch.float64)}
+        for sdef in blk["stages"]:
+            dst, off, v = run_stage(sdef, bufs)
+            if dst == rf.R_P1:
+                bufs[rf.R_P1][off:off + v.shape[0]] = v
+            else:
+                bufs[dst] = v
+        o1_in.append(bufs[rf.R_BK])
+    o1 = run_gru(1, torch.stack(o1_in))
+    pl = g["pool"]
+    for t in range(T):
+        mean = o1[t].mean(dim=(1, 2))
+        vb = torch.relu(pl["pool_w"].double() @ mean + pl["pool_b"].double())
+        img_bias = pl["proj_w"].double() @ vb + pl["proj_b"].double()
+        bufs = {rf.R_O1: o1[t]}
+        for sdef in g["deeplab"]:
+            dst, off, v = run_stage(sdef, bufs, img_bias if (sdef.flags & L.FLAG_IMG_BIAS) else None)
+            bufs[dst] = v
+        out_frames.append(bufs[rf.R_OUT])
+    got = torch.stack(out_frames)[None]
+    sd64 = {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}
+    with torch.no_grad():
+        y = so.spatial_gru(sd64, "spatial_grus.0", x.double(), x[:, 0].double())
+        y = so.convnext_block(sd64, "res_blocks.0.0", y.reshape(B * T, 64, H, W)).view(B, T, 64, H, W)
+        y = so.spatial_gru(sd64, "spatial_grus.1", y, x[:, 0].double())
+        want = so.deeplab_head(sd64, "res_blocks.1", y.reshape(B * T, 64, H, W)).view(B, T, 64, H, W)
+    assert got.shape == want.shape
+    assert ((got - want).abs().max() / want.abs().max()).item() < 5e-4
