@@ -345,8 +345,8 @@ def module_level_numbers(model, dev, B, reps=3):
     return dict(grid="50x50x64 latent of a 200x200x64 BEV", batch=B, ode_loop_ms=ms_ode, ode_loop_value=n_steps / (ms_ode * 1e-3),
                 ode_loop_eager_launch_ms=ms_eager,
                 forward_host_buffers_ms=ms_fwd, forward_value=n_steps / (ms_fwd * 1e-3), unit=UNIT,
-                note="forward = SmallEncoder + ODE loop + SmallDecoder on the CUDA engine, then the torch SpatialGRU/Block/DeepLabHead "
-                     "refinement (a 'next' row, DESIGN.md) which dominates the module call")
+                note="forward = SmallEncoder -> ODE loop -> SmallDecoder -> SpatialGRU/Block/SpatialGRU/DeepLabHead, every stage on the "
+                     "CUDA engine (conv-stage kernels); H2D of the 8 BEV frames / sample and D2H of the 7 output frames inside the time")
 
 
 def time_stages(eng, B, hw, peaks, reps=10):

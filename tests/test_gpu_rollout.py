@@ -133,9 +133,10 @@ def test_module_forward_matches_oracle_at_bev_200(precision):
     assert 0.02 < frac1 < 0.98, "degenerate mask: the argmax test would be trivial"
     # a mask pixel may only differ where the two logits are closer than twice the logit error ...
     assert not bool((flips & (margin > 2 * dmax)).any())
-    # ... and on these seeds there is no such pixel in the accurate mode; the bf16 mode may flip a vanishing fraction of near-ties
+    # ... i.e. only exact near-ties: at most a couple of the 560 000 mask pixels in the accurate mode (every stage of the module,
+    # encoder to DeepLabHead, now runs on the engine), a vanishing fraction in the bf16 mode
     if precision == "bf16x3":
-        assert int(flips.sum()) == 0
+        assert int(flips.sum()) <= 2, int(flips.sum())
     else:
         assert flips.double().mean().item() < 2e-3, flips.double().mean().item()
 
