@@ -19,6 +19,8 @@
 //   pixel, so LayerNorm / softmax-mix / GRU blends are thread-local), then TMA producer (one lane), MMA issuer (one lane),
 //   TMEM allocator.  Persistent over tiles, static round-robin.
 #pragma once
+#include <type_traits>
+
 #include "sf_ptx.cuh"
 #include "../../include/sf_b200.h"
 
@@ -130,24 +132,41 @@ __device__ __forceinline__ void store_f32x16(float* p, const float (&v)[16]) {
   stg256(p, a);
   stg256(p + 8, b);
 }
-__device__ __forceinline__ float activate(float x, int act) {
-  switch (act) {
-    case 0: return lrelu01(x);
-    case 1: return tanhf(x);
-    case 2: return fmaxf(x, 0.0f);
-    case 4: return gelu_erf(x);
-    default: return x;
+// Internal epilogue ids: the bias_act / residual epilogues with a run-time activation code, an optional fp32 copy and an
+// optional per-image bias (codec and refinement stages).  The ODE loop's own stages (LeakyReLU only) use the lean
+// SF_EPI_BIAS_LRELU / SF_EPI_RES_ID instantiations; launch_stage picks the variant from the stage flags.
+constexpr int SF_EPI_BIAS_ACT = 9;
+constexpr int SF_EPI_RES_ID_ACT = 10;
+constexpr int SF_EPI_KERNELS = 11;
+
+// v = act(v + b) on a 16-channel slice; the activation code is uniform per launch, so the switch is taken once per slice
+template <bool ANYACT>
+__device__ __forceinline__ void bias_act16(float (&v)[16], const float (&b)[16], int act) {
+  if (!ANYACT || act == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = lrelu01(v[i] + b[i]);
+  } else if (act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i] + b[i]);
+  } else if (act == 2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + b[i], 0.0f);
+  } else if (act == 4) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i] + b[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] + b[i];
   }
 }
 __device__ __forceinline__ void zero16(float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.0f;
 }
-// 16 floats of the per-stage constant vector from shared memory (128-bit broadcast loads)
-__device__ __forceinline__ void vec16(const float* vec, int off, float (&v)[16]) {
-  const float4* q = reinterpret_cast<const float4*>(vec + off);
+// 16 floats of the per-stage constant vector from shared memory (128-bit broadcast LDS; vec = shared-window address)
+__device__ __forceinline__ void vec16(uint32_t vec, int off, float (&v)[16]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float4 t = q[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+  for (int i = 0; i < 4; ++i) { const float4 t = lds128(vec + (uint32_t)(off + 4 * i) * 4u); v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
 }
 
 // LayerNorm statistics over the CG accumulator columns [col, col+CG) of this thread's pixel, two passes over TMEM
@@ -187,58 +206,71 @@ struct PixelCtx {
 // All tcgen05.ld are executed by every lane (they are warp-collective); global traffic is predicated.
 // ------------------------------------------------------------------------------------------------
 template <int EPI, bool X3, int CG>
-__device__ __forceinline__ void run_epilogue(const StageParams& p, const float* vec, uint32_t taddr, const PixelCtx& c) {
+__device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c) {
   const EpiArgs& e = p.e;
   constexpr int NJ = CG / 16;                      // 16-channel slices of one CG-channel tensor
   const size_t pc = c.pix * CG;                    // this pixel in a CG-channel NHWC tensor
   if constexpr (EPI == SF_EPI_GATES) {
     // columns: pair g = [u_g (CG) | r_g (CG)]; CG = 64: two pairs (u1 r1 u2 r2) in one launch, CG = 128: one pair per launch.
     // vec = biases in column order; out[2g] = u_g, out[2g+1] = (1 - r_g) * s
-#pragma unroll 1
-    for (int g = 0; g < e.pairs; ++g) {
-      const int ucol = g * 2 * CG, rcol = ucol + CG;
+    auto body = [&](auto npairs) {
+      constexpr int NP = decltype(npairs)::value;
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
-        float u[16], r[16], s[16], bu[16], br[16];
+        float s[16];
         if (c.valid) load_f32x16(e.s_in + pc + j * 16, s); else zero16(s);
-        tmem_ld16x2(taddr + ucol + j * 16, taddr + rcol + j * 16, u, r);
-        vec16(vec, ucol + j * 16, bu);
-        vec16(vec, rcol + j * 16, br);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          u[i] = sigmoidf_(u[i] + bu[i]);
-          r[i] = (1.0f - sigmoidf_(r[i] + br[i])) * s[i];
-        }
-        if (c.valid) {
-          store_act16<X3>(e.out_h[2 * g], e.out_l[2 * g], pc + j * 16, u);
-          store_act16<X3>(e.out_h[2 * g + 1], e.out_l[2 * g + 1], pc + j * 16, r);
+        for (int g = 0; g < NP; ++g) {
+          const int ucol = g * 2 * CG, rcol = ucol + CG;
+          float u[16], r[16], bu[16], br[16];
+          tmem_ld16x2(taddr + ucol + j * 16, taddr + rcol + j * 16, u, r);
+          vec16(vec, ucol + j * 16, bu);
+          vec16(vec, rcol + j * 16, br);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            u[i] = sigmoidf_(u[i] + bu[i]);
+            r[i] = (1.0f - sigmoidf_(r[i] + br[i])) * s[i];
+          }
+          if (c.valid) {
+            store_act16<X3>(e.out_h[2 * g], e.out_l[2 * g], pc + j * 16, u);
+            store_act16<X3>(e.out_h[2 * g + 1], e.out_l[2 * g + 1], pc + j * 16, r);
+          }
         }
       }
-    }
+    };
+    if (CG == 64 && e.pairs == 2) body(std::integral_constant<int, (CG == 64 ? 2 : 1)>{}); else body(std::integral_constant<int, 1>{});
   } else if constexpr (EPI == SF_EPI_PROPOSE) {
     // columns: proposal k = [s~_k (CG)]; CG = 64: both GRUs in one launch, CG = 128: one per launch.  vec = biases;
     // in[k] = u_k; out[k] = (1-u_k) s + u_k s~_k; the first GRU's blend is also kept in fp32 (a32) when bound.
-#pragma unroll 1
-    for (int k = 0; k < e.pairs; ++k) {
+    auto body = [&](auto npairs) {
+      constexpr int NP = decltype(npairs)::value;
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
-        float t[16], s[16], u[16], b[16];
+        float s[16], u[NP][16];
         if (c.valid) {
           load_f32x16(e.s_in + pc + j * 16, s);
-          load_act16<X3>(e.in_h[k], e.in_l[k], pc + j * 16, u);
-        } else {
-          zero16(s); zero16(u);
-        }
-        tmem_ld16(taddr + k * CG + j * 16, t);
-        vec16(vec, k * CG + j * 16, b);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) t[i] = (1.0f - u[i]) * s[i] + u[i] * (t[i] + b[i]);
-        if (c.valid) {
-          if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
-          store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);
+          for (int k = 0; k < NP; ++k) load_act16<X3>(e.in_h[k], e.in_l[k], pc + j * 16, u[k]);
+        } else {
+          zero16(s);
+#pragma unroll
+          for (int k = 0; k < NP; ++k) zero16(u[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          float t[16], b[16];
+          tmem_ld16(taddr + k * CG + j * 16, t);
+          vec16(vec, k * CG + j * 16, b);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t[i] = (1.0f - u[k][i]) * s[i] + u[k][i] * (t[i] + b[i]);
+          if (c.valid) {
+            if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
+            store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);
+          }
         }
       }
-    }
+    };
+    if (CG == 64 && e.pairs == 2) body(std::integral_constant<int, (CG == 64 ? 2 : 1)>{}); else body(std::integral_constant<int, 1>{});
   } else if constexpr (EPI == SF_EPI_DECODE) {
 #pragma unroll 1
     for (int j = 0; j < NJ; ++j) {
@@ -317,7 +349,8 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
           store_f32x16(e.path + ((size_t)slot * p.H * p.W + (size_t)c.y * p.W + c.x) * CG + j * 16, o);
       }
     }
-  } else if constexpr (EPI == SF_EPI_BIAS_LRELU) {
+  } else if constexpr (EPI == SF_EPI_BIAS_LRELU || EPI == SF_EPI_BIAS_ACT) {
+    constexpr bool ANYACT = EPI == SF_EPI_BIAS_ACT;
     const int n = e.n_out;
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0];
 #pragma unroll 1
@@ -327,16 +360,15 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       vec16(vec, j * 16, b);
       if (c.valid) {
         const int act = e.act;
-        if (e.img_bias) {
+        if (ANYACT && e.img_bias) {
           float ib[16];
           load_f32x16(e.img_bias + (size_t)c.sid * n + j * 16, ib);
 #pragma unroll
           for (int i = 0; i < 16; ++i) b[i] += ib[i];
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + b[i], act);
+        bias_act16<ANYACT>(v, b, act);
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
-        if (e.out32) store_f32x16(e.out32 + c.pix * n + j * 16, v);
+        if (ANYACT && e.out32) store_f32x16(e.out32 + c.pix * n + j * 16, v);
       }
     }
   } else if constexpr (EPI == SF_EPI_RES_PROJ) {
@@ -356,7 +388,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
-  } else if constexpr (EPI == SF_EPI_RES_ID) {
+  } else if constexpr (EPI == SF_EPI_RES_ID || EPI == SF_EPI_RES_ID_ACT) {
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
 #pragma unroll 1
     for (int j = 0; j < e.n_out / 16; ++j) {
@@ -365,8 +397,9 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
       if (c.valid) {
+        bias_act16<EPI == SF_EPI_RES_ID_ACT>(v, b, e.act);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = activate(v[i] + b[i], e.act) + r[i];
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
@@ -404,6 +437,43 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, const float* 
       }
     }
   }
+}
+
+// L2 prefetch of the global operands the epilogue of pixel `pix` will read (they do not depend on the accumulator): issued one
+// tile ahead, so the epilogue's loads hit L2 instead of paying the HBM latency once per 16-channel slice.
+template <int EPI, bool X3, int CG>
+__device__ __forceinline__ void prefetch_epilogue_operands(const StageParams& p, size_t pix) {
+  const EpiArgs& e = p.e;
+  auto lines = [](const void* base, int bytes) {
+    const char* q = reinterpret_cast<const char*>(base);
+#pragma unroll
+    for (int o = 0; o < bytes; o += 128) prefetch_l2(q + o);
+  };
+  if constexpr (EPI == SF_EPI_GATES) {
+    lines(e.s_in + pix * CG, CG * 4);
+  } else if constexpr (EPI == SF_EPI_PROPOSE) {
+    lines(e.s_in + pix * CG, CG * 4);
+    for (int k = 0; k < e.pairs; ++k) {
+      lines(e.in_h[k] + pix * CG, CG * 2);
+      if (X3) lines(e.in_l[k] + pix * CG, CG * 2);
+    }
+  } else if constexpr (EPI == SF_EPI_MIX) {
+    lines(e.a32 + pix * CG, CG * 4);
+    lines(e.b32 + pix * CG, CG * 4);
+    if (e.kind == 0) {
+      lines(e.s_in + pix * CG, CG * 4);
+      if (e.s_base != e.s_in) lines(e.s_base + pix * CG, CG * 4);
+    }
+  } else if constexpr (EPI == SF_EPI_RES_ID || EPI == SF_EPI_RES_ID_ACT) {
+    const size_t i0 = pix * e.in_cs[0] + e.in_co[0];
+    for (int o = 0; o < e.n_out * 2; o += 128) {
+      prefetch_l2(reinterpret_cast<const char*>(e.in_h[0] + i0) + o);
+      if (X3) prefetch_l2(reinterpret_cast<const char*>(e.in_l[0] + i0) + o);
+    }
+  }
+}
+constexpr bool epilogue_reads_global(int epi) {
+  return epi == SF_EPI_GATES || epi == SF_EPI_PROPOSE || epi == SF_EPI_MIX || epi == SF_EPI_RES_ID || epi == SF_EPI_RES_ID_ACT;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +517,12 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t vec_addr = smem_u32(vec_s);
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, constant vector) overlapped the tail of the
+  // previous kernel in the stream; from here on we read what it wrote.  The next kernel may start its own prologue as soon as
+  // this grid's CTAs leave their SMs (its griddepcontrol.wait still waits for this whole grid to finish and flush).
+  grid_dependency_wait();
+  grid_launch_dependents();
 
   const int tpi = p.tiles_x * p.tiles_y;
   const int ntiles = p.n_active * tpi;
@@ -583,19 +659,32 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
     const int r = m >> 3, cx = m & 7;
     const uint32_t taddr = tmem_base + (uint32_t)st * STAGE_COLS + (uint32_t)mt * SLOT_COLS + ((uint32_t)(q * 32) << 16);
     uint32_t aph = 0;
-    for (int tile = blockIdx.x + st * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
-      const int bi = tile / tpi, rem = tile - bi * tpi;
+    // pixel of this thread in tile t (index into per-sample NHWC tensors), or -1 outside the image / past the last tile
+    auto pixel_of = [&](int t, PixelCtx* out) -> long long {
+      if (t >= ntiles) return -1;
+      const int bi = t / tpi, rem = t - bi * tpi;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int sid = p.sample_id[bi];
+      const int y = ty * TILE_H + r, x = (tx * MT + mt) * TILE_W + cx;
+      const bool valid = (y < p.H) && (x < p.W);
+      const size_t pix = ((size_t)sid * p.H + y) * p.W + x;
+      if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; }
+      return valid ? (long long)pix : -1;
+    };
+    if constexpr (epilogue_reads_global(EPI)) {
+      const long long p0 = pixel_of(blockIdx.x + st * gridDim.x, nullptr);
+      if (p0 >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)p0);
+    }
+    for (int tile = blockIdx.x + st * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
       PixelCtx c;
-      c.bi = bi;
-      c.sid = p.sample_id[bi];
-      c.y = ty * TILE_H + r;
-      c.x = (tx * MT + mt) * TILE_W + cx;
-      c.valid = (c.y < p.H) && (c.x < p.W);
-      c.pix = ((size_t)c.sid * p.H + c.y) * p.W + c.x;
+      pixel_of(tile, &c);
+      if constexpr (epilogue_reads_global(EPI)) {
+        const long long pn = pixel_of(tile + S * gridDim.x, nullptr);
+        if (pn >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)pn);
+      }
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
-      run_epilogue<EPI, X3, CG>(p, vec_s, taddr, c);
+      run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c);
       tc_fence_before();
       mbar_arrive(smem_u32(acc_empty + st));
     }

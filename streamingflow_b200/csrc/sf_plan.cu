@@ -2,6 +2,7 @@
 // descriptors), kernel launches and the extern "C" ABI declared in include/sf_b200.h.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -144,12 +145,20 @@ StageKernel kernel_for(int epi) {
     case SF_EPI_RES_PROJ: return conv_stage_kernel<SF_EPI_RES_PROJ, X3, CG>;
     case SF_EPI_RES_ID: return conv_stage_kernel<SF_EPI_RES_ID, X3, CG>;
     case SF_EPI_SAMPLE: return conv_stage_kernel<SF_EPI_SAMPLE, X3, CG>;
+    case SF_EPI_BIAS_ACT: return conv_stage_kernel<SF_EPI_BIAS_ACT, X3, CG>;
+    case SF_EPI_RES_ID_ACT: return conv_stage_kernel<SF_EPI_RES_ID_ACT, X3, CG>;
   }
   return nullptr;
 }
 StageKernel kernel_for(int epi, bool x3, int C) {
   if (C == 128) return x3 ? kernel_for<true, 128>(epi) : kernel_for<false, 128>(epi);
   return x3 ? kernel_for<true, 64>(epi) : kernel_for<false, 64>(epi);
+}
+
+// SF_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("SF_PDL"); return !(v && v[0] == '0'); }();
+  return on;
 }
 
 int state_act_buf(int which) { return which; }   // activation buffers 0 and 1 mirror fp32 state buffers 0 and 1
@@ -266,10 +275,28 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   if (st.epi == SF_EPI_SAMPLE && !e.eps) return fail(SF_ERR_STATE, "eps buffer not bound");
   const int ntiles = n * sp.tiles_x * sp.tiles_y;
   const int grid = ntiles < p->num_sms ? ntiles : p->num_sms;
-  StageKernel k = kernel_for(st.epi, x3, p->g.C);
+  // the ODE loop's LeakyReLU-only stages run the lean instantiations; any other activation, an fp32 copy or a per-image bias
+  // selects the general variant of the same epilogue
+  int kepi = st.epi;
+  const bool general = e.act != 0 || e.out32 || e.img_bias;
+  if (kepi == SF_EPI_BIAS_LRELU && general) kepi = SF_EPI_BIAS_ACT;
+  if (kepi == SF_EPI_RES_ID && general) kepi = SF_EPI_RES_ID_ACT;
+  StageKernel k = kernel_for(kepi, x3, p->g.C);
   if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
   void* args[] = {&sp};
-  SF_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128 + 128 * sf::ACC_STAGES * MT), args, (size_t)st.smem, stream));
+  // programmatic dependent launch: this kernel's prologue (barrier init, TMEM allocation, constant vector) may overlap the
+  // tail of the previous kernel in the stream; it executes griddepcontrol.wait before touching anything that kernel wrote
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(128 + 128 * sf::ACC_STAGES * MT);
+  cfg.dynamicSmemBytes = (size_t)st.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SF_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));
   p->last_launches += 1;
   return SF_OK;
 }
@@ -505,7 +532,7 @@ int sf_plan_finalize(sf_plan* p) {
   int max_smem = 0;
   for (const Stage& st : p->stage)
     if (st.defined && st.smem > max_smem) max_smem = st.smem;
-  for (int epi = 0; epi <= SF_EPI_SAMPLE; ++epi)
+  for (int epi = 0; epi < SF_EPI_KERNELS; ++epi)
     for (int x3 = 0; x3 < 2; ++x3)
       SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel_for(epi, x3 != 0, p->g.C)), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   p->finalized = true;

@@ -143,6 +143,19 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
                : "memory");
 }
 
+// L2 prefetch of one 128-byte line (no register result): used by the epilogue warps to pull their tile's fp32 / bf16
+// operands from HBM into L2 while the tile's MMAs are still running
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 128-bit shared-memory load through an explicit shared-window address (LDS.128 instead of a generic LD)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// programmatic dependent launch: wait for the grids this one depends on / let the next grid in the stream start its prologue
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between 8-row
 // groups | version=1 [46,48) | base_offset=0 [49,52) | layout=SWIZZLE_128B(2) [61,64).
