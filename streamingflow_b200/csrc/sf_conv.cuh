@@ -526,6 +526,17 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
 
   const int tpi = p.tiles_x * p.tiles_y;
   const int ntiles = p.n_active * tpi;
+  // Work items.  Full waves of whole tiles first; when the last, partial wave would leave more than half of the CTAs idle, its
+  // tiles are split into single M-tiles (half tiles) so that the tail costs half a tile time instead of a whole one.
+  // item w < n_whole: tile w, all M-tiles; else tile n_whole + (w - n_whole) / MT, M-tile (w - n_whole) % MT only.
+  const int n_whole = (MT > 1 && 2 * (ntiles % (int)gridDim.x) <= (int)gridDim.x) ? ntiles - ntiles % (int)gridDim.x : ntiles;
+  const int nwork = n_whole + (ntiles - n_whole) * MT;
+  auto work_tile = [&](int w, uint32_t& mtmask) -> int {
+    if (w < n_whole) { mtmask = (1u << MT) - 1u; return w; }
+    const int h = w - n_whole;
+    mtmask = 1u << (h % MT);
+    return n_whole + h / MT;
+  };
   const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
   const uint32_t a_smem0 = smem_u32(a_base), b_smem0 = smem_u32(b_base);
 
@@ -539,7 +550,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
         tma_prefetch_desc(&p.wmap);
       }
       uint32_t sa = 0, pa = 1, sb = 0, pb = 1;      // slot index and the parity to wait for on the EMPTY barrier
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        uint32_t mtmask;
+        const int tile = work_tile(w, mtmask);
         const int bi = tile / tpi, rem = tile - bi * tpi;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * TILE_H, x0 = tx * TILE_W * MT;
@@ -585,7 +598,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
     {
       // ===================== MMA issuer (converged warp, one elected lane issues) =====================
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 1;   // parities to wait for on the FULL barriers / acc EMPTY
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        uint32_t mtmask;
+        const int tile = work_tile(w, mtmask);
         const int rem = tile % tpi;
         mbar_wait(smem_u32(acc_empty + as), pacc, p.err, 3);
         tc_fence_after();
@@ -625,6 +640,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
                     for (uint32_t k = 0; k < 4; ++k) {
 #pragma unroll
                       for (int mt = 0; mt < MT; ++mt) {
+                        if (MT > 1 && !((mtmask >> mt) & 1u)) continue;     // half tile: the other M-tile belongs to another CTA
                         umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_lo + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
                                   ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc, acc | (k > 0 ? 1u : 0u));
                       }
@@ -660,8 +676,11 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
     const uint32_t taddr = tmem_base + (uint32_t)st * STAGE_COLS + (uint32_t)mt * SLOT_COLS + ((uint32_t)(q * 32) << 16);
     uint32_t aph = 0;
     // pixel of this thread in tile t (index into per-sample NHWC tensors), or -1 outside the image / past the last tile
-    auto pixel_of = [&](int t, PixelCtx* out) -> long long {
-      if (t >= ntiles) return -1;
+    auto pixel_of = [&](int w, PixelCtx* out) -> long long {
+      if (w >= nwork) return -1;
+      uint32_t mtmask;
+      const int t = work_tile(w, mtmask);
+      if (!((mtmask >> mt) & 1u)) return -2;      // half tile owned by the other M-tile's warpgroup: nothing to do here
       const int bi = t / tpi, rem = t - bi * tpi;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int sid = p.sample_id[bi];
@@ -675,16 +694,16 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       const long long p0 = pixel_of(blockIdx.x + st * gridDim.x, nullptr);
       if (p0 >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)p0);
     }
-    for (int tile = blockIdx.x + st * gridDim.x; tile < ntiles; tile += S * gridDim.x, aph ^= 1) {
+    for (int w = blockIdx.x + st * gridDim.x; w < nwork; w += S * gridDim.x, aph ^= 1) {
       PixelCtx c;
-      pixel_of(tile, &c);
+      const bool mine = pixel_of(w, &c) != -2;
       if constexpr (epilogue_reads_global(EPI)) {
-        const long long pn = pixel_of(tile + S * gridDim.x, nullptr);
+        const long long pn = pixel_of(w + S * gridDim.x, nullptr);
         if (pn >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)pn);
       }
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
-      run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c);
+      if (mine) run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c);
       tc_fence_before();
       mbar_arrive(smem_u32(acc_empty + st));
     }

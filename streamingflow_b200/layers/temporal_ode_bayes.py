@@ -341,9 +341,9 @@ class NNFOwithBayesianJumps(nn.Module):
         return eng.unpack_f32(eng.state32[0], B), sel
 
     def _graph_rollout(self, eng, ro, hx_obs, flat, B, T):
-        """The whole step loop as ONE CUDA graph (north star): layout pack, noise draws (torch's graph-safe Philox state, so the
-        stream stays identical to eager mode), every stage launch and the output gather are captured once per (engine,
-        schedule, shapes) and replayed; only the observation copy into the graph's static input is issued per call."""
+        """The whole step loop as ONE CUDA graph (north star): noise draws (torch's graph-safe Philox state, so the stream stays
+        identical to eager mode) and every stage launch are captured once per (engine, schedule, shapes) and replayed; the
+        layout pack of the caller's observations and the gather of the selected states run eagerly around the replay."""
         _, c, h, w = hx_obs.shape
         sig = (id(eng), eng.max_images, tuple(hx_obs.shape), self.noise, self.noise_skip, eng.precision,
                tuple((e["kind"], e["x_buf"], e["s_in"], e["s_base"], e["s_out"], e["run_prior"], tuple(e["samples"]), tuple(e["x_img"]),
@@ -353,8 +353,12 @@ class NNFOwithBayesianJumps(nn.Module):
             if len(self._graphs) >= 8:
                 self._graphs.clear()
             dev = hx_obs.device
-            static_hx = hx_obs.clone()
-            eng.bind_observations(static_hx)            # allocations happen here, outside the capture
+            obs_before = eng.act[3][0].data_ptr() if 3 in eng.act else None
+            eng.reserve_observations(hx_obs.shape[0])   # allocations happen here, outside the capture
+            if obs_before is not None and eng.act[3][0].data_ptr() != obs_before:
+                # the observation buffer moved: graphs captured on this engine hold its old address
+                for k in [k for k in self._graphs if k[0] == id(eng)]:
+                    del self._graphs[k]
             eng.ensure_path_slots(ro.n_path)
             table, evs = eng.build_table(ro.events)
             tdev = eng.upload_table(table)
@@ -363,23 +367,22 @@ class NNFOwithBayesianJumps(nn.Module):
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                eng.pack_into(3, static_hx)
                 eng.zero_state(0)
                 self.noise_skip = skip
                 eps = self._draw_noise(ro.n_eps, h, w, dev)
                 eng.bind_eps(eps)
                 n_launch = eng.run_events(evs, tdev)
-                sel = eng.unpack_path(slots_dev)
-                final = eng.unpack_f32(eng.state32[0], B)
-            ent = dict(graph=graph, hx=static_hx, eps=eps, sel=sel, final=final, keep=(tdev, slots_dev, evs), launches=n_launch)
+            ent = dict(graph=graph, eps=eps, slots=slots_dev, keep=(tdev, evs), launches=n_launch)
             self._graphs[sig] = ent
             self.noise_skip = 0
         else:
-            ent["hx"].copy_(hx_obs)
             eng.bind_eps(ent["eps"])
+        # the layout pack reads the caller's tensor and the gathers write fresh output tensors: both stay outside the graph, so
+        # no staging copy of the observations and no clone of the results is needed around the replay
+        eng.pack_into(3, hx_obs)
         ent["graph"].replay()
         ro.launches = ent["launches"]
-        return ent["final"].clone(), ent["sel"].clone().view(B, T, c, h, w)
+        return eng.unpack_f32(eng.state32[0], B), eng.unpack_path(ent["slots"]).view(B, T, c, h, w)
 
     def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None):
         """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final
