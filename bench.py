@@ -374,9 +374,11 @@ def time_stages(eng, B, hw, peaks, reps=10):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
         if name.startswith("se"):
-            # squeeze-excite pair (reduce + apply): reads z twice, writes y once, 128 ch bf16 -> 768 B / pixel
-            gbs = 768.0 * hw * hw * n / (ms * 1e-3) / 1e9
-            out[name] = dict(ms_per_event=ms, gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm"])
+            # squeeze-excite layer, 128 channels bf16.  Folded (default): ONE streaming pass, the channel-sum reduce reads z once
+            # (256 B / pixel), then the tiny scale + weight-fold kernels.  Unfolded: reduce + apply read z twice and write y.
+            bytes_px = 256.0 if eng.se_fold else 768.0
+            gbs = bytes_px * hw * hw * n / (ms * 1e-3) / 1e9
+            out[name] = dict(ms_per_event=ms, gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm"], bytes_per_pixel=bytes_px)
             continue
         flops = 2.0 * STAGE_MACS[name] * hw * hw * n
         out[name] = dict(ms_per_event=ms, tflops=flops / (ms * 1e-3) / 1e12, frac_of_bf16_peak=flops / (ms * 1e-3) / 1e12 / peaks["bf16"])

@@ -133,12 +133,22 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
    others: out).  flags: bit 0 (propose) also keep the blend in the fp32 tensor SF_F32_A; bits 1-3 (bias_act) activation:
    0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU(erf); bit 4 (bias_act) also write the output to SF_F32_OUT in fp32;
    bit 5 (gates / propose at C = 64) a single gate pair / proposal (plain ConvGRU of the refinement) instead of two;
-   bit 6 (bias_act) add the per-image bias SF_F32_IMG_BIAS[image][n_out] (ASPP pooling branch).                          */
+   bit 6 (bias_act) add the per-image bias SF_F32_IMG_BIAS[image][n_out] (ASPP pooling branch);
+   bit 7 (res_id) the residual input is multiplied by the per-sample channel scales of SE layer (flags >> 8) & 1 (the SE
+   layer was folded into its consumers, see sf_plan_define_stage_fold).                                                  */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
                          const void* w_packed, int w_rows, const float* vec, int n_vec,
                          const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags);
 /* SE layer weights (fp32 device): fc1 [2C/8][2C], fc2 [2C][2C/8] for the two SE layers */
 int sf_plan_define_se(sf_plan* p, int which, const float* fc1, const float* fc2, int in_buf, int out_buf);
+/* Folds SE layer `which_se` (res_models.py:150-165, y = z * scale[sample][channel]) into a stage that convolves y: once per
+   event the K (input-channel) columns of the stage's weights are multiplied by the sample's scales, and the stage then reads z
+   itself with its sample's weights -- the [image][H][W][2C] tensor is not re-read and re-written just to be scaled.
+   w32: fp32 master of the packed matrix, [w_rows][64] in the packed row order (every row carries the unsplit fp32 weights);
+   row_meta[w_rows]: bits 0-15 first channel of the row's chunk in the SE layer's channel space, bit 16 set for the residual
+   ("lo") rows of the split mode; w_scaled: bf16 scratch [max_images][w_rows][64] the stage streams instead of w_packed.
+   Event-graph item 2000 + which = SE reduce + scales + weight fold (no activation pass); 1000 + which = reduce + apply.  */
+int sf_plan_define_stage_fold(sf_plan* p, int stage, int which_se, const float* w32, const int32_t* row_meta, void* w_scaled);
 /* stage slots used by an event: cell stages for kind 0 / kind 1, then the prior-network stages */
 int sf_plan_define_event_graph(sf_plan* p, const int32_t* cell0, const int32_t* cell1, int n_cell,
                                const int32_t* prior, int n_prior);

@@ -14,9 +14,10 @@ PREC_BF16, PREC_BF16X3 = 0, 1
 (EPI_GATES, EPI_PROPOSE, EPI_DECODE, EPI_LNGELU, EPI_MIX, EPI_BIAS_LRELU, EPI_RES_PROJ, EPI_RES_ID, EPI_SAMPLE) = range(9)
 (F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT, F32_IMG_BIAS) = range(12)
 ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE, ACT_GELU = 0, 1, 2, 3, 4
-FLAG_KEEP_A32, FLAG_OUT32, FLAG_SINGLE, FLAG_IMG_BIAS = 1, 16, 32, 64
+FLAG_KEEP_A32, FLAG_OUT32, FLAG_SINGLE, FLAG_IMG_BIAS, FLAG_RES_SE_SCALE = 1, 16, 32, 64, 128   # bit 8: which SE layer scales the residual
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
-SE_ITEM_BASE = 1000
+SE_ITEM_BASE = 1000          # event-graph item: SE reduce + apply (activation pass)
+SE_FOLD_ITEM_BASE = 2000     # event-graph item: SE reduce + scales folded into the consumers' weights
 
 
 class Chunk(C.Structure):
@@ -42,6 +43,7 @@ EXPORTS = {
     "sf_plan_bind_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sf_plan_define_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Chunk), C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int]),
+    "sf_plan_define_stage_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sf_plan_define_se": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "sf_plan_define_event_graph": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
                                              C.POINTER(C.c_int32), C.c_int]),

@@ -60,6 +60,8 @@ struct EpiArgs {
   int kind;       // event kind (0 derivative step, 1 jump)
   int act;        // bias_act / residual epilogues: 0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU
   int pairs;      // gate pairs / proposals handled by this launch (2 at C = 64 in the dual cell, else 1)
+  const float* res_scale;  // optional SE scales [active sample][res_scale_ch] multiplied into the residual input (res_id)
+  int res_scale_ch;
   float* out32;   // optional fp32 NHWC copy of the bias_act output [image][H][W][n_out]
   const float* img_bias;   // optional per-image bias [image][n_out] (bias_act)
 };
@@ -78,6 +80,7 @@ struct alignas(64) StageParams {
   const float* vec;
   int nvec;
   int a_slot_bytes, b_slot_bytes, nA, nB;
+  int w_rows_per_sample;     // > 0: per-sample weights (SE layer folded in): active sample bi reads rows [bi * this, (bi+1) * this)
   int* err;
   EpiArgs e;
 };
@@ -394,6 +397,11 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec,
     for (int j = 0; j < e.n_out / 16; ++j) {
       float v[16], r[16], b[16];
       if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], i0 + j * 16, r); else zero16(r);
+      if (e.res_scale) {             // residual = SE output: z * scale[sample][channel] (SE layer folded into its consumers)
+        const float4* sc = reinterpret_cast<const float4*>(e.res_scale + (size_t)c.bi * e.res_scale_ch + e.in_co[0] + j * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 t = __ldg(sc + i); r[4 * i] *= t.x; r[4 * i + 1] *= t.y; r[4 * i + 2] *= t.z; r[4 * i + 3] *= t.w; }
+      }
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
       if (c.valid) {
@@ -580,7 +588,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
               mbar_wait(b_empty0 + sb * 8, pb, p.err, 2);
               if (elect_one()) {
                 mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
-                int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows;
+                int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows + bi * p.w_rows_per_sample;
                 uint32_t dst = b_smem0 + sb * p.b_slot_bytes;
                 for (int q = 0; q < grp_rows; q += 64, row += 64, dst += 64 * ROW_BYTES)
                   tma_load_2d(dst, &p.wmap, b_full0 + sb * 8, 0, row);

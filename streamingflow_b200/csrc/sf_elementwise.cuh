@@ -172,6 +172,30 @@ __global__ void __launch_bounds__(256) se_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ---- SE layer folded into a consumer's weights: w_scaled[sample][row][k] = bf16(w32[row][k] * scale[sample][c0(row) + k]) ---
+// (residual rows of the split mode get the rounding residual of that product).  One thread = 8 input channels of one row.
+__global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ w32, const int32_t* __restrict__ row_meta,
+                                                      const float* __restrict__ scale, __nv_bfloat16* __restrict__ out, int rows, int CH) {
+  const int bi = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int row = idx >> 3, g = idx & 7;
+  if (row >= rows) return;
+  const int meta = row_meta[row];
+  const int c0 = meta & 0xffff;
+  const bool lo = (meta >> 16) & 1;
+  const float4* wp = reinterpret_cast<const float4*>(w32 + (size_t)row * 64 + g * 8);
+  const float4* sp = reinterpret_cast<const float4*>(scale + (size_t)bi * CH + c0 + g * 8);
+  const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = sp[0], s1 = sp[1];
+  const float v[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (lo) h[i] = pack_bf16x2(v[2 * i] - bf16_lo_f(h[i]), v[2 * i + 1] - bf16_hi_f(h[i]));
+  }
+  *reinterpret_cast<uint4*>(out + ((size_t)bi * rows + row) * 64 + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+}
+
 // ---- NCHW fp32 -> NHWC bf16 (hi [+ lo]) : encoded observations entering the ODE loop ---------------------
 // block = 256 threads handles 32 consecutive pixels x 64 channels of one image through a padded smem tile.
 template <bool X3>

@@ -60,6 +60,11 @@ struct Stage {
   CUtensorMap wmap;
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
   std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
+  // SE layer folded into this stage's weights (sf_plan_define_stage_fold)
+  int fold_se = -1;
+  const float* w32 = nullptr;
+  const int32_t* row_meta = nullptr;
+  void* w_scaled = nullptr;
 };
 struct SeDef {
   bool defined = false;
@@ -170,6 +175,8 @@ int resolve_buf(const sf_event* ev, int buf) {
   return buf;
 }
 
+float* se_scale_ptr(sf_plan* p, int which);
+
 int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
   if (sidx < 0 || sidx >= SF_MAX_STAGES || !p->stage[sidx].defined) return fail(SF_ERR_STATE, "stage not defined");
   if (ev->n_active <= 0) return SF_OK;
@@ -206,6 +213,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.b_slot_bytes = st.b_slot;
   sp.nA = st.nA;
   sp.nB = st.nB;
+  sp.w_rows_per_sample = st.fold_se >= 0 ? st.w_rows : 0;
   sp.err = reinterpret_cast<int*>(p->f32[SF_F32_COUNT]);
   EpiArgs& e = sp.e;
   e.kind = ev->kind;
@@ -268,6 +276,12 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   e.act = (st.flags >> 1) & 7;                                        // bias_act activation code
   e.out32 = (st.flags & 16) ? reinterpret_cast<float*>(p->f32[SF_F32_OUT]) : nullptr;
   e.img_bias = (st.flags & 64) ? reinterpret_cast<const float*>(p->f32[SF_F32_IMG_BIAS]) : nullptr;
+  e.res_scale = nullptr;
+  if (st.flags & 128) {
+    if (!p->f32[SF_F32_SE_SUMS]) return fail(SF_ERR_STATE, "SE scratch not bound");
+    e.res_scale = se_scale_ptr(p, (st.flags >> 8) & 1);
+    e.res_scale_ch = 2 * p->g.C;
+  }
   if ((st.flags & 64) && !e.img_bias) return fail(SF_ERR_STATE, "per-image bias requested but SF_F32_IMG_BIAS is not bound");
   if ((st.flags & 16) && !e.out32) return fail(SF_ERR_STATE, "fp32 output requested but SF_F32_OUT is not bound");
   if (st.epi == SF_EPI_MIX || st.epi == SF_EPI_GATES || st.epi == SF_EPI_PROPOSE)
@@ -392,6 +406,24 @@ int launch_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* ta
   return SF_OK;
 }
 
+// SE layer folded into its consumers: reduce + scales (last block of the reduce), then the scaled per-sample weights of every
+// stage registered for this layer.  No pass over the activation tensor.
+int launch_se_fold(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  if (ev->n_active <= 0) return SF_OK;
+  const int hw = p->g.H * p->g.W;
+  int n = launch_se_reduce(p, which, ev, table, 0, hw, true, stream);
+  if (n < 0) return n;
+  for (Stage& st : p->stage) {
+    if (!st.defined || st.fold_se != which) continue;
+    dim3 grid((st.w_rows * 8 + 255) / 256, ev->n_active);
+    se_fold_kernel<<<grid, 256, 0, stream>>>(st.w32, st.row_meta, se_scale_ptr(p, which), reinterpret_cast<__nv_bfloat16*>(st.w_scaled),
+                                             st.w_rows, 2 * p->g.C);
+    SF_CUDA(cudaGetLastError());
+    p->last_launches += 1;
+  }
+  return SF_OK;
+}
+
 int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
   if (ev->n_active <= 0) return SF_OK;
   const int hw = p->g.H * p->g.W;
@@ -401,6 +433,7 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
 }
 
 int run_item(sf_plan* p, int item, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
+  if (item >= 2000) return launch_se_fold(p, item - 2000, ev, table, stream);
   if (item >= 1000) return launch_se(p, item - 1000, ev, table, stream);
   return launch_stage(p, item, ev, table, stream);
 }
@@ -511,6 +544,18 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.defined = true;
   p->finalized = false;
   return SF_OK;
+}
+
+int sf_plan_define_stage_fold(sf_plan* p, int stage, int which_se, const float* w32, const int32_t* row_meta, void* w_scaled) {
+  if (!p || stage < 0 || stage >= SF_MAX_STAGES || !p->stage[stage].defined) return fail(SF_ERR_INVALID, "bad stage");
+  if (which_se < 0 || which_se > 1 || !w32 || !row_meta || !w_scaled) return fail(SF_ERR_INVALID, "bad fold arguments");
+  Stage& st = p->stage[stage];
+  st.fold_se = which_se;
+  st.w32 = w32;
+  st.row_meta = row_meta;
+  st.w_scaled = w_scaled;
+  // the stage streams its sample's rows of the scaled copy: one weight map over [max_images * w_rows][64]
+  return encode_weight_map(w_scaled, st.w_rows * p->g.max_images, &st.wmap);
 }
 
 int sf_plan_define_se(sf_plan* p, int which, const float* fc1, const float* fc2, int in_buf, int out_buf) {

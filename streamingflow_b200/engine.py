@@ -47,6 +47,7 @@ class StageDef:
         self.name, self.epilogue, self.vec, self.io, self.flags = name, epilogue, vec, list(io), flags
         self.io_off = list(io_off) if io_off is not None else [0] * len(self.io)
         self.chunks: List[Tuple[int, int, torch.Tensor, int, int, int, int]] = []
+        self.fold_se: Optional[int] = None      # SE layer whose per-sample scales are folded into this stage's weights
 
     def add(self, buf, w, col, init, c0=0, ox=0, oy=0):
         """w: [n, cin, R, R] with cin a multiple of 64: one chunk per 64 input channels of buffer ``buf`` starting at c0.
@@ -109,9 +110,13 @@ def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
     return out
 
 
-def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[object]:
+def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str, fold_se: bool = False) -> List[object]:
     """p_model = ConvNet(C, 2C) with BatchNorm folded (res_models.py:168-180), as a list of StageDefs and the two SE markers
-    'se0' / 'se1'.  Outputs wider than 128 channels are produced 128 channels per launch."""
+    'se0' / 'se1'.  Outputs wider than 128 channels are produced 128 channels per launch.
+
+    fold_se: the SE layers (res_models.py:150-165) are not applied to the activation tensors; their per-sample channel scales
+    are folded into the weights of the convs that consume them (q3, q5) and into q4's residual, which then read z itself."""
+    Y1, Y2 = (BUF_Z1, BUF_Z2) if fold_se else (BUF_Y1, BUF_Y2)
     m = p + ".model."
     w1, b1 = _bn_fold(sd, m + "0.layers.conv_1")
     w2, b2 = _bn_fold(sd, m + "0.layers.conv_2")
@@ -129,13 +134,37 @@ def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[object]:
     w4, b4 = _bn_fold(sd, m + "2.layers.conv_2")
     for h in range(halves):
         r = slice(128 * h, 128 * h + 128)
-        items.append(StageDef(f"q3{'ab'[h] if halves > 1 else ''}", L.EPI_BIAS_LRELU, b3[r], [BUF_Q3], [128 * h]).add(BUF_Y1, w3[r], 0, 1))
+        items.append(StageDef(f"q3{'ab'[h] if halves > 1 else ''}", L.EPI_BIAS_LRELU, b3[r], [BUF_Q3], [128 * h]).add(Y1, w3[r], 0, 1))
+        items[-1].fold_se = 0 if fold_se else None
     for h in range(halves):
         r = slice(128 * h, 128 * h + 128)
-        items.append(StageDef(f"q4{'ab'[h] if halves > 1 else ''}", L.EPI_RES_ID, b4[r], [BUF_Y1, BUF_Z2], [128 * h, 128 * h]).add(BUF_Q3, w4[r], 0, 1))
+        items.append(StageDef(f"q4{'ab'[h] if halves > 1 else ''}", L.EPI_RES_ID, b4[r], [Y1, BUF_Z2], [128 * h, 128 * h],
+                              flags=L.FLAG_RES_SE_SCALE if fold_se else 0).add(BUF_Q3, w4[r], 0, 1))
     items.append("se1")
-    items.append(StageDef("q5", L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(BUF_Y2, sd[m + "4.conv.weight"].float(), 0, 1))
+    items.append(StageDef("q5", L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(Y2, sd[m + "4.conv.weight"].float(), 0, 1))
+    items[-1].fold_se = 1 if fold_se else None
     return items
+
+
+def pack_stage_master(sdef: StageDef, x3: bool):
+    """fp32 master of pack_stage's matrix for a stage whose weights get an SE layer folded in: the same rows in the same order,
+    every row holding the UNSPLIT fp32 weights, plus per-row metadata (bits 0-15: the chunk's first channel = the offset into
+    the SE scale vector; bit 16: residual row of the split mode).  se_fold_kernel turns it into per-sample bf16 weights."""
+    blocks, meta = [], []
+    for buf, c0, w, col, init, ox, oy in sdef.chunks:
+        n, _, R, _ = w.shape
+        taps = w.permute(3, 2, 0, 1).contiguous().float()           # [dx, dy, n, 64]
+        if not x3:
+            blocks.append(taps.reshape(-1, 64))
+            meta.append(torch.full((R * R * n,), c0, dtype=torch.int32))
+        else:
+            blocks.append(torch.stack([taps, taps], dim=2).reshape(-1, 64))      # [dx, dy, rep (hi, lo), n, 64]
+            m = torch.full((R, R, 2, n), c0, dtype=torch.int32)
+            m[:, :, 1] |= 1 << 16
+            meta.append(m.reshape(-1))
+            blocks.append(taps.reshape(-1, 64))                                   # lo-plane chunk: hi weights
+            meta.append(torch.full((R * R * n,), c0, dtype=torch.int32))
+    return torch.cat(blocks, 0).contiguous(), torch.cat(meta, 0).contiguous()
 
 
 def pack_stage(sdef: StageDef, x3: bool):
@@ -205,8 +234,11 @@ class OdeEngine:
     """One plan + workspace for a fixed (max_images, H, W, precision) on one CUDA device."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, H: int, W: int, max_images: int, precision: str = "bf16",
-                 device: Optional[torch.device] = None, path_slots: int = 0):
+                 device: Optional[torch.device] = None, path_slots: int = 0, se_fold: bool = True):
+        """se_fold: fold the two SE layers of p_model into their consumers' weights (default).  False keeps the separate
+        reduce / apply kernels -- required when the channel sums are all-reduced across GPUs in between (row sharding)."""
         self.lib = L.load()
+        self.se_fold = bool(se_fold)
         dev = torch.device(device if device is not None else "cuda")
         if dev.type != "cuda":
             raise L.SfError("the ODE engine runs on a CUDA (B200) device only; there is no CPU path")
@@ -249,6 +281,8 @@ class OdeEngine:
     def _alloc_workspace(self, path_slots):
         B, H, W, Cc = self.max_images, self.H, self.W, self.C
         for buf, mult in _BUF_CHANNELS.items():
+            if self.se_fold and buf in (BUF_Y1, BUF_Y2):
+                continue                              # SE outputs are never materialised when the layers are folded
             self._new_act(buf, B, Cc * mult)
         self._new_act(BUF_ZERO, 1, Cc)
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
@@ -296,9 +330,9 @@ class OdeEngine:
                 if ws == 0:
                     self.stage_names[slot] = sdef.name
         prior_items, slot = [], 2 * n_cell
-        for it in prior_stage_defs(sd, pre + "p_model"):
+        for it in prior_stage_defs(sd, pre + "p_model", fold_se=self.se_fold):
             if isinstance(it, str):
-                prior_items.append(L.SE_ITEM_BASE + int(it[2]))
+                prior_items.append((L.SE_FOLD_ITEM_BASE if self.se_fold else L.SE_ITEM_BASE) + int(it[2]))
                 self.stage_names[prior_items[-1]] = "se" + str(int(it[2]) + 1)
             else:
                 self.stage_defs[slot] = it
@@ -316,6 +350,14 @@ class OdeEngine:
             L.check(self.lib.sf_plan_define_stage(self.plan, slot, sdef.epilogue, len(chunks), arr, wp.data_ptr(), wp.shape[0],
                                                   vec.data_ptr(), vec.numel(), io, io_off, len(sdef.io), sdef.flags),
                     f"sf_plan_define_stage({slot}:{sdef.name})")
+            if sdef.fold_se is not None:
+                w32, meta = pack_stage_master(sdef, self.x3)
+                assert w32.shape[0] == wp.shape[0]
+                w32, meta = w32.to(self.device), meta.to(self.device)
+                scaled = torch.zeros((self.max_images, wp.shape[0], 64), dtype=torch.bfloat16, device=self.device)
+                self._keep += [w32, meta, scaled]
+                L.check(self.lib.sf_plan_define_stage_fold(self.plan, slot, sdef.fold_se, w32.data_ptr(), meta.data_ptr(), scaled.data_ptr()),
+                        f"sf_plan_define_stage_fold({slot}:{sdef.name})")
         for which, (idx, zin, yout) in enumerate(((1, BUF_Z1, BUF_Y1), (3, BUF_Z2, BUF_Y2))):
             fc1 = sd[f"{pre}p_model.model.{idx}.fc.0.weight"].float().contiguous()
             fc2 = sd[f"{pre}p_model.model.{idx}.fc.2.weight"].float().contiguous()

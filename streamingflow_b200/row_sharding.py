@@ -92,7 +92,8 @@ class RowShardedOde:
         dev = next(ode.parameters()).device
         if ode.training:
             raise L.SfError("eval mode only")
-        self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev)
+        # the SE channel sums are all-reduced across the ranks between reduce and apply: keep the two-kernel SE layers
+        self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev, se_fold=False)
         self.device = dev
         self.launches = 0
 

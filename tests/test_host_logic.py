@@ -117,6 +117,37 @@ def test_packed_stage_plans_reproduce_the_convolutions(x3):
     assert (F.conv2d(src[en.BUF_Q3], w4, b4, padding=1) - bn).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("x3", [False, True])
+def test_se_fold_master_matches_packing_of_scaled_weights(x3):
+    """SE layer folded into a consumer: se_fold_kernel's arithmetic (fp32 master row x scale[c0 + k] -> bf16, residual rows get the
+    rounding residual) replayed on the host equals pack_stage of the conv whose input channels were scaled."""
+    from streamingflow_b200 import engine as en
+
+    torch.manual_seed(3)
+    sd = so.recipe_state_dict(nnfo_shapes(64), 7, 1.0, torch.float32)
+    prior = en.prior_stage_defs(sd, "p_model", fold_se=True)
+    q3, q4, q5 = prior[3], prior[4], prior[6]
+    assert q3.name == "q3" and q3.fold_se == 0 and q5.fold_se == 1 and q4.fold_se is None
+    assert q3.chunks[0][0] == en.BUF_Z1 and q5.chunks[0][0] == en.BUF_Z2 and q4.io[0] == en.BUF_Z1 and q4.flags & 128
+    scale = torch.rand(128) + 0.25
+    for sdef in (q3, q5):
+        w32, meta = en.pack_stage_master(sdef, x3)
+        chunks, wp = en.pack_stage(sdef, x3)
+        assert w32.shape == wp.shape and meta.shape[0] == wp.shape[0]
+        c0 = (meta & 0xffff).long()
+        v = w32 * scale[c0[:, None] + torch.arange(64)[None, :]]
+        hi = v.to(torch.bfloat16)
+        folded = torch.where(((meta >> 16) & 1).bool()[:, None], (v - hi.float()).to(torch.bfloat16), hi)
+        scaled = en.StageDef(sdef.name, sdef.epilogue, sdef.vec, sdef.io)
+        for buf, cc, w, col, init, ox, oy in sdef.chunks:
+            scaled.chunks.append((buf, cc, w * scale[cc:cc + 64][None, :, None, None], col, init, ox, oy))
+        _, want = en.pack_stage(scaled, x3)
+        assert torch.equal(folded.view(torch.int16), want.view(torch.int16))
+    # without the fold the stages read the materialised SE outputs
+    plain = en.prior_stage_defs(sd, "p_model")
+    assert plain[3].chunks[0][0] == en.BUF_Y1 and plain[6].chunks[0][0] == en.BUF_Y2 and plain[3].fold_se is None
+
+
 def _tiny_module(z, dtype):
     from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
 
