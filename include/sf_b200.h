@@ -171,6 +171,17 @@ int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* t
 /* layout kernels (HBM-bound, 128-bit vectorised) */
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);
 int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n_out, int C, int H, int W, void* stream);
+/* Noise for the rsample calls of a whole rollout in ONE launch, bit-identical to n_slots successive
+   torch.empty([1,C,H,W], device="cuda").normal_() calls (model_utils.py:107-108 -> torch.distributions.Normal.rsample ->
+   at::native::normal_ -> distribution_nullary_kernel with curand_normal4 on Philox4_32_10): slot i is filled exactly as the
+   i-th call would fill it, with torch's launch geometry (256-thread blocks, unroll 4, grid = min(SMs * maxThreads/256,
+   ceil(numel/256))) and Philox offset offset0 + i * offset_per_slot.  sf_normal_policy returns that grid and the per-call offset
+   increment for a tensor of numel elements on `device`; the caller (which owns the torch generator) passes seed / offset0 and
+   advances the generator by n_slots * offset_per_slot afterwards.                                                          */
+int sf_normal_policy(long long numel, int device, int* grid, int* offset_per_slot);
+int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long long seed, unsigned long long offset0, int grid,
+                         int offset_per_slot, void* stream);
+
 /* SmallEncoder / SmallDecoder glue on NHWC bf16 planes: 2x2 max-pool (res_models.py:96-104), nearest x2 up-sampling
    (:134-147; call once per plane), fp32 NHWC (gathered by slot) -> bf16 hi [+ lo] */
 int sf_maxpool2(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int n_images, int H, int W, int C, void* stream);

@@ -31,6 +31,7 @@ constexpr int TILE_W = 8;
 constexpr int KC = 64;            // channels per K-chunk (128 bytes of bf16)
 constexpr int ROW_BYTES = 128;    // one pixel of one chunk
 constexpr int VEC_MAX = 512;      // per-stage constant vector (bias / LN / gate weights), floats
+constexpr int WG_SCRATCH = 128;   // floats of shared scratch per epilogue warpgroup (behind the constant vector)
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_RING = 16;
 
@@ -202,6 +203,7 @@ struct PixelCtx {
   int y, x;
   bool valid;
   size_t pix;    // (sid*H + y)*W + x
+  int wg, m;     // epilogue warpgroup index and the thread's index in it (= TMEM lane)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -393,14 +395,26 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec,
     }
   } else if constexpr (EPI == SF_EPI_RES_ID || EPI == SF_EPI_RES_ID_ACT) {
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
+    // residual = SE output z * scale[sample][channel] when the SE layer is folded into its consumers: the tile's (one sample's)
+    // scales are staged once in the warpgroup's shared scratch (warpgroup-wide named barrier, id 1 + wg)
+    const uint32_t sc_s = vec + (uint32_t)(VEC_MAX + c.wg * WG_SCRATCH) * 4u;
+    if (e.res_scale) {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");          // readers of the previous tile are done
+      if (c.m < e.n_out) {
+        const float sv = __ldg(e.res_scale + (size_t)c.bi * e.res_scale_ch + e.in_co[0] + c.m);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc_s + (uint32_t)c.m * 4u), "f"(sv) : "memory");
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
+    }
 #pragma unroll 1
     for (int j = 0; j < e.n_out / 16; ++j) {
       float v[16], r[16], b[16];
       if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], i0 + j * 16, r); else zero16(r);
-      if (e.res_scale) {             // residual = SE output: z * scale[sample][channel] (SE layer folded into its consumers)
-        const float4* sc = reinterpret_cast<const float4*>(e.res_scale + (size_t)c.bi * e.res_scale_ch + e.in_co[0] + j * 16);
+      if (e.res_scale) {
+        float sc[16];
+        vec16(sc_s, j * 16, sc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float4 t = __ldg(sc + i); r[4 * i] *= t.x; r[4 * i + 1] *= t.y; r[4 * i + 2] *= t.z; r[4 * i + 3] *= t.w; }
+        for (int i = 0; i < 16; ++i) r[i] *= sc[i];
       }
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
@@ -500,7 +514,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + (size_t)nA * p.a_slot_bytes;
   float* vec_s = reinterpret_cast<float*>(b_base + (size_t)nB * p.b_slot_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX + WG_SCRATCH * NGROUPS);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + nA;
   uint64_t* b_full = a_empty + nA;
@@ -695,7 +709,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       const int y = ty * TILE_H + r, x = (tx * MT + mt) * TILE_W + cx;
       const bool valid = (y < p.H) && (x < p.W);
       const size_t pix = ((size_t)sid * p.H + y) * p.W + x;
-      if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; }
+      if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; out->wg = g; out->m = m; }
       return valid ? (long long)pix : -1;
     };
     if constexpr (epilogue_reads_global(EPI)) {

@@ -1,6 +1,8 @@
 // sf_elementwise.cuh -- the HBM-bound kernels of the path: squeeze-excite reduce / apply
 // (res_models.py:150-165) and the NCHW fp32 <-> NHWC bf16 layout kernels. 128-bit accesses throughout.
 #pragma once
+#include <curand_kernel.h>
+
 #include "sf_ptx.cuh"
 
 namespace sf {
@@ -194,6 +196,29 @@ __global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ 
     if (lo) h[i] = pack_bf16x2(v[2 * i] - bf16_lo_f(h[i]), v[2 * i + 1] - bf16_hi_f(h[i]));
   }
   *reinterpret_cast<uint4*>(out + ((size_t)bi * rows + row) * 64 + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+// ---- standard-normal noise for every rsample call of a rollout, one launch --------------------------------------------
+// Slot s (blockIdx.y) is filled exactly as the s-th of a sequence of torch normal_() calls on a numel-element CUDA float tensor
+// would fill it: same thread -> element mapping (element idx + T * (4 k + i) comes from component i of thread idx's k-th
+// curand_normal4 draw, T = gridDim.x * 256), same Philox4_32_10 subsequence (= thread index) and offset (offset0 + s * per_slot).
+__global__ void __launch_bounds__(256) normal_slots_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
+                                                           unsigned long long offset0, unsigned int per_slot) {
+  const unsigned int idx = blockIdx.x * 256u + threadIdx.x;
+  curandStatePhilox4_32_10_t state;
+  curand_init(seed, idx, offset0 + (unsigned long long)blockIdx.y * per_slot, &state);
+  const long long T = (long long)gridDim.x * 256;
+  const long long rounded = ((numel - 1) / (T * 4) + 1) * T * 4;
+  float* o = out + (long long)blockIdx.y * numel;
+  for (long long li = idx; li < rounded; li += T * 4) {
+    const float4 r = curand_normal4(&state);
+    const float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long l = li + T * i;
+      if (l < numel) o[l] = v[i];
+    }
+  }
 }
 
 // ---- NCHW fp32 -> NHWC bf16 (hi [+ lo]) : encoded observations entering the ODE loop ---------------------

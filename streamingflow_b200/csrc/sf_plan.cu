@@ -528,7 +528,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.flags = flags;
   st.n_out = 0;
   for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
-  const int fixed = 1024 + sf::VEC_MAX * 4 + BAR_AREA;
+  const int fixed = 1024 + (sf::VEC_MAX + 4 * sf::WG_SCRATCH) * 4 + BAR_AREA;
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
   // activation ring: one slot = one chunk's tile + halo (3 slots when they leave room for >= 2 weight slots);
   // weight ring: everything that is left, up to MAX_RING slots
@@ -638,6 +638,36 @@ int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images,
     pack_nchw_kernel<true><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), C, hw);
   else
     pack_nchw_kernel<false><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), nullptr, C, hw);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_normal_policy(long long numel, int device, int* grid, int* offset_per_slot) {
+  if (numel <= 0 || !grid || !offset_per_slot) return fail(SF_ERR_INVALID, "bad normal policy arguments");
+  // two cheap attribute queries, cached per device (cudaGetDeviceProperties costs milliseconds and this runs once per rollout)
+  static int sms[64] = {0}, threads_per_sm[64] = {0};
+  if (device < 0 || device >= 64) return fail(SF_ERR_INVALID, "bad device ordinal");
+  if (!sms[device]) {
+    int a = 0, b = 0;
+    SF_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, device));
+    SF_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrMaxThreadsPerMultiProcessor, device));
+    threads_per_sm[device] = b;
+    sms[device] = a;
+  }
+  // at::cuda::detail calc_execution_policy: block 256, unroll 4, grid = min(SMs * (maxThreadsPerSM / 256), ceil(numel / 256))
+  const long long blocks_per_sm = threads_per_sm[device] / 256;
+  long long g = (numel + 255) / 256;
+  const long long cap = (long long)sms[device] * blocks_per_sm;
+  if (g > cap) g = cap;
+  *grid = (int)g;
+  *offset_per_slot = (int)(((numel - 1) / (256 * g * 4) + 1) * 4);       // curand4_engine_calls = 4 per loop iteration
+  return SF_OK;
+}
+
+int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long long seed, unsigned long long offset0, int grid,
+                         int offset_per_slot, void* stream) {
+  if (!out || n_slots <= 0 || numel <= 0 || grid <= 0 || offset_per_slot <= 0 || n_slots > 65535) return fail(SF_ERR_INVALID, "bad normal fill arguments");
+  normal_slots_kernel<<<dim3(grid, n_slots), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

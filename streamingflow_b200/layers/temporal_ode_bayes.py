@@ -14,6 +14,7 @@ reference's own N > 1 behaviour on 4-D inputs is the degenerate ``n_present`` pa
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 import weakref
@@ -179,10 +180,28 @@ class NNFOwithBayesianJumps(nn.Module):
                 sd[f"{name}.{k}"] = v
         return sd
 
-    def _draw_noise(self, n, h, w, device):
+    def _draw_noise(self, n, h, w, device, out=None):
         """Standard-normal tensors in the reference's order: one ``torch.empty([1,C,h,w]).normal_()`` per infer_state call
-        (torch.distributions.Normal.rsample -> _standard_normal), here drawn in place into one [n, C, h, w] buffer."""
-        eps = torch.empty((max(n, 1), self.hidden_size, h, w), dtype=torch.float32, device=device)
+        (torch.distributions.Normal.rsample -> _standard_normal), here drawn in place into one [n, C, h, w] buffer
+        (``out``: an existing buffer of at least that size, e.g. the static noise buffer of a captured graph)."""
+        eps = out if out is not None else torch.empty((max(n, 1), self.hidden_size, h, w), dtype=torch.float32, device=device)
+        if device.type == "cuda" and self.noise != "bulk" and not torch.cuda.is_current_stream_capturing():
+            # one launch for all n slots, bit-identical to n successive normal_() calls (sf_normal_fill_slots reproduces torch's
+            # Philox4_32_10 / curand_normal4 kernel: same thread -> element mapping, offset advanced per call); the draws a
+            # sharded rank has to discard are a pure offset bump
+            lib = L.load()
+            gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+            numel = self.hidden_size * h * w
+            grid, per = ctypes.c_int(), ctypes.c_int()
+            L.check(lib.sf_normal_policy(numel, gen.device.index, ctypes.byref(grid), ctypes.byref(per)), "sf_normal_policy")
+            seed, off = gen.initial_seed(), gen.get_offset() + self.noise_skip * per.value
+            self.noise_skip = 0
+            if n > 0:
+                with torch.cuda.device(device):
+                    L.check(lib.sf_normal_fill_slots(eps.data_ptr(), n, numel, seed, off, grid.value, per.value,
+                                                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "sf_normal_fill_slots")
+            gen.set_offset(off + n * per.value)
+            return eps
         for _ in range(self.noise_skip):                # keep the global sample-major stream when the batch is sharded
             eps[0].normal_()
         self.noise_skip = 0
@@ -363,22 +382,24 @@ class NNFOwithBayesianJumps(nn.Module):
             table, evs = eng.build_table(ro.events)
             tdev = eng.upload_table(table)
             slots_dev = torch.tensor(flat, dtype=torch.int32).to(dev)
-            skip = self.noise_skip
             torch.cuda.synchronize(dev)
+            eps = torch.empty((max(ro.n_eps, 1), c, h, w), dtype=torch.float32, device=dev)     # the graph's static noise buffer
+            eng.bind_eps(eps)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 eng.zero_state(0)
-                self.noise_skip = skip
-                eps = self._draw_noise(ro.n_eps, h, w, dev)
-                eng.bind_eps(eps)
                 n_launch = eng.run_events(evs, tdev)
             ent = dict(graph=graph, eps=eps, slots=slots_dev, keep=(tdev, evs), launches=n_launch)
             self._graphs[sig] = ent
-            self.noise_skip = 0
-        else:
-            eng.bind_eps(ent["eps"])
-        # the layout pack reads the caller's tensor and the gathers write fresh output tensors: both stay outside the graph, so
-        # no staging copy of the observations and no clone of the results is needed around the replay
+        eng.bind_eps(ent["eps"])
+        # Around the replay, eagerly: the noise of the whole rollout (one launch, the reference's Philox stream), the layout pack
+        # of the caller's observations and the gathers into fresh output tensors -- no staging copy, no clone of the results.
+        try:
+            noise = self._draw_noise(ro.n_eps, h, w, hx_obs.device, out=ent["eps"])
+        except TypeError:                                  # a test double with the four-argument signature
+            noise = self._draw_noise(ro.n_eps, h, w, hx_obs.device)
+        if noise.data_ptr() != ent["eps"].data_ptr():
+            ent["eps"][: noise.shape[0]].copy_(noise)
         eng.pack_into(3, hx_obs)
         ent["graph"].replay()
         ro.launches = ent["launches"]
