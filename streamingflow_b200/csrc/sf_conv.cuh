@@ -210,8 +210,11 @@ struct PixelCtx {
 // fused epilogues.  taddr = TMEM address of this warp's lane quadrant, column 0 of the accumulator stage.
 // All tcgen05.ld are executed by every lane (they are warp-collective); global traffic is predicated.
 // ------------------------------------------------------------------------------------------------
+// acc_empty: the accumulator stage's EMPTY barrier.  Epilogues whose tail no longer reads TMEM arrive on it themselves as soon
+// as their last tcgen05.ld has completed (returning true), so the next tile's MMAs overlap that tail; otherwise the caller
+// arrives after the epilogue returns.
 template <int EPI, bool X3, int CG>
-__device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c) {
+__device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c, uint32_t acc_empty) {
   const EpiArgs& e = p.e;
   constexpr int NJ = CG / 16;                      // 16-channel slices of one CG-channel tensor
   const size_t pc = c.pix * CG;                    // this pixel in a CG-channel NHWC tensor
@@ -322,6 +325,9 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec,
         l1 = fmaf(g1w[i], yv, l1);
       }
     }
+    // the state update below works on global memory only: hand the accumulator back now
+    tc_fence_before();
+    mbar_arrive(acc_empty);
     if (c.valid) {
       const float g0 = __fdividef(1.0f, 1.0f + __expf(l1 - l0));     // softmax over the two logits, channel 0
       const float g1 = 1.0f - g0;
@@ -459,43 +465,7 @@ __device__ __forceinline__ void run_epilogue(const StageParams& p, uint32_t vec,
       }
     }
   }
-}
-
-// L2 prefetch of the global operands the epilogue of pixel `pix` will read (they do not depend on the accumulator): issued one
-// tile ahead, so the epilogue's loads hit L2 instead of paying the HBM latency once per 16-channel slice.
-template <int EPI, bool X3, int CG>
-__device__ __forceinline__ void prefetch_epilogue_operands(const StageParams& p, size_t pix) {
-  const EpiArgs& e = p.e;
-  auto lines = [](const void* base, int bytes) {
-    const char* q = reinterpret_cast<const char*>(base);
-#pragma unroll
-    for (int o = 0; o < bytes; o += 128) prefetch_l2(q + o);
-  };
-  if constexpr (EPI == SF_EPI_GATES) {
-    lines(e.s_in + pix * CG, CG * 4);
-  } else if constexpr (EPI == SF_EPI_PROPOSE) {
-    lines(e.s_in + pix * CG, CG * 4);
-    for (int k = 0; k < e.pairs; ++k) {
-      lines(e.in_h[k] + pix * CG, CG * 2);
-      if (X3) lines(e.in_l[k] + pix * CG, CG * 2);
-    }
-  } else if constexpr (EPI == SF_EPI_MIX) {
-    lines(e.a32 + pix * CG, CG * 4);
-    lines(e.b32 + pix * CG, CG * 4);
-    if (e.kind == 0) {
-      lines(e.s_in + pix * CG, CG * 4);
-      if (e.s_base != e.s_in) lines(e.s_base + pix * CG, CG * 4);
-    }
-  } else if constexpr (EPI == SF_EPI_RES_ID || EPI == SF_EPI_RES_ID_ACT) {
-    const size_t i0 = pix * e.in_cs[0] + e.in_co[0];
-    for (int o = 0; o < e.n_out * 2; o += 128) {
-      prefetch_l2(reinterpret_cast<const char*>(e.in_h[0] + i0) + o);
-      if (X3) prefetch_l2(reinterpret_cast<const char*>(e.in_l[0] + i0) + o);
-    }
-  }
-}
-constexpr bool epilogue_reads_global(int epi) {
-  return epi == SF_EPI_GATES || epi == SF_EPI_PROPOSE || epi == SF_EPI_MIX || epi == SF_EPI_RES_ID || epi == SF_EPI_RES_ID_ACT;
+  return EPI == SF_EPI_MIX;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -712,22 +682,17 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; out->wg = g; out->m = m; }
       return valid ? (long long)pix : -1;
     };
-    if constexpr (epilogue_reads_global(EPI)) {
-      const long long p0 = pixel_of(blockIdx.x + st * gridDim.x, nullptr);
-      if (p0 >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)p0);
-    }
     for (int w = blockIdx.x + st * gridDim.x; w < nwork; w += S * gridDim.x, aph ^= 1) {
       PixelCtx c;
       const bool mine = pixel_of(w, &c) != -2;
-      if constexpr (epilogue_reads_global(EPI)) {
-        const long long pn = pixel_of(w + S * gridDim.x, nullptr);
-        if (pn >= 0) prefetch_epilogue_operands<EPI, X3, CG>(p, (size_t)pn);
-      }
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
-      if (mine) run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c);
-      tc_fence_before();
-      mbar_arrive(smem_u32(acc_empty + st));
+      bool released = false;
+      if (mine) released = run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c, smem_u32(acc_empty + st));
+      if (!released) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(acc_empty + st));
+      }
     }
   }
   tc_fence_before();

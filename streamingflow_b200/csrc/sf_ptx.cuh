@@ -143,9 +143,6 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
                : "memory");
 }
 
-// L2 prefetch of one 128-byte line (no register result): used by the epilogue warps to pull their tile's fp32 / bf16
-// operands from HBM into L2 while the tile's MMAs are still running
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 128-bit shared-memory load through an explicit shared-window address (LDS.128 instead of a generic LD)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
