@@ -229,7 +229,7 @@ def main():
             b.record()
         barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    launches = ro.launches + 2               # stage kernels of one rollout + layout pack + path gather
+    launches = ro.launches + 4               # stage kernels of one rollout + layout pack + noise fill + path gather + final-state gather
     eng.check_errflag()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:

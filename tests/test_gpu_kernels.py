@@ -111,10 +111,14 @@ def _act(eng, buf, n):
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("kind", ["step", "jump"])
-@pytest.mark.parametrize("H,W,C", [(20, 13, 64), (50, 50, 64), (20, 13, 128), (36, 40, 128)])
+@pytest.mark.parametrize("H,W,C", [(20, 13, 64), (50, 50, 64), (20, 13, 128), (36, 40, 128), (100, 100, 64), (120, 120, 64)])
 def test_one_event_every_intermediate_matches_oracle(precision, kind, H, W, C):
     """Runs ONE event (6 cell stages + 5 prior stages + 2 SE layers) and checks every buffer a stage writes against the
-    oracle's corresponding tensor.  Sizes with ragged tiles (20x13: partial 16x8 tiles in both directions)."""
+    oracle's corresponding tensor.  Sizes with ragged tiles (20x13: partial 16x8 tiles in both directions) and all three
+    work-item regimes of the persistent kernels on 148 SMs: every tile split into single M-tiles (small grids), whole tiles
+    only (100x100 x 3 samples = 147 tiles), full waves of whole tiles plus a split tail (120x120 x 3 = 192 tiles)."""
+    if H >= 100 and (kind == "jump" or precision == "bf16x3") and not (H == 120 and kind == "jump" and precision == "bf16x3"):
+        pytest.skip("large grids: one combination per regime is enough")
     from streamingflow_b200 import engine as en
 
     B = 3
@@ -196,6 +200,56 @@ def test_batch_composition_does_not_change_a_sample():
     assert torch.equal(s_perm, s_all[[2, 0, 3, 1]]) and torch.equal(x_perm, x_all[[2, 0, 3, 1]])
     s_one, x_one = run([1])
     assert torch.equal(s_one[0], s_all[1]) and torch.equal(x_one[0], x_all[1])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_se_layers_folded_into_weights_match_the_two_kernel_form(precision):
+    """The default engine folds the squeeze-excite scales into the consuming convs' weights (no activation pass); the
+    row-sharded path keeps reduce -> apply.  Same inputs: the sampled input and prior parameters agree to rounding."""
+    from streamingflow_b200 import engine as en
+    from streamingflow_b200.engine import OdeEngine
+
+    H, W, B = 40, 24, 3
+    sd = so.recipe_state_dict(nnfo_shapes(64), 5, 1.0, torch.float32)
+    hot = {k: v.cuda() for k, v in sd.items() if k.startswith(("gru_c", "gru_obs", "p_model"))}
+    g = torch.Generator().manual_seed(4)
+    state = 0.5 * torch.randn(B, 64, H, W, generator=g).cuda()
+    eps = torch.randn(B, 64, H, W, generator=g).cuda()
+    outs = []
+    for fold in (True, False):
+        eng = OdeEngine(hot, "", H, W, B, precision, torch.device("cuda"), se_fold=fold)
+        assert eng.se_fold == fold and (en.BUF_Y1 in eng.act) == (not fold)
+        eng.set_state(0, state)
+        eng.bind_eps(eps.contiguous())
+        ev = dict(kind=0, samples=[0, 1, 2], x_img=[0, 1, 2], rec=[-1] * 3, eps=[0, 1, 2], dt=[0.0] * 3, x_buf=en.BUF_X, s_in=0,
+                  s_base=0, s_out=0, run_cell=0, run_prior=1, want_f32=1)
+        eng.run_rollout([ev])
+        torch.cuda.synchronize()
+        eng.check_errflag()
+        outs.append((eng.x32[:B].clone(), eng.params32[:B].clone()))
+    tol = 2e-2 if precision == "bf16" else 1e-4
+    for a, b in zip(*outs):
+        assert (a - b).abs().max().item() / b.abs().max().item() < tol
+
+
+def test_rollout_noise_in_one_launch_equals_successive_normal_calls():
+    """sf_normal_fill_slots == n successive torch normal_() calls, bit for bit, at the bench shapes: the 10 MB slots of the
+    200x200x64 state take the capped grid (148 SMs x 8 blocks) and three loop iterations per thread; 50x50x64 does not;
+    the generator ends at the same offset, and skipped draws (batch sharding) are an offset bump."""
+    from streamingflow_b200.layers.temporal_ode_bayes import NNFOwithBayesianJumps
+    from streamingflow_b200.config import ode_cfg
+
+    m = NNFOwithBayesianJumps(64, 64, ode_cfg(64)).eval().cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for h, n in ((200, 3), (50, 5), (7, 4)):
+        torch.manual_seed(99)
+        want = [torch.empty([1, 64, h, h], device="cuda").normal_() for _ in range(n + 2)]
+        tail_want = torch.randn(5, device="cuda")
+        torch.manual_seed(99)
+        m.noise_skip = 2
+        got = m._draw_noise(n, h, h, dev)
+        tail = torch.randn(5, device="cuda")
+        assert all(torch.equal(got[i], want[i + 2][0]) for i in range(n)) and torch.equal(tail, tail_want)
 
 
 def test_zero_dt_step_keeps_the_state():
