@@ -242,7 +242,9 @@ def main():
 
     def e2e_once():
         with torch.no_grad():
-            ode.integrate_latents_streamed(hx_host, [n_obs] * B, [times] * B, [TARGETS] * B, 0.05, out_host=sel_host)
+            # join=False: the downloads of this step stay on their copy stream; the device-wide synchronize that closes the
+            # timed region waits for them, and the next step's uploads / compute pipeline behind this one
+            ode.integrate_latents_streamed(hx_host, [n_obs] * B, [times] * B, [TARGETS] * B, 0.05, out_host=sel_host, join=False)
 
     e2e_once()
     barrier()
@@ -251,6 +253,7 @@ def main():
     ea.record()
     for _ in range(n_e2e):
         e2e_once()
+    torch.cuda.current_stream().wait_event(ode.download_done)      # the closing event comes after the last step's last download
     eb.record()
     barrier()
     t = torch.tensor([ea.elapsed_time(eb)], device=dev, dtype=torch.float64)
@@ -259,7 +262,8 @@ def main():
     e2e_value = world * steps_per_rollout * n_e2e / (t.item() * 1e-3)
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hx_host.numel() * 4, d2h_bytes_per_step=sel_host.numel() * 4,
                api="NNFOwithBayesianJumps.integrate_latents_streamed (the body of forward between srvp_encode and srvp_decode) on pinned "
-                   "host buffers; uploads / downloads pipelined against the rollout on copy streams, all inside the timed region")
+                   "host buffers; uploads / downloads pipelined against the rollout on copy streams (double-buffered staging: consecutive steps "
+                   "pipeline into each other), all copies of every timed step inside the timed region")
 
     # ---------------- per-stage roofline (rank 0)
     peaks = load_peaks()

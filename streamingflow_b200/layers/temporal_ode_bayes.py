@@ -405,25 +405,47 @@ class NNFOwithBayesianJumps(nn.Module):
         ro.launches = ent["launches"]
         return eng.unpack_f32(eng.state32[0], B), eng.unpack_path(ent["slots"]).view(B, T, c, h, w)
 
-    def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None):
+    def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None, join=True):
         """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final
-        states on device, selected latents [B, T, C, h, w] as a view of the pinned CPU tensor ``out_host`` [T, B, C, h, w]).  Host<->device copies are
-        pipelined against the rollout: observation k of every sample is uploaded on a copy stream while earlier events run
-        (a jump only needs its own frame), and each target's selected state is gathered and downloaded as soon as the
-        event that produces it has been enqueued."""
+        states on device, selected latents [B, T, C, h, w] as a view of the pinned CPU tensor ``out_host`` [T, B, C, h, w]).
+        Host<->device copies are pipelined against the rollout: observation k of every sample is uploaded on a copy stream
+        while earlier events run (a jump only needs its own frame), and each target's selected state is gathered and
+        downloaded as soon as the event that produces it has been enqueued.  The device staging buffers are double-buffered
+        and the per-schedule host work (event table, slot lists) is cached, so consecutive calls pipeline into each other: the
+        uploads of call r+1 run under the compute of call r.  ``join=False`` leaves the downloads running on their copy stream
+        when the call returns (the caller synchronises the device, or ``self.download_done``, before reading ``out_host``);
+        the default makes the current stream wait for them."""
         B = len(obs_counts)
         _, c, h, w = hx_host.shape
         dev = next(self.parameters()).device
-        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
-        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
         kmax = max(obs_counts)
-        ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b)
         eng = self._engine_for(h, w, B, dev)
+        T = len(targets[0])
+        cache = self.__dict__.setdefault("_stream_plans", {})
+        sig = (id(eng), tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times), tuple(tuple(float(x) for x in t) for t in targets),
+               float(delta_t), self.use_variable_ode_step, self.solver, bool(self.impute))
+        plan = cache.get(sig)
+        if plan is None:
+            if len(cache) >= 8:
+                cache.clear()
+            plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
+            base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+            ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b)
+            table, evs = eng.build_table(ro.events)
+            tdev = eng.upload_table(table)
+            slots_dev = torch.tensor([[ro.out_slots[b][t] for b in range(B)] for t in range(T)], dtype=torch.int32).to(dev)
+            last_writer = {}
+            for i, e in enumerate(ro.events):
+                for slot in e["rec"]:
+                    if slot >= 0:
+                        last_writer[slot] = i
+            ready_at = [max(last_writer[ro.out_slots[b][t]] for b in range(B)) for t in range(T)]
+            plan = cache[sig] = dict(ro=ro, base=base, evs=evs, tdev=tdev, slots=slots_dev, ready_at=ready_at)
+        ro, base, evs, tdev, slots_dev, ready_at = (plan[k] for k in ("ro", "base", "evs", "tdev", "slots", "ready_at"))
         eng.reserve_observations(kmax * B)
         eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
         eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
-        T = len(targets[0])
         if out_host is None:
             out_host = torch.empty((T, B, c, h, w), dtype=torch.float32).pin_memory()
         assert tuple(out_host.shape) == (T, B, c, h, w) and out_host.is_contiguous()
@@ -434,11 +456,21 @@ class NNFOwithBayesianJumps(nn.Module):
         stage = self.__dict__.setdefault("_stage_bufs", {})
         key = (str(dev), kmax * B, B, T, c, h, w)
         if stage.get("key") != key:
-            stage.update(key=key, hx=torch.empty((kmax * B, c, h, w), dtype=torch.float32, device=dev),
-                         out=torch.empty((T, B, c, h, w), dtype=torch.float32, device=dev))
-        hx_dev, out_dev = stage["hx"], stage["out"]
-        # uploads, in order of need (observation index k across all samples)
-        s_in.wait_stream(main)
+            torch.cuda.synchronize(dev)
+            stage.clear()
+            stage.update(key=key, turn=0,
+                         hx=[torch.empty((kmax * B, c, h, w), dtype=torch.float32, device=dev) for _ in range(2)],
+                         out=[torch.empty((T, B, c, h, w), dtype=torch.float32, device=dev) for _ in range(2)],
+                         hx_free=[None, None], out_free=[None, None])
+        turn = stage["turn"]
+        stage["turn"] = 1 - turn
+        hx_dev, out_dev = stage["hx"][turn], stage["out"][turn]
+        # uploads, in order of need (observation index k across all samples); the staging buffer was last read by the packs of
+        # the call before the previous one
+        if stage["hx_free"][turn] is not None:
+            s_in.wait_event(stage["hx_free"][turn])
+        else:
+            s_in.wait_stream(main)
         up_done = []
         with torch.cuda.stream(s_in):
             for k in range(kmax):
@@ -448,15 +480,8 @@ class NNFOwithBayesianJumps(nn.Module):
                 e = torch.cuda.Event()
                 e.record(s_in)
                 up_done.append(e)
-        table, evs = eng.build_table(ro.events)
-        tdev = eng.upload_table(table)
-        slots_dev = torch.tensor([[ro.out_slots[b][t] for b in range(B)] for t in range(T)], dtype=torch.int32).to(dev)
-        last_writer = {}
-        for i, e in enumerate(ro.events):
-            for slot in e["rec"]:
-                if slot >= 0:
-                    last_writer[slot] = i
-        ready_at = [max(last_writer[ro.out_slots[b][t]] for b in range(B)) for t in range(T)]
+        if stage["out_free"][turn] is not None:
+            main.wait_event(stage["out_free"][turn])          # the downloads that last read this gather buffer
         packed, flushed, launches = set(), set(), 0
         for i, e in enumerate(ro.events):
             if e["kind"] == JUMP:
@@ -465,6 +490,10 @@ class NNFOwithBayesianJumps(nn.Module):
                         main.wait_event(up_done[k])
                         eng.pack_into(3, hx_dev[k * B:(k + 1) * B], img_offset=k * B)
                         packed.add(k)
+                        if len(packed) == kmax:
+                            free = torch.cuda.Event()
+                            free.record(main)
+                            stage["hx_free"][turn] = free
             launches += eng.run_events(evs[i:i + 1], tdev)
             for t in range(T):
                 if t not in flushed and ready_at[t] <= i:
@@ -475,7 +504,12 @@ class NNFOwithBayesianJumps(nn.Module):
                     with torch.cuda.stream(s_out):
                         out_host[t].copy_(out_dev[t], non_blocking=True)      # contiguous pinned destination: one async DMA
                     flushed.add(t)
-        main.wait_stream(s_out)
+        down = torch.cuda.Event()
+        down.record(s_out)
+        stage["out_free"][turn] = down
+        self.__dict__["download_done"] = down
+        if join:
+            main.wait_event(down)
         ro.launches = launches
         self.last_rollout = ro
         return eng.unpack_f32(eng.state32[0], B), out_host.transpose(0, 1)
