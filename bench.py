@@ -59,9 +59,33 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.stop, self.thread = gpu_index, [], None, threading.Event(), None
 
     def __enter__(self):
+        # NVML polled from a thread every 10 ms (the timed region is ~0.1 s; nvidia-smi -lms often delivers no sample in time)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def poll():
+                while not self.stop.is_set():
+                    try:
+                        r = get_reasons(h)
+                        self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx), "0"] +
+                                         ["Active" if r & m else "Not Active" for _, m in bits])
+                    except Exception:
+                        pass
+                    self.stop.wait(0.01)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,12 +100,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.thread is not None:
+            self.thread.join(timeout=1)
 
     def summary(self):
         sm, mx, reasons = [], [], set()

@@ -268,6 +268,7 @@ class OdeEngine:
 
     # ------------------------------------------------------------------ workspace
     def _new_act(self, buf, n_images, channels):
+        self.alloc_gen = getattr(self, "alloc_gen", 0) + 1     # captured CUDA graphs hold buffer addresses: (re)allocation invalidates them
         shape = (n_images, self.H, self.W, channels)
         hi = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
         lo = torch.zeros(shape, dtype=torch.bfloat16, device=self.device) if self.x3 else None
@@ -303,6 +304,7 @@ class OdeEngine:
 
     def ensure_path_slots(self, n):
         if self.path is None or self.path.shape[0] < n:
+            self.alloc_gen = getattr(self, "alloc_gen", 0) + 1
             self.path = torch.zeros((n, self.H, self.W, self.C), dtype=torch.float32, device=self.device)
             self._bind_f32(L.F32_PATH, self.path)
 

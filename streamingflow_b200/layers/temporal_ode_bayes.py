@@ -133,6 +133,7 @@ class NNFOwithBayesianJumps(nn.Module):
         # engine options (not part of the reference API)
         self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
         self.noise = "reference"
+        self.event_group = int(os.environ.get("SF_EVENT_GROUP", "0"))   # > 0: at most this many samples per batched event
         self.noise_skip = 0                             # draws to discard first (batch sharding: samples of earlier ranks)
         self.cuda_graph = os.environ.get("SF_B200_CUDA_GRAPH", "0") == "1"   # capture / replay the whole rollout as one CUDA graph
         self.fused_codec = os.environ.get("SF_B200_FUSED_CODEC", "1") == "1"  # SmallEncoder / SmallDecoder on the conv-stage kernels
@@ -211,6 +212,15 @@ class NNFOwithBayesianJumps(nn.Module):
             for i in range(n):
                 eps[i].normal_()
         return eps
+
+    def _noise_into(self, buf, n, h, w, device):
+        """Draws the rollout's noise into ``buf`` (the static noise buffer of captured graphs)."""
+        try:
+            noise = self._draw_noise(n, h, w, device, out=buf)
+        except TypeError:                                  # a test double with the four-argument signature
+            noise = self._draw_noise(n, h, w, device)
+        if noise.data_ptr() != buf.data_ptr():
+            buf[: noise.shape[0]].copy_(noise[: buf.shape[0]])
 
     # ------------------------------------------------------------------ encoder / decoder wrappers (reference :396-434)
     def srvp_decode(self, x, skip=None):
@@ -336,7 +346,7 @@ class NNFOwithBayesianJumps(nn.Module):
             dev = hx_obs.device
         plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-        ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all)
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all, max_group=self.event_group)
         eng = self._engine_for(h, w, B, dev)
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
@@ -367,18 +377,15 @@ class NNFOwithBayesianJumps(nn.Module):
         sig = (id(eng), eng.max_images, tuple(hx_obs.shape), self.noise, self.noise_skip, eng.precision,
                tuple((e["kind"], e["x_buf"], e["s_in"], e["s_base"], e["s_out"], e["run_prior"], tuple(e["samples"]), tuple(e["x_img"]),
                       tuple(e["rec"]), tuple(e["eps"]), tuple(e["dt"])) for e in ro.events), tuple(flat), self._weights_fingerprint())
+        eng.reserve_observations(hx_obs.shape[0])       # allocations happen here, outside the capture; a buffer that moves bumps
+        eng.ensure_path_slots(ro.n_path)                # eng.alloc_gen, which retires the graphs captured with the old addresses
         ent = self._graphs.get(sig)
+        if ent is not None and ent["gen"] != eng.alloc_gen:
+            ent = None
         if ent is None:
             if len(self._graphs) >= 8:
                 self._graphs.clear()
             dev = hx_obs.device
-            obs_before = eng.act[3][0].data_ptr() if 3 in eng.act else None
-            eng.reserve_observations(hx_obs.shape[0])   # allocations happen here, outside the capture
-            if obs_before is not None and eng.act[3][0].data_ptr() != obs_before:
-                # the observation buffer moved: graphs captured on this engine hold its old address
-                for k in [k for k in self._graphs if k[0] == id(eng)]:
-                    del self._graphs[k]
-            eng.ensure_path_slots(ro.n_path)
             table, evs = eng.build_table(ro.events)
             tdev = eng.upload_table(table)
             slots_dev = torch.tensor(flat, dtype=torch.int32).to(dev)
@@ -389,17 +396,12 @@ class NNFOwithBayesianJumps(nn.Module):
             with torch.cuda.graph(graph):
                 eng.zero_state(0)
                 n_launch = eng.run_events(evs, tdev)
-            ent = dict(graph=graph, eps=eps, slots=slots_dev, keep=(tdev, evs), launches=n_launch)
+            ent = dict(graph=graph, eps=eps, slots=slots_dev, keep=(tdev, evs), launches=n_launch, gen=eng.alloc_gen)
             self._graphs[sig] = ent
         eng.bind_eps(ent["eps"])
         # Around the replay, eagerly: the noise of the whole rollout (one launch, the reference's Philox stream), the layout pack
         # of the caller's observations and the gathers into fresh output tensors -- no staging copy, no clone of the results.
-        try:
-            noise = self._draw_noise(ro.n_eps, h, w, hx_obs.device, out=ent["eps"])
-        except TypeError:                                  # a test double with the four-argument signature
-            noise = self._draw_noise(ro.n_eps, h, w, hx_obs.device)
-        if noise.data_ptr() != ent["eps"].data_ptr():
-            ent["eps"][: noise.shape[0]].copy_(noise)
+        self._noise_into(ent["eps"], ro.n_eps, h, w, hx_obs.device)
         eng.pack_into(3, hx_obs)
         ent["graph"].replay()
         ro.launches = ent["launches"]
@@ -443,9 +445,26 @@ class NNFOwithBayesianJumps(nn.Module):
             plan = cache[sig] = dict(ro=ro, base=base, evs=evs, tdev=tdev, slots=slots_dev, ready_at=ready_at)
         ro, base, evs, tdev, slots_dev, ready_at = (plan[k] for k in ("ro", "base", "evs", "tdev", "slots", "ready_at"))
         eng.reserve_observations(kmax * B)
-        eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
-        eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
+        if self.cuda_graph and plan.get("gen") != eng.alloc_gen:
+            # one captured graph per batched event (its 15 stage launches); copies, packs and gathers stay eager around them
+            plan["eps"] = torch.empty((max(ro.n_eps, 1), c, h, w), dtype=torch.float32, device=dev)
+            eng.bind_eps(plan["eps"])
+            torch.cuda.synchronize(dev)
+            plan["graphs"], plan["graph_launches"] = [], []
+            for i in range(len(evs)):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    plan["graph_launches"].append(eng.run_events(evs[i:i + 1], tdev))
+                plan["graphs"].append(gph)
+            plan["gen"] = eng.alloc_gen
+        graphs = plan.get("graphs") if self.cuda_graph else None
+        eng.zero_state(0)
+        if graphs is not None:
+            eng.bind_eps(plan["eps"])
+            self._noise_into(plan["eps"], ro.n_eps, h, w, dev)
+        else:
+            eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
         if out_host is None:
             out_host = torch.empty((T, B, c, h, w), dtype=torch.float32).pin_memory()
         assert tuple(out_host.shape) == (T, B, c, h, w) and out_host.is_contiguous()
@@ -494,7 +513,11 @@ class NNFOwithBayesianJumps(nn.Module):
                             free = torch.cuda.Event()
                             free.record(main)
                             stage["hx_free"][turn] = free
-            launches += eng.run_events(evs[i:i + 1], tdev)
+            if graphs is not None:
+                graphs[i].replay()
+                launches += plan["graph_launches"][i]
+            else:
+                launches += eng.run_events(evs[i:i + 1], tdev)
             for t in range(T):
                 if t not in flushed and ready_at[t] <= i:
                     eng.unpack_path(slots_dev[t], out=out_dev[t])

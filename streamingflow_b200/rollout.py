@@ -35,7 +35,7 @@ class Rollout:
 
 
 def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool,
-                    record_all: bool = False, obs_index=None) -> Rollout:
+                    record_all: bool = False, obs_index=None, max_group: int = 0) -> Rollout:
     """record_all additionally records the state after EVERY op (debug / parity traces).  obs_index(b, k) overrides the
     image index of sample b's k-th observation in the OBS buffer (default: sample-major obs_base[b] + k)."""
     ro = Rollout()
@@ -101,7 +101,13 @@ def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver
             g["eps"].append(e["eps"])
             g["dt"].append(e["dt"])
         for g in groups.values():
-            ro.events.append(g)
             ro.n_cell_evals += len(g["samples"])
             ro.n_prior_evals += len(g["samples"]) * g["run_prior"]
+            n = len(g["samples"])
+            step = max_group if max_group and max_group > 0 else n
+            for i in range(0, n, step):          # optional cap on the samples per event (keeps an event's intermediates in L2)
+                part = dict(g)
+                for k in ("samples", "x_img", "rec", "eps", "dt"):
+                    part[k] = g[k][i:i + step]
+                ro.events.append(part)
     return ro

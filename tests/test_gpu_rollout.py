@@ -184,6 +184,20 @@ def test_streamed_host_buffer_rollout_equals_device_rollout():
         s_host, sel_host = m.integrate_latents_streamed(hx.pin_memory(), counts, times, targets, 0.05)
     torch.cuda.synchronize()
     assert torch.equal(s_dev, s_host) and torch.equal(sel_dev.cpu(), sel_host)
+    # graph mode (one captured graph per batched event), consecutive calls pipelined through the double-buffered staging with
+    # the downloads left running (join=False): every call still returns its own inputs' result
+    m.cuda_graph = True
+    hx2 = torch.tanh(so.recipe_array("hx2", (sum(counts), 64, h, w), 5))
+    pinned = [hx.pin_memory(), hx2.pin_memory(), hx.pin_memory()]
+    outs = [torch.empty((len(targets[0]), len(counts), 64, h, w)).pin_memory() for _ in pinned]
+    with torch.no_grad():
+        for src, dst in zip(pinned, outs):
+            m.integrate_latents_streamed(src, counts, times, targets, 0.05, out_host=dst, join=False)
+        torch.cuda.synchronize()
+        m.cuda_graph = False
+        _, sel2 = m.integrate_latents(hx2.cuda(), counts, times, targets, 0.05)
+    assert torch.equal(outs[0].transpose(0, 1), sel_dev.cpu()) and torch.equal(outs[2].transpose(0, 1), sel_dev.cpu())
+    assert torch.equal(outs[1].transpose(0, 1), sel2.cpu()) and not torch.equal(outs[1], outs[0])
 
 
 @pytest.mark.parametrize("config", ["config3_streaming_40_steps", "config4_8s_horizon"])
