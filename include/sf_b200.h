@@ -134,6 +134,9 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
    0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU(erf); bit 4 (bias_act) also write the output to SF_F32_OUT in fp32;
    bit 5 (gates / propose at C = 64) a single gate pair / proposal (plain ConvGRU of the refinement) instead of two;
    bit 6 (bias_act) add the per-image bias SF_F32_IMG_BIAS[image][n_out] (ASPP pooling branch);
+   bit 9 (lngelu, C = 64, n = 64 chunks) row-paired taps: the packed weights order each dx column as pairs of vertically
+   adjacent taps [dy = 1 | 0], [3 | 2], ... (+ the last tap alone when R is odd), per rep [tap_hi rows | tap_lo rows]; the kernel
+   issues one MMA of twice the width per pair and folds the second column block back one row in the epilogue;
    bit 7 (res_id) the residual input is multiplied by the per-sample channel scales of SE layer (flags >> 8) & 1 (the SE
    layer was folded into its consumers, see sf_plan_define_stage_fold).                                                  */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,

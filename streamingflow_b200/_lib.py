@@ -15,6 +15,7 @@ PREC_BF16, PREC_BF16X3 = 0, 1
 (F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT, F32_IMG_BIAS) = range(12)
 ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE, ACT_GELU = 0, 1, 2, 3, 4
 FLAG_KEEP_A32, FLAG_OUT32, FLAG_SINGLE, FLAG_IMG_BIAS, FLAG_RES_SE_SCALE = 1, 16, 32, 64, 128   # bit 8: which SE layer scales the residual
+FLAG_PAIR_ROWS = 512          # lngelu stages at C = 64: vertically adjacent taps paired into one MMA of twice the width
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
 SE_ITEM_BASE = 1000          # event-graph item: SE reduce + apply (activation pass)
 SE_FOLD_ITEM_BASE = 2000     # event-graph item: SE reduce + scales folded into the consumers' weights

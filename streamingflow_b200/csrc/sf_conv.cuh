@@ -32,6 +32,7 @@ constexpr int KC = 64;            // channels per K-chunk (128 bytes of bf16)
 constexpr int ROW_BYTES = 128;    // one pixel of one chunk
 constexpr int VEC_MAX = 512;      // per-stage constant vector (bias / LN / gate weights), floats
 constexpr int WG_SCRATCH = 128;   // floats of shared scratch per epilogue warpgroup (behind the constant vector)
+constexpr int WG_SCRATCH_PAIR = 1024;   // ... for a stage with row-paired taps: 2 buffers x 4 warps x 8 lanes x 16 floats
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_RING = 16;
 
@@ -81,6 +82,8 @@ struct alignas(64) StageParams {
   const float* vec;
   int nvec;
   int a_slot_bytes, b_slot_bytes, nA, nB;
+  int pair_rows;             // 1: vertically adjacent taps are paired into one MMA of twice the width (see conv_stage_kernel)
+  int wg_scratch;            // floats of shared scratch per epilogue warpgroup
   int w_rows_per_sample;     // > 0: per-sample weights (SE layer folded in): active sample bi reads rows [bi * this, (bi+1) * this)
   int* err;
   EpiArgs e;
@@ -293,6 +296,37 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
       }
     }
   } else if constexpr (EPI == SF_EPI_LNGELU) {
+    if (p.pair_rows) {
+      // Row-paired taps: column block 1 [CG, 2CG) of lane m holds the partial sum that belongs to the pixel ONE ROW BELOW
+      // (lane m + 8).  Fold it in: block0[m] += block1[m - 8].  Inside a warp that is a shuffle by 8 lanes; the first row of a
+      // warp takes the last row of the warp above through the warpgroup's shared scratch (double-buffered per slice; one
+      // named barrier per slice).  The tile's first row (lane row 0) is a scratch row: it only feeds row 1.
+      const int lane = c.m & 31, q = c.m >> 5;
+      const uint32_t scratch = vec + (uint32_t)(VEC_MAX + c.wg * p.wg_scratch) * 4u;
+#pragma unroll 1
+      for (int j = 0; j < NJ; ++j) {
+        float v0[16], v1[16];
+        tmem_ld16x2(taddr + j * 16, taddr + CG + j * 16, v0, v1);
+        const uint32_t buf = scratch + (uint32_t)((j & 1) * 512 + q * 128) * 4u;
+        if (lane >= 24) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)((lane - 24) * 16 + 4 * i) * 4u), "f"(v1[4 * i]),
+                         "f"(v1[4 * i + 1]), "f"(v1[4 * i + 2]), "f"(v1[4 * i + 3]) : "memory");
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
+        float up[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) up[i] = __shfl_up_sync(0xffffffffu, v1[i], 8);
+        if (lane < 8) {
+          if (q > 0) vec16(buf - 128u * 4u, lane * 16, up); else zero16(up);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v0[i] += up[i];
+        tmem_st16(taddr + j * 16, v0);
+      }
+      tmem_st_wait();
+    }
     float mean, rstd;
     ln_stats<CG>(taddr, mean, rstd);
 #pragma unroll 1
@@ -403,7 +437,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
     const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
     // residual = SE output z * scale[sample][channel] when the SE layer is folded into its consumers: the tile's (one sample's)
     // scales are staged once in the warpgroup's shared scratch (warpgroup-wide named barrier, id 1 + wg)
-    const uint32_t sc_s = vec + (uint32_t)(VEC_MAX + c.wg * WG_SCRATCH) * 4u;
+    const uint32_t sc_s = vec + (uint32_t)(VEC_MAX + c.wg * p.wg_scratch) * 4u;
     if (e.res_scale) {
       asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");          // readers of the previous tile are done
       if (c.m < e.n_out) {
@@ -484,7 +518,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + (size_t)nA * p.a_slot_bytes;
   float* vec_s = reinterpret_cast<float*>(b_base + (size_t)nB * p.b_slot_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX + WG_SCRATCH * NGROUPS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX + p.wg_scratch * NGROUPS);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + nA;
   uint64_t* b_full = a_empty + nA;
@@ -547,7 +581,8 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
         const int tile = work_tile(w, mtmask);
         const int bi = tile / tpi, rem = tile - bi * tpi;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int y0 = ty * TILE_H, x0 = tx * TILE_W * MT;
+        // row-paired taps: 15 output rows per tile; lane row 0 is the row above them (it only produces block-1 partial sums)
+        const int y0 = p.pair_rows ? ty * (TILE_H - 1) - 1 : ty * TILE_H, x0 = tx * TILE_W * MT;
         const int sid = __shfl_sync(0xffffffffu, p.sample_id[bi], 0), ximg = __shfl_sync(0xffffffffu, p.x_img[bi], 0);
         for (int c = 0; c < p.nchunk; ++c) {
           const ChunkK ck = p.chunk[c];
@@ -622,7 +657,30 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
               // first tap of this group: dy = gi*tb; one pixel row = 128 B = 8 descriptor units
               uint32_t a_lo = a_lo0 + ((uint32_t)(gi * ck.tb) * WP + (uint32_t)dx) * (ROW_BYTES >> 4);
               const int ntap = min(ck.tb, R - gi * ck.tb);
-              if (elect_one()) {
+              if (p.pair_rows) {
+                // Row-paired taps.  This B tile holds the taps dy = gi*tb .. gi*tb + ntap - 1 of column dx as ONE operand of
+                // n * ntap rows per rep, ordered [dy_hi | dy_lo]; a single MMA per K step, on the window of dy_hi, produces the
+                // dy_hi term of its own pixel in column block 0 and the dy_lo term of the pixel one row below in block 1 (the
+                // epilogue folds block 1 back).  Twice the N per MMA for the 64-channel stages, whose issue cost is ~41 + N/2.
+                if (elect_one()) {
+                  const uint32_t a_pair = a_lo + (uint32_t)(ntap - 1) * WP * (ROW_BYTES >> 4);
+                  const uint32_t idesc_pair = make_idesc_bf16(128, (uint32_t)(ck.n * ntap));
+                  uint32_t acc = accumulate;
+                  for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo * ntap) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) {
+#pragma unroll
+                      for (int mt = 0; mt < MT; ++mt) {
+                        if (MT > 1 && !((mtmask >> mt) & 1u)) continue;
+                        umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_pair + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
+                                  ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc_pair, acc | (k > 0 ? 1u : 0u));
+                      }
+                    }
+                    acc = 1u;
+                  }
+                  umma_commit(b_empty0 + sb * 8);
+                }
+              } else if (elect_one()) {
                 uint32_t acc = accumulate;
                 for (int t = 0; t < ntap; ++t, a_lo += WP * (ROW_BYTES >> 4)) {
                   for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo) {
@@ -676,8 +734,8 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       const int bi = t / tpi, rem = t - bi * tpi;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int sid = p.sample_id[bi];
-      const int y = ty * TILE_H + r, x = (tx * MT + mt) * TILE_W + cx;
-      const bool valid = (y < p.H) && (x < p.W);
+      const int y = p.pair_rows ? ty * (TILE_H - 1) - 1 + r : ty * TILE_H + r, x = (tx * MT + mt) * TILE_W + cx;
+      const bool valid = (y < p.H) && (x < p.W) && !(p.pair_rows && r == 0);
       const size_t pix = ((size_t)sid * p.H + y) * p.W + x;
       if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; out->wg = g; out->m = m; }
       return valid ? (long long)pix : -1;

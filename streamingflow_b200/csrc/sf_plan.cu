@@ -198,7 +198,11 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.W = p->g.W;
   const int MT = sf::mtiles_for(st.epi, p->g.C);
   sp.tiles_x = (p->g.W + TILE_W * MT - 1) / (TILE_W * MT);
-  sp.tiles_y = (p->g.H + TILE_H - 1) / TILE_H;
+  const bool pair = (st.flags & 512) != 0;
+  const int tile_rows = pair ? TILE_H - 1 : TILE_H;          // row-paired taps: lane row 0 of a tile is the row above its 15 output rows
+  sp.tiles_y = (p->g.H + tile_rows - 1) / tile_rows;
+  sp.pair_rows = pair ? 1 : 0;
+  sp.wg_scratch = pair ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH;
   sp.n_active = ev->n_active;
   const int n = ev->n_active;
   const int32_t* rows = table + ev->table_off;
@@ -514,6 +518,11 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
     int tb = B_TILE_MAX / tap_bytes;
     if (tb < 1) tb = 1;
     if (tb > c.R) tb = c.R;
+    if (flags & 512) {        // row-paired taps: one B tile = one pair of vertically adjacent taps
+      if (epilogue != SF_EPI_LNGELU || p->g.C != 64 || c.n != 64 || c.col != 0 || c.R < 2)
+        return fail(SF_ERR_INVALID, "row-paired taps need the lngelu epilogue, 64 channels and n = 64 chunks at column 0");
+      tb = 2;
+    }
     st.tb.push_back(tb);
     const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
     a_slot = a > a_slot ? a : a_slot;
@@ -528,7 +537,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.flags = flags;
   st.n_out = 0;
   for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
-  const int fixed = 1024 + (sf::VEC_MAX + 4 * sf::WG_SCRATCH) * 4 + BAR_AREA;
+  const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA;
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
   // activation ring: one slot = one chunk's tile + halo (3 slots when they leave room for >= 2 weight slots);
   // weight ring: everything that is left, up to MAX_RING slots

@@ -14,6 +14,7 @@ Weight sources (reference parameter names) -> conv stages (SURVEY.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -68,7 +69,7 @@ class StageDef:
         return self
 
 
-def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
+def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True) -> List[StageDef]:
     """The conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters; C = 64 or 128."""
     g = lambda k: sd[f"{p}.{k}"].float()
     C_ = g("conv_update_1.weight").shape[0]
@@ -99,7 +100,9 @@ def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str) -> List[StageDef]:
     out.append(StageDef("decode", L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B]).add(BUF_HH, g("conv_decoder_2.weight"), 0, 1))
     t = "trusting_gate.0."
     w7 = g(t + "layers.0.weight")
-    out.append(StageDef("trunk7", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1])
+    # 64 channels: vertically adjacent taps of the 7x7 conv are paired into N = 128 MMAs (the MMA issue cost is ~41 + N/2 cycles)
+    out.append(StageDef("trunk7", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1],
+                        flags=L.FLAG_PAIR_ROWS if (C_ == 64 and pair_rows) else 0)
                .add(BUF_A, w7[:, :C_], 0, 1).add(BUF_B, w7[:, C_:], 0, 0))
     out.append(StageDef("trunk1", L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
                .add(BUF_T1, g(t + "layers.3.weight"), 0, 1))
@@ -167,9 +170,22 @@ def pack_stage_master(sdef: StageDef, x3: bool):
     return torch.cat(blocks, 0).contiguous(), torch.cat(meta, 0).contiguous()
 
 
+def _pair_order(R: int) -> List[int]:
+    """dy order of a dx column with row-paired taps: [1, 0, 3, 2, ..., R-1 alone when R is odd]."""
+    order = []
+    for g in range(R // 2):
+        order += [2 * g + 1, 2 * g]
+    if R % 2:
+        order.append(R - 1)
+    return order
+
+
 def pack_stage(sdef: StageDef, x3: bool):
     """Packs a stage's weights into the [rows, 64] bf16 matrix the TMA weight ring streams, in consumption order:
-    chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed)."""
+    chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed).
+    Row-paired stages (FLAG_PAIR_ROWS): chunk -> dx -> pair -> rep -> [tap_hi n rows | tap_lo n rows]."""
+    if sdef.flags & L.FLAG_PAIR_ROWS:
+        return _pack_stage_paired(sdef, x3)
     chunks, blocks, row = [], [], 0
     for buf, c0, w, col, init, ox, oy in sdef.chunks:
         n, _, R, _ = w.shape
@@ -191,12 +207,77 @@ def pack_stage(sdef: StageDef, x3: bool):
     return chunks, torch.cat(blocks, 0).contiguous()
 
 
+def _pack_stage_paired(sdef: StageDef, x3: bool):
+    chunks, blocks, row = [], [], 0
+    for buf, c0, w, col, init, ox, oy in sdef.chunks:
+        n, _, R, _ = w.shape
+        order = _pair_order(R)
+        groups = [order[i:i + 2] for i in range(0, R - R % 2, 2)] + ([[order[-1]]] if R % 2 else [])
+        taps = w.permute(3, 2, 0, 1).contiguous()                  # [dx, dy, n, 64]
+        hi = taps.to(torch.bfloat16)
+        lo = (taps - hi.float()).to(torch.bfloat16)
+        reps = [hi, lo] if x3 else [hi]
+        rows = []
+        for dx in range(R):
+            for grp in groups:
+                for plane in reps:
+                    for dy in grp:
+                        rows.append(plane[dx, dy])
+        chunks.append(dict(buf=buf, plane=0, c0=c0, R=R, n=n, nrep=len(reps), col=col, wrow=row, init=init, ox=ox, oy=oy))
+        blocks.append(torch.cat(rows, 0))
+        row += R * R * len(reps) * n
+        if x3:                                                      # lo plane of the activations x hi weights
+            rows = [hi[dx, dy] for dx in range(R) for grp in groups for dy in grp]
+            chunks.append(dict(buf=buf, plane=1, c0=c0, R=R, n=n, nrep=1, col=col, wrow=row, init=0, ox=ox, oy=oy))
+            blocks.append(torch.cat(rows, 0))
+            row += R * R * n
+    return chunks, torch.cat(blocks, 0).contiguous()
+
+
+def _emulate_paired(sdef: StageDef, x3: bool, sources: Dict[int, torch.Tensor]) -> torch.Tensor:
+    """Host replay of a row-paired stage exactly as the kernel runs it: per dx column and pair, ONE product of the dy_hi window
+    with the [tap_hi | tap_lo] rows; the tap_lo half lands one row above its pixel and is folded back one row down (the
+    epilogue's block-1 shift), with the virtual row above the image computed like the kernel's scratch row."""
+    import torch.nn.functional as F
+
+    chunks, wp = pack_stage(sdef, x3)
+    wp = wp.double()
+    H, W = next(iter(sources.values())).shape[-2:]
+    n = chunks[0]["n"]
+    blk0 = torch.zeros(n, H + 1, W, dtype=torch.float64)           # virtual rows -1 .. H-1
+    blk1 = torch.zeros(n, H + 1, W, dtype=torch.float64)
+    for ck in chunks:
+        x = sources[ck["buf"]][0, ck["c0"]:ck["c0"] + 64].double()
+        xh = x.to(torch.bfloat16).double()
+        x = (xh if ck["plane"] == 0 else (x - xh).to(torch.bfloat16).double()) if x3 else xh
+        R, nrep = ck["R"], ck["nrep"]
+        pad = (R - 1) // 2
+        xp = F.pad(x, (pad, pad, pad + 1, pad))                      # one extra row on top: virtual row -1 reads rows -1-pad ..
+        order = _pair_order(R)
+        groups = [order[i:i + 2] for i in range(0, R - R % 2, 2)] + ([[order[-1]]] if R % 2 else [])
+        r0 = ck["wrow"]
+        for dx in range(R):
+            for grp in groups:
+                win = xp[:, grp[0]:grp[0] + H + 1, dx:dx + W]       # window of dy_hi for virtual rows -1 .. H-1
+                for rep in range(nrep):
+                    for t, dy in enumerate(grp):
+                        wt = wp[r0:r0 + n]
+                        r0 += n
+                        prod = torch.einsum("nc,chw->nhw", wt, win)
+                        (blk0 if t == 0 else blk1).add_(prod)
+    acc = torch.zeros(256, H, W, dtype=torch.float64)
+    acc[:n] = blk0[:, 1:] + blk1[:, :-1]                             # out[v] = block0[v] + block1[v - 1]
+    return acc
+
+
 def emulate_stage(sdef: StageDef, x3: bool, sources: Dict[int, torch.Tensor]) -> torch.Tensor:
     """Numerically replays the packed plan on the host (pure indexing of the packed matrix, fp64 products): the
     accumulator columns [pixels..., 256] the tensor core would produce.  Used by CPU tests to pin the packing and
     the chunk / tap / column bookkeeping against F.conv2d without a GPU.  sources[buf] is NCHW [1, Cbuf, H, W]."""
     import torch.nn.functional as F
 
+    if sdef.flags & L.FLAG_PAIR_ROWS:
+        return _emulate_paired(sdef, x3, sources)
     chunks, wp = pack_stage(sdef, x3)
     wp = wp.double()
     any_src = next(iter(sources.values()))
@@ -323,7 +404,8 @@ class OdeEngine:
         self._keep = []
         self.stage_defs: Dict[int, StageDef] = {}
         self.stage_names: Dict[int, str] = {}
-        cells = [cell_stage_defs(sd, pre + "gru_c"), cell_stage_defs(sd, pre + "gru_obs.gru_d")]
+        pair = os.environ.get("SF_PAIR_ROWS", "1") != "0"
+        cells = [cell_stage_defs(sd, pre + "gru_c", pair), cell_stage_defs(sd, pre + "gru_obs.gru_d", pair)]
         n_cell = len(cells[0])
         cell_slots = [list(range(ws * n_cell, (ws + 1) * n_cell)) for ws in range(2)]
         for ws in range(2):
