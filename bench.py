@@ -180,7 +180,7 @@ def workload_config(args, hw, batch):
                          f"observations (8 jumps + 10 variable Euler state-steps per sample), ODE grid {hw}x{hw}x64 "
                          f"({'cell-level: the literal 200x200x64 state' if args.grid == 'cell' else 'module-level latent of a 200x200x64 BEV'})",
                 grid=args.grid, batch_per_gpu=batch, precision=args.precision, solver="euler", variable_step=True, impute=True,
-                launch="eager" if getattr(args, "no_graph", True) else "one CUDA graph per rollout (pack + noise + stages + gather)",
+                launch="eager" if getattr(args, "no_graph", True) else "one CUDA graph per rollout (all stage launches); layout pack, one-launch noise draw and gathers eager around it",
                 l2="inputs + workspace (>1 GB at 200x200, B=8) exceed the 126 MB L2; no explicit flush" if hw >= 200 else
                    "working set fits L2 (module-level latent): L2 flushed by a 256 MB memset between steps",
                 parallelism=f"batch-sharded x{args.gpus}, no collective in the data path")
