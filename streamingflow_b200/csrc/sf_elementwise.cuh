@@ -202,54 +202,77 @@ __global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ 
 // Slot s (blockIdx.y) is filled exactly as the s-th of a sequence of torch normal_() calls on a numel-element CUDA float tensor
 // would fill it: same thread -> element mapping (element idx + T * (4 k + i) comes from component i of thread idx's k-th
 // curand_normal4 draw, T = gridDim.x * 256), same Philox4_32_10 subsequence (= thread index) and offset (offset0 + s * per_slot).
+// curand_init(seed, idx, offset) followed by k curand_normal4 draws evaluates Philox at counter (offset / 4 + k) of subsequence
+// idx (offset is a multiple of 4 here: ATen advances it by 4 per loop iteration); curand itself evaluates two extra blocks per
+// thread (one in each skipahead, one look-ahead per draw), so the counters are formed directly.
 __global__ void __launch_bounds__(256) normal_slots_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
-                                                           unsigned long long offset0, unsigned int per_slot) {
+                                                           unsigned long long offset0, unsigned int per_slot, int n_slots) {
   const unsigned int idx = blockIdx.x * 256u + threadIdx.x;
-  curandStatePhilox4_32_10_t state;
-  curand_init(seed, idx, offset0 + (unsigned long long)blockIdx.y * per_slot, &state);
+  const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
   const long long T = (long long)gridDim.x * 256;
   const long long rounded = ((numel - 1) / (T * 4) + 1) * T * 4;
-  float* o = out + (long long)blockIdx.y * numel;
-  for (long long li = idx; li < rounded; li += T * 4) {
-    const float4 r = curand_normal4(&state);
-    const float v[4] = {r.x, r.y, r.z, r.w};
+  for (int slot = blockIdx.y; slot < n_slots; slot += gridDim.y) {      // a block walks several slots: fewer, longer-lived blocks
+    unsigned long long ctr = (offset0 + (unsigned long long)slot * per_slot) >> 2;
+    float* o = out + (long long)slot * numel;
+    for (long long li = idx; li < rounded && li < numel; li += T * 4, ++ctr) {      // li >= numel: none of the 4 outputs is stored
+      const uint4 x = curand_Philox4x32_10(make_uint4((unsigned int)ctr, (unsigned int)(ctr >> 32), idx, 0u), key);
+      const float2 a = _curand_box_muller(x.x, x.y), b = _curand_box_muller(x.z, x.w);      // = curand_normal4
+      const float v[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long l = li + T * i;
-      if (l < numel) o[l] = v[i];
+      for (int i = 0; i < 4; ++i) {
+        const long long l = li + T * i;
+        if (l < numel) o[l] = v[i];
+      }
     }
   }
 }
 
 // ---- NCHW fp32 -> NHWC bf16 (hi [+ lo]) : encoded observations entering the ODE loop ---------------------
-// block = 256 threads handles 32 consecutive pixels x 64 channels of one image through a padded smem tile.
+// block = 256 threads handles 64 consecutive pixels x 64 channels of one image through a padded smem tile: 16 scalar loads
+// in flight per thread (each warp-load = 128 contiguous bytes of one channel row), two 16-byte NHWC stores per thread.
+constexpr int PACK_PX = 64;
 template <bool X3>
 __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dh,
                                                         __nv_bfloat16* __restrict__ dl, int C, int hw) {
-  __shared__ float tile[64][33];
-  const int img = blockIdx.z, cb = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  __shared__ float tile[64][PACK_PX + 1];
+  const int img = blockIdx.z, cb = blockIdx.y * 64, p0 = blockIdx.x * PACK_PX;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int c = w; c < 64; c += 8) {
-    const int px = p0 + lane;
-    tile[c][lane] = (px < hw) ? src[((size_t)img * C + cb + c) * hw + px] : 0.0f;
+  float v[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* row = src + ((size_t)img * C + cb + w + 8 * k) * hw + p0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int px = lane + 32 * h;
+      v[k][h] = (p0 + px < hw) ? __ldg(row + px) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    tile[w + 8 * k][lane] = v[k][0];
+    tile[w + 8 * k][lane + 32] = v[k][1];
   }
   __syncthreads();
-  // 32 pixels x 8 groups of 8 channels = 256 work items
-  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
-  if (p0 + px < hw) {
-    float f[8];
+  // 64 pixels x 8 groups of 8 channels = 512 work items, two per thread
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = tile[g * 8 + i][px];
-    uint32_t h[4];
+  for (int it = 0; it < 2; ++it) {
+    const int item = threadIdx.x + 256 * it;
+    const int px = item >> 3, g = item & 7;
+    if (p0 + px < hw) {
+      float f[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-    const size_t off = ((size_t)img * hw + p0 + px) * C + cb + g * 8;
-    *reinterpret_cast<uint4*>(dh + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (X3) {
-      uint32_t l[4];
+      for (int i = 0; i < 8; ++i) f[i] = tile[g * 8 + i][px];
+      uint32_t h[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
-      *reinterpret_cast<uint4*>(dl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      for (int i = 0; i < 4; ++i) h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      const size_t off = ((size_t)img * hw + p0 + px) * C + cb + g * 8;
+      *reinterpret_cast<uint4*>(dh + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (X3) {
+        uint32_t l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(h[i]), f[2 * i + 1] - bf16_hi_f(h[i]));
+        *reinterpret_cast<uint4*>(dl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
   }
 }

@@ -641,7 +641,7 @@ int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* t
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream) {
   if (!src || !dst_hi || C % 64 || n_images <= 0) return fail(SF_ERR_INVALID, "bad pack arguments");
   const int hw = H * W;
-  dim3 grid((hw + 31) / 32, C / 64, n_images);
+  dim3 grid((hw + PACK_PX - 1) / PACK_PX, C / 64, n_images);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dst_lo)
     pack_nchw_kernel<true><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_hi), reinterpret_cast<__nv_bfloat16*>(dst_lo), C, hw);
@@ -676,7 +676,11 @@ int sf_normal_policy(long long numel, int device, int* grid, int* offset_per_slo
 int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long long seed, unsigned long long offset0, int grid,
                          int offset_per_slot, void* stream) {
   if (!out || n_slots <= 0 || numel <= 0 || grid <= 0 || offset_per_slot <= 0 || n_slots > 65535) return fail(SF_ERR_INVALID, "bad normal fill arguments");
-  normal_slots_kernel<<<dim3(grid, n_slots), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot);
+  if ((offset0 & 3) || (offset_per_slot & 3)) return fail(SF_ERR_INVALID, "Philox offsets must be multiples of 4 (ATen's generator invariant)");
+  // about 8 waves of resident blocks in total; each block row walks n_slots / grid.y slots
+  int rows = (8 * 148 * 8 + grid - 1) / grid;
+  if (rows > n_slots) rows = n_slots;
+  normal_slots_kernel<<<dim3(grid, rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot, n_slots);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
