@@ -34,7 +34,8 @@ counts = [8] * B
 g = torch.Generator().manual_seed(seed)
 hx = torch.tanh(torch.randn(sum(counts), C, H, W, generator=g)).to(dev)
 tape = torch.randn(18 * B, C, H, W, generator=g).to(dev)
-sharded = RowShardedOde(m, H, W, B)
+use_graphs = not (len(sys.argv) > 6 and sys.argv[6] == "eager")
+sharded = RowShardedOde(m, H, W, B, use_graphs=use_graphs)
 with torch.no_grad():
     band, ro = sharded.integrate(hx, counts, times, targets, 0.05, noise=tape)
     torch.cuda.synchronize()
@@ -56,5 +57,6 @@ with torch.no_grad():
         err = ((full.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
         print(json.dumps(dict(test="row_sharding", world=world, H=H, W=W, B=B, C=C, precision=precision, max_rel_err=err,
                               ms_sharded=1e3 * dt_sharded, ms_single_gpu=1e3 * dt_single, events=len(ro.events),
-                              halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo)), flush=True)
+                              halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo,
+                              launch="graph segments" if use_graphs else "eager")), flush=True)
 dist.destroy_process_group()
