@@ -22,8 +22,8 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 2000000000LL) return false;
   return true;
 }
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr, uint32_t sbo = 1024u) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ uint32_t idesc_bf16(uint32_t M, uint32_t N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int mode, int nacc,
         for (int k = 0; k < 4; ++k) {
           // consecutive MMAs rotate over nacc independent accumulators (dependent MMAs on one accumulator serialise)
           const uint32_t d = tmem + (uint32_t)(((t * 4 + k) & (nacc - 1)) * N);
-          if (mode == 0) mma_ss<CTAS>(d, sw128_desc(a0 + t * 1024 * 3) + 2 * k, bdesc + 2 * k, idesc, it ? 1u : 0u);
+          if (mode == 2)        // the conv kernel's A operand: 8-row groups 18 pixel rows apart (halo box of a 16-wide tile), tap-shifted start
+            mma_ss<CTAS>(d, sw128_desc(a0 + (t * 18 + t + 1) * 128, 18 * 128) + 2 * k, bdesc + (uint64_t)(t * 512) + 2 * k, idesc, it ? 1u : 0u);
+          else if (mode == 0) mma_ss<CTAS>(d, sw128_desc(a0 + t * 1024 * 3) + 2 * k, bdesc + 2 * k, idesc, it ? 1u : 0u);
           else mma_ts<CTAS>(d, a_tmem, bdesc + 2 * k, idesc, it ? 1u : 0u);
         }
       }
@@ -162,7 +164,7 @@ void run(int N, int mode, int nacc, int grid, int iters, long long* d_out, int* 
   const double cyc = (double)h[0] / mmas;
   const double flops = 2.0 * 128 * CTAS * N * 16 * mmas * (grid / CTAS);
   printf("cta_group::%d  %s  N=%3d nacc=%d grid=%3d : %7.1f cycles/MMA (ideal %5.1f) -> tensor %5.1f %%   chip %7.1f TFLOP/s  [%s]\n", CTAS,
-         mode ? "A=tmem" : "A=smem", N, nacc, grid, cyc, N / 2.0, 100.0 * (N / 2.0) / cyc, flops / (ms * 1e-3) / 1e12, st ? "TIMEOUT" : "ok");
+         mode == 1 ? "A=tmem" : mode == 2 ? "A=smem conv-window" : "A=smem", N, nacc, grid, cyc, N / 2.0, 100.0 * (N / 2.0) / cyc, flops / (ms * 1e-3) / 1e12, st ? "TIMEOUT" : "ok");
 }
 
 int main() {
@@ -177,6 +179,7 @@ int main() {
           if (grid == 148 && nacc * 2 * N <= (mode ? 256 : 512) && nacc < 8) continue;     // full grid: widest rotation only
           run<1>(N, mode, nacc, grid, iters, d_out, d_status);
         }
+  for (int N : {64, 128, 256}) run<1>(N, 2, 2, 148, iters, d_out, d_status);
   for (int grid : {2, 148})
     for (int mode = 0; mode < 2; ++mode)
       for (int N : {64, 128, 256})

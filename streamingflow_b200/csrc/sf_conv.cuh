@@ -82,6 +82,7 @@ struct alignas(64) StageParams {
   const float* vec;
   int nvec;
   int a_slot_bytes, b_slot_bytes, nA, nB;
+  int debug;                 // experiments (SF_DEBUG_STAGE): 1 = epilogues skipped, 2 = MMAs skipped, 4 = operand loads skipped
   int pair_rows;             // 1: vertically adjacent taps are paired into one MMA of twice the width (see conv_stage_kernel)
   int wg_scratch;            // floats of shared scratch per epilogue warpgroup
   int w_rows_per_sample;     // > 0: per-sample weights (SE layer folded in): active sample bi reads rows [bi * this, (bi+1) * this)
@@ -590,7 +591,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
           const int img = ck.img_sel ? ximg : sid;
           // the tile + halo of this chunk: one box, all taps read it through shifted descriptors
           mbar_wait(a_empty0 + sa * 8, pa, p.err, 1);
-          if (elect_one()) {
+          if (p.debug & 4) {
+            if (elect_one()) mbar_arrive(a_full0 + sa * 8);
+          } else if (elect_one()) {
             mbar_expect_tx(a_full0 + sa * 8, (uint32_t)a_box_bytes(R, MT));
             tma_load_4d(a_smem0 + sa * p.a_slot_bytes, &p.amap[c], a_full0 + sa * 8, ck.c0, x0 - pad + ck.ox, y0 - pad + ck.oy, img);
           }
@@ -605,7 +608,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
               const int ntap = min(ck.tb, R - gi * ck.tb);
               const int grp_rows = tap_rows * ntap;             // rows of this B tile
               mbar_wait(b_empty0 + sb * 8, pb, p.err, 2);
-              if (elect_one()) {
+              if (p.debug & 4) {
+                if (elect_one()) mbar_arrive(b_full0 + sb * 8);
+              } else if (elect_one()) {
                 mbar_expect_tx(b_full0 + sb * 8, (uint32_t)grp_rows * ROW_BYTES);
                 int row = ck.wrow + (dx * R + gi * ck.tb) * tap_rows + bi * p.w_rows_per_sample;
                 uint32_t dst = b_smem0 + sb * p.b_slot_bytes;
@@ -657,7 +662,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
               // first tap of this group: dy = gi*tb; one pixel row = 128 B = 8 descriptor units
               uint32_t a_lo = a_lo0 + ((uint32_t)(gi * ck.tb) * WP + (uint32_t)dx) * (ROW_BYTES >> 4);
               const int ntap = min(ck.tb, R - gi * ck.tb);
-              if (p.pair_rows) {
+              if (p.debug & 2) {
+                if (elect_one()) umma_commit(b_empty0 + sb * 8);
+              } else if (p.pair_rows) {
                 // Row-paired taps.  This B tile holds the taps dy = gi*tb .. gi*tb + ntap - 1 of column dx as ONE operand of
                 // n * ntap rows per rep, ordered [dy_hi | dy_lo]; a single MMA per K step, on the window of dy_hi, produces the
                 // dy_hi term of its own pixel in column block 0 and the dy_lo term of the pixel one row below in block 1 (the
@@ -746,7 +753,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
       bool released = false;
-      if (mine) released = run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c, smem_u32(acc_empty + st));
+      if (mine && !(p.debug & 1)) released = run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c, smem_u32(acc_empty + st));
       if (!released) {
         tc_fence_before();
         mbar_arrive(smem_u32(acc_empty + st));

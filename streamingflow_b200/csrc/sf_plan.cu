@@ -218,6 +218,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.nA = st.nA;
   sp.nB = st.nB;
   sp.w_rows_per_sample = st.fold_se >= 0 ? st.w_rows : 0;
+  { const char* v = getenv("SF_DEBUG_STAGE"); sp.debug = v ? atoi(v) : 0; }
   sp.err = reinterpret_cast<int*>(p->f32[SF_F32_COUNT]);
   EpiArgs& e = sp.e;
   e.kind = ev->kind;
