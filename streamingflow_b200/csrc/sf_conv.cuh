@@ -259,7 +259,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
         float s[16], u[NP][16];
-        if (c.valid && !(p.debug & 16)) {
+        if (c.valid) {
           load_f32x16(e.s_in + pc + j * 16, s);
 #pragma unroll
           for (int k = 0; k < NP; ++k) load_act16<X3>(e.in_h[k], e.in_l[k], pc + j * 16, u[k]);
@@ -275,7 +275,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
           vec16(vec, k * CG + j * 16, b);
 #pragma unroll
           for (int i = 0; i < 16; ++i) t[i] = (1.0f - u[k][i]) * s[i] + u[k][i] * (t[i] + b[i]);
-          if (c.valid && !(p.debug & 32)) {
+          if (c.valid) {
             if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
             store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);
           }
