@@ -145,12 +145,20 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)
 
 // 256-bit global accesses (sm_100: LDG/STG.256): one full 32-byte sector per thread per instruction
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  // L1::no_allocate: every epilogue / streaming access touches its bytes once; keeping them out of the (small, shared-memory
+  // sized-down) L1 is worth 5 % of the whole rollout (A/B on one box; SF_LDG_QUAL / SF_STG_QUAL override for experiments)
+#ifndef SF_LDG_QUAL
+#define SF_LDG_QUAL ".L1::no_allocate"
+#endif
+#ifndef SF_STG_QUAL
+#define SF_STG_QUAL ".L1::no_allocate"
+#endif
+  asm volatile("ld.global" SF_LDG_QUAL ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
 }
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+  asm volatile("st.global" SF_STG_QUAL ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
