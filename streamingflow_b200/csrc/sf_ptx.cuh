@@ -187,19 +187,21 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }   // MUFU.EX2 + MUFU.RCP
-// exact (erf) GELU, nn.GELU() default.  erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below both precision
-// contracts): ~16 instructions instead of erff's ~30 -- the LN+GELU epilogues are instruction-issue bound.
-__device__ __forceinline__ float erf_as(float x) {
+// exact (erf) GELU, nn.GELU() default, via erfc: with z = |x| / sqrt(2) and Abramowitz & Stegun 7.1.26
+//   erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z)      (|error| <= 1.5e-7, far below both precision contracts)
+// GELU(x) = max(x, 0) - g,  g = 0.5 |x| erfc(z)   (x >= 0: x - 0.5 x erfc;  x < 0: 0.5 x erfc(|x|/sqrt 2) = -g).
+// 14 FP32 instructions + MUFU.RCP + MUFU.EX2; the LN+GELU epilogues are instruction-issue bound.
+__device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-ax * ax);
-  return copysignf(e, x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);        // 0.5 folded into the coefficients
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  float e;                                                             // exp(-z^2) = 2^(-x^2 log2(e) / 2): one MUFU.EX2
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * (-0.5f * 1.4426950408889634f)));
+  return fmaxf(x, 0.0f) - (q * t) * (e * ax);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float lrelu01(float x) { return x > 0.0f ? x : 0.1f * x; }
 __device__ __forceinline__ float softplus_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }   // F.softplus(beta=1, threshold=20)
 
