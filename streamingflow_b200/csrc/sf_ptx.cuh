@@ -203,7 +203,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaxf(x, 0.0f) - (q * t) * (e * ax);
 }
 __device__ __forceinline__ float lrelu01(float x) { return x > 0.0f ? x : 0.1f * x; }
-__device__ __forceinline__ float softplus_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }   // F.softplus(beta=1, threshold=20)
+// F.softplus(beta=1, threshold=20) = log(1 + e^x) (x itself above 20), evaluated as max(x, 0) + log(1 + e^-|x|) with the MUFU
+// exp / log: ~8 instructions instead of ~35 for log1pf(expf(x)).  Absolute error <= ~2e-7 (1 + e^-|x| is rounded to fp32 before
+// the log), far below both precision contracts (the value scales unit-variance noise); above 20 it returns x exactly like torch.
+__device__ __forceinline__ float softplus_(float x) { return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x))); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
