@@ -241,7 +241,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             u[i] = sigmoidf_(u[i] + bu[i]);
-            r[i] = (1.0f - sigmoidf_(r[i] + br[i])) * s[i];
+            r[i] = one_minus_sigmoidf_(r[i] + br[i]) * s[i];
           }
           if (c.valid) {
             store_act16<X3>(e.out_h[2 * g], e.out_l[2 * g], pc + j * 16, u);
@@ -274,7 +274,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
           tmem_ld16(taddr + k * CG + j * 16, t);
           vec16(vec, k * CG + j * 16, b);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) t[i] = (1.0f - u[k][i]) * s[i] + u[k][i] * (t[i] + b[i]);
+          for (int i = 0; i < 16; ++i) t[i] = fmaf(u[k][i], (t[i] + b[i]) - s[i], s[i]);      // (1 - u) s + u s~
           if (c.valid) {
             if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
             store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);

@@ -186,7 +186,10 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 }
 
 // ---------------------------------------------------------------- small math helpers
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }   // MUFU.EX2 + MUFU.RCP
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_approx(1.0f + __expf(-x)); }          // MUFU.EX2 + MUFU.RCP
+// 1 - sigmoid(x) = sigmoid(-x) = 1 / (1 + e^x), without forming the sigmoid first
+__device__ __forceinline__ float one_minus_sigmoidf_(float x) { return rcp_approx(1.0f + __expf(x)); }
 // exact (erf) GELU, nn.GELU() default, via erfc: with z = |x| / sqrt(2) and Abramowitz & Stegun 7.1.26
 //   erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z)      (|error| <= 1.5e-7, far below both precision contracts)
 // GELU(x) = max(x, 0) - g,  g = 0.5 |x| erfc(z)   (x >= 0: x - 0.5 x erfc;  x < 0: 0.5 x erfc(|x|/sqrt 2) = -g).
