@@ -148,6 +148,37 @@ def test_se_fold_master_matches_packing_of_scaled_weights(x3):
     assert plain[3].chunks[0][0] == en.BUF_Y1 and plain[6].chunks[0][0] == en.BUF_Y2 and plain[3].fold_se is None
 
 
+def test_row_paired_tap_packing_order_and_event_group_cap():
+    """Host logic of two kernel-side schemes: the dy order of row-paired taps (upper tap of each pair first, odd tap last), the
+    rows it produces, and the optional cap on the samples of a batched event (same ops, same noise slots, smaller groups)."""
+    from streamingflow_b200 import engine as en
+    from streamingflow_b200 import _lib as L
+
+    assert en._pair_order(7) == [1, 0, 3, 2, 5, 4, 6] and en._pair_order(3) == [1, 0, 2] and en._pair_order(2) == [1, 0]
+    w = torch.arange(64 * 64 * 7 * 7, dtype=torch.float32).reshape(64, 64, 7, 7) / 4096.0
+    sdef = en.StageDef("t", L.EPI_LNGELU, torch.zeros(128), [en.BUF_T1], flags=L.FLAG_PAIR_ROWS).add(en.BUF_A, w, 0, 1)
+    chunks, wp = en.pack_stage(sdef, False)
+    assert len(chunks) == 1 and chunks[0]["nrep"] == 1 and wp.shape == (49 * 64, 64)
+    for dx in (0, 3, 6):
+        for slot, dy in enumerate(en._pair_order(7)):
+            rows = wp[(dx * 7 + slot) * 64:(dx * 7 + slot + 1) * 64].float()
+            assert torch.equal(rows, w[:, :, dy, dx].to(torch.bfloat16).float())
+    chunks3, wp3 = en.pack_stage(sdef, True)          # split mode: [pair][rep (hi, lo)][tap] rows, then the lo-plane chunk
+    assert [c["nrep"] for c in chunks3] == [2, 1] and wp3.shape[0] == 49 * 64 * 3
+    hi = w[:, :, 1, 0].to(torch.bfloat16)
+    assert torch.equal(wp3[:64], hi) and torch.equal(wp3[64:128], w[:, :, 0, 0].to(torch.bfloat16))                 # rep hi: dy 1 | dy 0
+    assert torch.equal(wp3[128:192], (w[:, :, 1, 0] - hi.float()).to(torch.bfloat16))                                 # rep lo: dy 1 ...
+
+    times, tg = [-1.0, -0.5, 0.0], [-1.0, -0.5, 0.0, 0.5, 1.0]
+    plans = [sc.plan_sample(times, tg, 0.05, True, "euler") for _ in range(5)]
+    whole = compile_rollout(plans, [0, 3, 6, 9, 12], "euler", True)
+    capped = compile_rollout(plans, [0, 3, 6, 9, 12], "euler", True, max_group=2)
+    assert all(len(e["samples"]) <= 2 for e in capped.events) and len(capped.events) == 3 * len(whole.events)
+    assert capped.n_eps == whole.n_eps and capped.n_state_steps == whole.n_state_steps and capped.out_slots == whole.out_slots
+    flat = lambda ro, k: sorted((b, v) for e in ro.events for b, v in zip(e["samples"], e[k]))
+    assert flat(capped, "eps") == flat(whole, "eps") and flat(capped, "rec") == flat(whole, "rec")
+
+
 def _tiny_module(z, dtype):
     from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
 
