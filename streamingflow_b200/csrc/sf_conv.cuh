@@ -17,7 +17,12 @@
 //   pull the same weight tile from L2 at once.
 // Warp roles: warps [0, 8*MT) = epilogue warpgroups (one thread per pixel: its TMEM lane holds all output channels of that
 //   pixel, so LayerNorm / softmax-mix / GRU blends are thread-local), then TMA producer (one lane), MMA issuer (one lane),
-//   TMEM allocator.  Persistent over tiles, static round-robin.
+//   TMEM allocator.  Persistent over work items, static round-robin: whole tiles, then (when the last wave would leave more
+//   than half of the CTAs idle) single M-tiles.
+// Row-paired taps (the 7x7 trunk at 64 channels): vertically adjacent taps share one MMA of twice the width; the epilogue
+//   folds the second column block back one row (see the lngelu epilogue and the MMA issuer).
+// Epilogue global accesses are 256-bit with L1::no_allocate; a stage whose epilogue tail no longer reads TMEM hands the
+//   accumulator back early (mix).  Launches use programmatic dependent launch: the prologue runs under the previous stage's tail.
 #pragma once
 #include <type_traits>
 
