@@ -75,7 +75,8 @@ struct SeDef {
 
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_AREA = 512;
-constexpr int B_TILE_MAX = 24 * 1024;
+// weight tile (one ring slot) size cap: a whole dx column of taps travels as one tile when it fits (SF_B_TILE_MAX overrides, KB)
+const int B_TILE_MAX = [] { const char* v = getenv("SF_B_TILE_MAX"); return (v ? atoi(v) : 48) * 1024; }();
 
 }  // namespace
 
@@ -508,27 +509,41 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st = Stage();
   st.epi = epilogue;
   st.chunks.assign(chunks, chunks + n_chunks);
-  int a_slot = 0, b_slot = 0;
   for (const sf_chunk& c : st.chunks) {
     if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
     if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(epilogue, p->g.C)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
-    // a whole dx column of taps travels as ONE weight tile when it is small enough: fewer barrier round trips per MMA
-    const int tap_bytes = c.n * c.nrep * ROW_BYTES;
-    int tb = B_TILE_MAX / tap_bytes;
-    if (tb < 1) tb = 1;
-    if (tb > c.R) tb = c.R;
-    if (flags & 512) {        // row-paired taps: one B tile = one pair of vertically adjacent taps
-      if (epilogue != SF_EPI_LNGELU || p->g.C != 64 || c.n != 64 || c.col != 0 || c.R < 2)
-        return fail(SF_ERR_INVALID, "row-paired taps need the lngelu epilogue, 64 channels and n = 64 chunks at column 0");
-      tb = 2;
-    }
-    st.tb.push_back(tb);
-    const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * c.n * c.nrep * ROW_BYTES;
-    a_slot = a > a_slot ? a : a_slot;
-    b_slot = b > b_slot ? b : b_slot;
+    if ((flags & 512) && (epilogue != SF_EPI_LNGELU || p->g.C != 64 || c.n != 64 || c.col != 0 || c.R < 2))
+      return fail(SF_ERR_INVALID, "row-paired taps need the lngelu epilogue, 64 channels and n = 64 chunks at column 0");
   }
+  if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
+  const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA;
+  // Weight tiles: as many taps of a dx column per tile as the cap allows (fewer producer <-> issuer barrier round trips per MMA;
+  // measured: 48 KB tiles are worth 4 % of the rollout over 24 KB ones), shrunk until at least two weight slots fit next to
+  // the activation ring.  Activation ring: one slot = one chunk's tile + halo, 3 slots when they leave room, up to 4.
+  int a_slot = 0, b_slot = 0, nA = 0, nB = 0;
+  for (int cap = B_TILE_MAX;; cap -= 8 * 1024) {
+    st.tb.clear();
+    a_slot = b_slot = 0;
+    for (const sf_chunk& c : st.chunks) {
+      const int tap_bytes = c.n * c.nrep * ROW_BYTES;
+      int tb = cap / tap_bytes;
+      if (tb < 1) tb = 1;
+      if (tb > c.R) tb = c.R;
+      if (flags & 512) tb = 2;          // row-paired taps: one B tile = one pair of vertically adjacent taps
+      st.tb.push_back(tb);
+      const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
+      a_slot = a > a_slot ? a : a_slot;
+      b_slot = b > b_slot ? b : b_slot;
+    }
+    nA = (fixed + 3 * a_slot + 2 * b_slot <= SMEM_BUDGET) ? 3 : 2;
+    nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
+    if (nB > sf::MAX_RING) nB = sf::MAX_RING;
+    if (nB >= 2) break;
+    if (cap <= 8 * 1024) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
+  }
+  while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
   st.w = w_packed;
   st.w_rows = w_rows;
   st.vec = vec;
@@ -538,15 +553,6 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.flags = flags;
   st.n_out = 0;
   for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
-  const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA;
-  if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
-  // activation ring: one slot = one chunk's tile + halo (3 slots when they leave room for >= 2 weight slots);
-  // weight ring: everything that is left, up to MAX_RING slots
-  int nA = (fixed + 3 * a_slot + 2 * b_slot <= SMEM_BUDGET) ? 3 : 2;
-  int nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
-  if (nB > sf::MAX_RING) nB = sf::MAX_RING;
-  if (nB < 2) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
-  while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
   st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
   st.smem = fixed + nA * a_slot + nB * b_slot;
   int rc = encode_weight_map(w_packed, w_rows, &st.wmap);
