@@ -674,21 +674,25 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
                 // n * ntap rows per rep, ordered [dy_hi | dy_lo]; a single MMA per K step, on the window of dy_hi, produces the
                 // dy_hi term of its own pixel in column block 0 and the dy_lo term of the pixel one row below in block 1 (the
                 // epilogue folds block 1 back).  Twice the N per MMA for the 64-channel stages, whose issue cost is ~41 + N/2.
+                // (a tile may hold several pairs: tb is even, so the pairs inside it start at even tap offsets)
                 if (elect_one()) {
-                  const uint32_t a_pair = a_lo + (uint32_t)(ntap - 1) * WP * (ROW_BYTES >> 4);
-                  const uint32_t idesc_pair = make_idesc_bf16(128, (uint32_t)(ck.n * ntap));
                   uint32_t acc = accumulate;
-                  for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo * ntap) {
+                  for (int t0 = 0; t0 < ntap; t0 += 2) {
+                    const int m = min(2, ntap - t0);
+                    const uint32_t a_pair = a_lo + (uint32_t)(t0 + m - 1) * WP * (ROW_BYTES >> 4);
+                    const uint32_t idesc_pair = make_idesc_bf16(128, (uint32_t)(ck.n * m));
+                    for (int rep = 0; rep < ck.nrep; ++rep, b_lo += rep_lo * m) {
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) {
+                      for (uint32_t k = 0; k < 4; ++k) {
 #pragma unroll
-                      for (int mt = 0; mt < MT; ++mt) {
-                        if (MT > 1 && !((mtmask >> mt) & 1u)) continue;
-                        umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_pair + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
-                                  ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc_pair, acc | (k > 0 ? 1u : 0u));
+                        for (int mt = 0; mt < MT; ++mt) {
+                          if (MT > 1 && !((mtmask >> mt) & 1u)) continue;
+                          umma_bf16(d_addr + mt * SLOT_COLS, ((uint64_t)a_hi << 32) | (a_pair + mt * (TILE_W * ROW_BYTES >> 4) + 2 * k),
+                                    ((uint64_t)B_HI << 32) | (b_lo + 2 * k), idesc_pair, acc | (k > 0 ? 1u : 0u));
+                        }
                       }
+                      acc = 1u;
                     }
-                    acc = 1u;
                   }
                   umma_commit(b_empty0 + sb * 8);
                 }

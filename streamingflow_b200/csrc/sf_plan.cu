@@ -531,7 +531,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
       int tb = cap / tap_bytes;
       if (tb < 1) tb = 1;
       if (tb > c.R) tb = c.R;
-      if (flags & 512) tb = 2;          // row-paired taps: one B tile = one pair of vertically adjacent taps
+      if (flags & 512) tb = tb < 2 ? 2 : (tb & ~1);          // row-paired taps: a B tile = whole pairs of vertically adjacent taps
       st.tb.push_back(tb);
       const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
       a_slot = a > a_slot ? a : a_slot;
