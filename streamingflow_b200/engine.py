@@ -503,6 +503,23 @@ class OdeEngine:
         if lo is not None:
             lo.zero_()
 
+    def snapshot(self, n: int):
+        """Copies of everything an event reads from a previous one for the first n samples (state master + operand planes, the
+        sampled input's operand planes): StreamingOdeSession rolls a prediction forward and then restores them."""
+        keep = [self.state32[0][:n].clone()]
+        for buf in (BUF_S0, BUF_X):
+            keep += [None if p is None else p[:n].clone() for p in self.act[buf]]
+        return keep
+
+    def restore(self, snap, n: int):
+        self.state32[0][:n].copy_(snap[0])
+        k = 1
+        for buf in (BUF_S0, BUF_X):
+            for p in self.act[buf]:
+                if p is not None:
+                    p[:n].copy_(snap[k])
+                k += 1
+
     def unpack_path(self, slots, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Recorded states (NHWC fp32 path buffer) -> NCHW fp32 [len(slots), 64, H, W]."""
         idx = slots if isinstance(slots, torch.Tensor) else torch.tensor(list(slots), dtype=torch.int32, device=self.device)

@@ -55,6 +55,13 @@ class OracleBackend:
     def unpack_f32(self, t, n):
         return t[:n].clone()
 
+    def snapshot(self, n):
+        return [self.state[0][:n].clone(), self.x[:n].clone()]
+
+    def restore(self, snap, n):
+        self.state[0][:n] = snap[0]
+        self.x[:n] = snap[1]
+
     def run_rollout(self, events):
         for e in events:
             for j, b in enumerate(e["samples"]):

@@ -179,6 +179,57 @@ def test_row_paired_tap_packing_order_and_event_group_cap():
     assert flat(capped, "eps") == flat(whole, "eps") and flat(capped, "rec") == flat(whole, "rec")
 
 
+@pytest.mark.parametrize("solver,variable", [("euler", True), ("euler", False), ("midpoint", True)])
+def test_streaming_session_equals_the_one_shot_rollout(solver, variable):
+    """StreamingOdeSession (push each observation, then one non-destructive predict) executes the same operations, in the same
+    order and with the same noise, as integrate_latents over the whole history -- oracle standing in for the CUDA engine.
+    Covers an observation closer than delta_t to its predecessor (no step before its jump), a target at the last observation's
+    own time (served from the current state) and the +-delta_t/2 window; predict leaves the session where it was."""
+    from streamingflow_b200.layers.temporal_ode_bayes import NNFOwithBayesianJumps
+    from streamingflow_b200.streaming import StreamingOdeSession
+
+    C, h = 8, 6
+    m = NNFOwithBayesianJumps(C, C, make_cfg(C, solver=solver, variable=variable)).eval().double()
+    m.load_state_dict(so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 21, 1.5, torch.float64), strict=True)
+    m.__dict__["_engine_factory"] = lambda sd, H, W, n, prec, dev: OracleBackend(sd, H, W, n, prec, dev, torch.float64)
+    times = [-0.5, -0.35, -0.32, -0.1, 0.0]
+    targets = [0.0, 0.1, 0.25, 0.26, 0.5]
+    g = torch.Generator().manual_seed(5)
+    hx = torch.tanh(torch.randn(len(times), C, h, h, generator=g, dtype=torch.float64))
+    tape = torch.randn(200, C, h, h, generator=g, dtype=torch.float64)
+    m._draw_noise = lambda n, hh, ww, device: tape[:max(n, 1)].clone()
+    with torch.no_grad():
+        final, want = m.integrate_latents(hx, [len(times)], [times], [targets], 0.05)
+    used = {"off": 0}
+
+    def sequential(n, hh, ww, device):
+        a = used["off"]
+        used["off"] += n
+        return tape[a:a + max(n, 1)].clone()
+
+    m._draw_noise = sequential
+    with torch.no_grad():
+        sess = StreamingOdeSession(m, 1, h, h, 0.05, torch.device("cpu"))
+        for k, t in enumerate(times):
+            sess.push([t], hx[k:k + 1])
+        at_obs, clock = sess.state().clone(), list(sess.now)
+        got = sess.predict([targets])
+        assert torch.equal(sess.state(), at_obs) and sess.now == clock               # the look-ahead did not move the session
+        assert (got - want).abs().max() < 1e-12
+        assert used["off"] == m.last_rollout.n_eps                                   # same number of noise draws, same order
+        again = sess.predict([[0.5]])
+        assert again.shape == (1, 1, C, h, h) and torch.isfinite(again).all() and torch.equal(sess.state(), at_obs)
+        with pytest.raises(ValueError):
+            sess.push([-1.0], hx[:1])                                                # older than the session time
+    # two samples with different clocks advance together
+    with torch.no_grad():
+        s2 = StreamingOdeSession(m, 2, h, h, 0.05, torch.device("cpu"))
+        s2.push([-0.5, -0.4], hx[:2])
+        s2.push([-0.2, -0.4 + 0.03], hx[2:4])
+        out = s2.predict([[0.0, 0.5], [0.0, 0.5]])
+    assert out.shape == (2, 2, C, h, h) and torch.isfinite(out).all() and s2.now[1] == -0.4
+
+
 def _tiny_module(z, dtype):
     from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
 
