@@ -200,6 +200,42 @@ def test_streamed_host_buffer_rollout_equals_device_rollout():
     assert torch.equal(outs[1].transpose(0, 1), sel2.cpu()) and not torch.equal(outs[1], outs[0])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_streaming_session_equals_one_shot_rollout_on_device(precision):
+    """StreamingOdeSession on the CUDA engine: pushing the observations one by one and predicting once gives bit-identical
+    latents to integrate_latents over the whole history (same events, same noise); the look-ahead is non-destructive."""
+    from streamingflow_b200.streaming import StreamingOdeSession
+
+    m = _nnfo("euler", True, True, 9, 1.0, precision)
+    h = w = 24
+    times = [-1.0, -0.8, -0.6, -0.5, -0.4, -0.2, 0.0]
+    targets = [0.0, 0.5, 1.0, 1.5, 2.0]
+    hx = torch.tanh(so.recipe_array("hx", (len(times), 64, h, w), 9)).cuda()
+    tape = torch.stack([so.recipe_array(f"eps{i}", (64, h, w), 9) for i in range(40)]).cuda()
+    m._draw_noise = lambda n, hh, ww, device: tape[:max(n, 1)].contiguous()
+    with torch.no_grad():
+        _, want = m.integrate_latents(hx, [len(times)], [times], [targets], 0.05)
+    used = {"off": 0}
+
+    def sequential(n, hh, ww, device):
+        a = used["off"]
+        used["off"] += n
+        return tape[a:a + max(n, 1)].contiguous()
+
+    m._draw_noise = sequential
+    with torch.no_grad():
+        sess = StreamingOdeSession(m, 1, h, w, 0.05)
+        for k, t in enumerate(times):
+            sess.push([t], hx[k:k + 1])
+        at_obs = sess.state().clone()
+        got = sess.predict([targets])
+        torch.cuda.synchronize()
+        assert torch.equal(got, want) and torch.equal(sess.state(), at_obs) and used["off"] == m.last_rollout.n_eps
+        again = sess.predict([[0.5, 1.0]])                     # a second look-ahead from the same state, fresh noise
+        # the first step only sees the input sampled at the last jump: identical; the second one sees the new noise
+        assert torch.equal(sess.state(), at_obs) and torch.equal(again[0, 0], got[0, 1]) and torch.isfinite(again).all()
+
+
 @pytest.mark.parametrize("config", ["config3_streaming_40_steps", "config4_8s_horizon"])
 def test_long_rollout_configs_match_oracle(config):
     """BASELINE configs 3 and 4 as parity cases (small grid so the fp64 oracle finishes in seconds): config 3 = streaming
