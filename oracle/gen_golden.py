@@ -179,7 +179,6 @@ def gen_tiny_full(ref, out_dir):
 
 
 def gen_c64_latent(ref, out_dir):
-    C, H, seed, gain = 64, 32, 7, 1.0
     canon = sorted(CANON_CAM + CANON_LIDAR)
     variants = [
         ("euler_var", "euler", True, True, canon, CANON_TARGETS),
@@ -189,6 +188,17 @@ def gen_c64_latent(ref, out_dir):
         ("euler_var_jitter", "euler", True, True,
          sorted([-1.013, -0.492, -0.004, -0.81, -0.6, -0.418, -0.2, 0.011]), [-1.0, -0.5, 0.0, 0.49, 1.0, 1.52, 2.0]),
     ]
+    gen_latent(ref, out_dir, 64, 32, 7, variants)
+
+
+def gen_c128_latent(ref, out_dir):
+    """The 128-channel network of BASELINE config 5 (in_channels = latent_dim = OUT_CHANNELS = FILTER_SIZE = 128) on a small grid."""
+    canon = sorted(CANON_CAM + CANON_LIDAR)
+    gen_latent(ref, out_dir, 128, 16, 11, [("euler_var", "euler", True, True, canon, CANON_TARGETS),
+                                           ("midpoint_var", "midpoint", True, True, CANON_CAM, [0.0, 0.5, 1.0])])
+
+
+def gen_latent(ref, out_dir, C, H, seed, variants, gain=1.0):
     for tag, solver, variable, impute, times, targets in variants:
         res = {}
         for name, dtype in (("f64", torch.float64), ("f32", torch.float32)):
@@ -214,9 +224,9 @@ def gen_c64_latent(ref, out_dir):
                 res["dts"] = np.array([e[1] for e in tr.events])
                 res["n_eps"] = len(tape.tape)
                 res["encoded_f64"] = m.srvp_encoder(obs[0]).detach().to(torch.float32).numpy()
-        np.savez_compressed(os.path.join(out_dir, f"c64_latent_{tag}.npz"), C=C, H=H, seed=seed, gain=gain, solver=solver,
+        np.savez_compressed(os.path.join(out_dir, f"c{C}_latent_{tag}.npz"), C=C, H=H, seed=seed, gain=gain, solver=solver,
                             variable=variable, impute=impute, times=np.array(times), targets=np.array(targets), **res)
-        print(f"c64_latent_{tag}.npz: events {len(res['kinds'])}, n_eps {res['n_eps']}, "
+        print(f"c{C}_latent_{tag}.npz: events {len(res['kinds'])}, n_eps {res['n_eps']}, "
               f"ref f32-vs-f64 state {res['ref_f32_state_err']:.2e} x {res['ref_f32_x_err']:.2e}")
 
 
@@ -242,14 +252,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                   "tests", "golden"))
+    ap.add_argument("--only", default="", help="comma-separated subset: schedules,tiny,c64,c128,decoder")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(8)
     ref = ri.import_reference()
-    gen_schedules(ref, args.out)
-    gen_tiny_full(ref, args.out)
-    gen_c64_latent(ref, args.out)
-    gen_decoder(ref, args.out)
+    steps = dict(schedules=gen_schedules, tiny=gen_tiny_full, c64=gen_c64_latent, c128=gen_c128_latent, decoder=gen_decoder)
+    for name, fn in steps.items():
+        if not args.only or name in args.only.split(","):
+            fn(ref, args.out)
 
 
 if __name__ == "__main__":

@@ -70,10 +70,12 @@ def test_full_module_matches_reference(golden_dir):
         assert sum(1 for _ in eps) == 64 - int(z["n_eps"])      # same number of noise draws as the reference
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c64_latent_*.npz"))),
-                         ids=lambda p: os.path.basename(p)[11:-4])
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c64_latent_*.npz")) +
+                                        glob.glob(os.path.join(os.path.dirname(__file__), "golden", "c128_latent_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
 def test_c64_latent_rollout_matches_reference(path):
-    """NNFOwithBayesianJumps.forward at the production width C=64: per-event latent states, selection, decode."""
+    """NNFOwithBayesianJumps.forward at the production width C=64 (and the 128-channel network of config 5): per-event
+    latent states, selection, decode."""
     z = np.load(path)
     C, H, seed = int(z["C"]), int(z["H"]), int(z["seed"])
     from oracle.shapes import nnfo_shapes
