@@ -101,3 +101,30 @@ def test_halo_exchange_fills_the_local_window(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_halo_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
     assert all(open(tmp_path / f"ok{r}").read() == "1" for r in range(3))
+
+
+def test_row_sharded_event_program_splits_at_the_nccl_calls():
+    """The op list of one row-sharded event: stage launches, SE reduce -> all-reduce -> apply, then pack -> send/recv -> unpack;
+    the graph replay captures the runs between the NCCL calls ('allreduce', 'p2p') as segments."""
+    from types import SimpleNamespace as NS
+    from streamingflow_b200 import _lib as L
+    from streamingflow_b200.row_sharding import RowShardedOde
+
+    eng = NS(cell_slots=[[0, 1, 2, 3, 4, 5], [6, 7, 8, 9, 10, 11]], prior_items=[12, 13, L.SE_ITEM_BASE, 14, 15, L.SE_ITEM_BASE + 1, 16])
+    ev = NS(kind=1, run_cell=1, run_prior=1)
+    ops = RowShardedOde._event_ops(NS(eng=eng, world=4), ev)
+    kinds = [k for k, _ in ops]
+    assert kinds == ["stage"] * 8 + ["se_reduce", "allreduce", "se_apply"] + ["stage"] * 2 + ["se_reduce", "allreduce", "se_apply", "stage",
+                                                                                      "pack", "p2p", "unpack"]
+    assert [a for k, a in ops if k == "stage"][:6] == eng.cell_slots[1]
+    segments, cur = [], []
+    for k, _ in ops + [("flush", 0)]:
+        if k in ("allreduce", "p2p", "flush"):
+            if cur:
+                segments.append(cur)
+            cur = []
+        else:
+            cur.append(k)
+    assert len(segments) == 4 and segments[-1] == ["unpack"] and segments[2][-1] == "pack"
+    single = RowShardedOde._event_ops(NS(eng=eng, world=1), NS(kind=0, run_cell=1, run_prior=0))
+    assert [k for k, _ in single] == ["stage"] * 6          # one rank: no collectives, no halo exchange
