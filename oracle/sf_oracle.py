@@ -303,29 +303,43 @@ class Schedule:
     select: List[int] = field(default_factory=list)        # per target: index into path_*
 
 
-def build_schedule(times: Sequence[float], targets: Sequence[float], delta_t: float, variable: bool) -> Schedule:
+def build_schedule(times: Sequence[float], targets: Sequence[float], delta_t: float, variable: bool,
+                   stamp_dtype=np.float64) -> Schedule:
     """Restates temporal_ode_bayes.py:508 (start time), :539-553 (propagate to each observation),
     :562-581 (jump + record), :585-604 (propagate to each target + record window), :606-622 (selection).
-    All arithmetic is IEEE double on host, exactly like the reference's ``.item()`` floats; note
-    ``current_time += dt`` with ``dt = t_next - current_time`` can land 1 ulp short and trigger an
-    extra ~1e-16 s step -- reproduced here by construction."""
+    ``current_time`` is a host double (``.item()``), but every comparison / subtraction against ``obs_time`` /
+    ``predict_time`` happens in the dtype of those 0-dim tensors (``stamp_dtype``: float64 from the nuScenes loader,
+    float32 if a caller passes such stamps); a fixed step adds two python floats.  Note ``current_time += dt`` with
+    ``dt = t_next - current_time`` can land 1 ulp short and trigger an extra ~1e-16 s step -- reproduced
+    here by construction."""
+    D = stamp_dtype
     times = [float(t) for t in times]
     targets = [float(t) for t in targets]
     sch = Schedule()
     cur = min(times)
     for i, t_obs in enumerate(times):
-        while cur <= (t_obs - delta_t):
-            dt = (t_obs - cur) if variable else delta_t
-            cur = cur + dt
+        while D(cur) <= D(t_obs) - D(delta_t):
+            if variable:
+                dt = D(t_obs) - D(cur)
+                cur = float(D(cur) + dt)
+                dt = float(dt)
+            else:
+                dt = delta_t
+                cur = cur + dt
             sch.events.append(Event("step", dt, -1, cur, False))
         sch.events.append(Event("jump", 0.0, i, t_obs, True))
         sch.path_t.append(t_obs)
         sch.path_ev.append(len(sch.events) - 1)
     for t_pred in targets:
-        while cur < t_pred:
-            dt = (t_pred - cur) if variable else delta_t
-            cur = cur + dt
-            rec = (cur > t_pred - 0.5 * delta_t) and (cur < t_pred + 0.5 * delta_t)
+        while D(cur) < D(t_pred):
+            if variable:
+                dt = D(t_pred) - D(cur)
+                cur = float(D(cur) + dt)
+                dt = float(dt)
+            else:
+                dt = delta_t
+                cur = cur + dt
+            rec = bool((D(cur) > D(t_pred) - D(0.5 * delta_t)) and (D(cur) < D(t_pred) + D(0.5 * delta_t)))
             sch.events.append(Event("step", dt, -1, cur, rec))
             if rec:
                 sch.path_t.append(cur)

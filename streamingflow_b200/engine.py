@@ -401,6 +401,8 @@ class OdeEngine:
         ``{prefix}p_model.*``."""
         sd = {k: v.detach().to(self.device) for k, v in sd.items() if k.startswith(prefix)}
         pre = prefix
+        # captured CUDA graphs hold the addresses of the packed weights / vectors released below: retire them
+        self.alloc_gen = getattr(self, "alloc_gen", 0) + 1
         self._keep = []
         self.stage_defs: Dict[int, StageDef] = {}
         self.stage_names: Dict[int, str] = {}
@@ -468,26 +470,33 @@ class OdeEngine:
                                           n, c, h, w, self._stream()), "sf_pack_nchw_f32")
 
     def reserve_observations(self, n_images: int):
-        if BUF_OBS not in self.act or self.act[BUF_OBS][0].shape[0] < n_images:
+        """An engine-owned observation buffer of at least n_images (re-bound if the slot currently points at somebody else's
+        planes, e.g. the fused encoder's output: a captured graph must never keep reading a buffer the engine does not own)."""
+        if BUF_OBS not in self.act or not getattr(self, "_obs_owned", False) or self.act[BUF_OBS][0].shape[0] < n_images:
             self._new_act(BUF_OBS, n_images, self.C)
+            self._obs_owned = True
         self.n_obs_images = n_images
 
     def bind_observations(self, hx_nchw: torch.Tensor):
         """Encoded observations [n_img, 64, H, W] fp32 -> OBS activation buffer (the jump cell's x input)."""
         n = hx_nchw.shape[0]
-        if BUF_OBS not in self.act or self.act[BUF_OBS][0].shape[0] < n:
-            self._new_act(BUF_OBS, n, self.C)
+        self.reserve_observations(n)
         self.pack_into(BUF_OBS, hx_nchw)
-        self.n_obs_images = n
 
     def bind_observation_planes(self, hi: torch.Tensor, lo: Optional[torch.Tensor]):
         """Use already-encoded NHWC bf16 planes [n, H, W, C] (the fused encoder's output buffer) as the observation buffer."""
         assert tuple(hi.shape[1:]) == (self.H, self.W, self.C) and hi.dtype == torch.bfloat16 and hi.is_contiguous()
         if self.x3 and lo is None:
             raise L.SfError("bf16x3 needs the residual plane of the observations")
-        self.act[BUF_OBS] = (hi, lo)
-        L.check(self.lib.sf_plan_bind_act(self.plan, BUF_OBS, hi.data_ptr(), lo.data_ptr() if lo is not None else None, self.C, hi.shape[0]),
-                "sf_plan_bind_act")
+        cur = self.act.get(BUF_OBS)
+        same = cur is not None and cur[0].data_ptr() == hi.data_ptr() and cur[0].shape[0] == hi.shape[0] and \
+            (cur[1] is None) == (lo is None) and (lo is None or cur[1].data_ptr() == lo.data_ptr())
+        if not same:
+            self.alloc_gen = getattr(self, "alloc_gen", 0) + 1      # the OBS slot's address changes: graphs captured with the old one retire
+            self.act[BUF_OBS] = (hi, lo)
+            self._obs_owned = False
+            L.check(self.lib.sf_plan_bind_act(self.plan, BUF_OBS, hi.data_ptr(), lo.data_ptr() if lo is not None else None, self.C, hi.shape[0]),
+                    "sf_plan_bind_act")
         self.n_obs_images = hi.shape[0]
 
     def set_state(self, which: int, state_nchw: torch.Tensor):

@@ -51,6 +51,12 @@ class _DualGRUBase(nn.Module):
                                            nn.Conv2d(hidden_size, 2, kernel_size=1, bias=False))
         self.__dict__["_owner"] = None          # weakref to the NNFOwithBayesianJumps that owns the engine
 
+    def __getstate__(self):
+        # the owner weakref must not travel with a copy / pickle: the new owner re-wires it (NNFOwithBayesianJumps.__setstate__)
+        d = dict(self.__dict__)
+        d["_owner"] = None
+        return d
+
     def _run(self, x, state, derivative: bool):
         owner = self._owner() if self._owner is not None else None
         if owner is None:
@@ -127,9 +133,7 @@ class NNFOwithBayesianJumps(nn.Module):
         assert self.solver in ["euler", "midpoint"], "Solver must be either 'euler' or 'midpoint'."
         self.input_size, self.hidden_size, self.logvar, self.mixing = input_size, hidden_size, logvar, mixing
         self.apply(init_weights)
-        me = weakref.ref(self)
-        self.gru_c.__dict__["_owner"] = me
-        self.gru_obs.gru_d.__dict__["_owner"] = me
+        self._wire_cells()
         # engine options (not part of the reference API)
         self.precision = os.environ.get("SF_B200_PRECISION", getattr(cfg.MODEL, "ODE_PRECISION", "bf16"))
         self.noise = "reference"
@@ -145,7 +149,37 @@ class NNFOwithBayesianJumps(nn.Module):
         self.__dict__["_engine_factory"] = None        # tests inject a checker backend here; the product path never does
         self.last_rollout = None
 
+    # ------------------------------------------------------------------ copy / pickle (EMA copies, torch.save of the whole module)
+    _RUNTIME_CACHES = ("_engines", "_codecs", "_graphs", "_stream_plans", "_copy_streams", "_stage_bufs", "download_done")
+
+    def _wire_cells(self):
+        me = weakref.ref(self)
+        self.gru_c.__dict__["_owner"] = me
+        self.gru_obs.gru_d.__dict__["_owner"] = me
+
+    def __getstate__(self):
+        """Engines, codecs, captured graphs and copy streams are per-instance device resources (ctypes plan handles): a copy or
+        an unpickled module starts without them and rebuilds them on its first call."""
+        d = dict(self.__dict__)
+        for k in self._RUNTIME_CACHES:
+            d.pop(k, None)
+        d["_engines"], d["_codecs"], d["_graphs"] = {}, {}, {}
+        d["last_rollout"], d["last_trace"] = None, None
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._wire_cells()
+
     # ------------------------------------------------------------------ engine management
+    def _guard_no_grad(self, *tensors):
+        """The CUDA engine is inference only and returns tensors without a grad_fn.  Silently cutting a gradient path would be
+        worse than failing: raise when autograd is recording and anything upstream could need a gradient."""
+        if torch.is_grad_enabled() and (any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+                                        or any(p.requires_grad for mod in (self.gru_c, self.gru_obs, self.p_model) for p in mod.parameters())):
+            raise L.SfError("streamingflow_b200's ODE head has no backward: call it under torch.no_grad() (or freeze its parameters "
+                            "with requires_grad_(False) and pass inputs that do not require grad); gradients would be cut silently")
+
     def _weights_fingerprint(self):
         return tuple((p.data_ptr(), p._version) for mod in (self.gru_c, self.gru_obs, self.p_model)
                      for p in list(mod.parameters()) + list(mod.buffers()))
@@ -213,6 +247,22 @@ class NNFOwithBayesianJumps(nn.Module):
                 eps[i].normal_()
         return eps
 
+    def discard_noise(self, n, like):
+        """Advances the noise stream by n draws of the latent shape of the BEV tensor ``like`` [..., H, W] without producing
+        them (batch sharding: the draws that belong to other ranks' samples)."""
+        h, w = like.shape[-2] // 2 // 2, like.shape[-1] // 2 // 2
+        dev = like.device
+        if dev.type == "cuda" and self.noise != "bulk":
+            lib = L.load()
+            gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+            grid, per = ctypes.c_int(), ctypes.c_int()
+            L.check(lib.sf_normal_policy(self.hidden_size * h * w, gen.device.index, ctypes.byref(grid), ctypes.byref(per)), "sf_normal_policy")
+            gen.set_offset(gen.get_offset() + n * per.value)
+            return
+        buf = torch.empty((1, self.hidden_size, h, w), dtype=torch.float32, device=dev)
+        for _ in range(n):
+            buf.normal_()
+
     def _noise_into(self, buf, n, h, w, device):
         """Draws the rollout's noise into ``buf`` (the static noise buffer of captured graphs)."""
         try:
@@ -253,6 +303,7 @@ class NNFOwithBayesianJumps(nn.Module):
         return ev
 
     def _cell_call(self, cell, x, state, derivative):
+        self._guard_no_grad(x, state)
         n, _, h, w = x.shape
         eng = self._engine_for(h, w, n, x.device)
         eng.set_state(0, state)
@@ -272,6 +323,7 @@ class NNFOwithBayesianJumps(nn.Module):
 
     def infer_state(self, x, deterministic=False):
         """(sample, params) of the latent prior at state x (reference :463-477)."""
+        self._guard_no_grad(x)
         n, _, h, w = x.shape
         eng = self._engine_for(h, w, n, x.device)
         eng.set_state(0, x)
@@ -281,6 +333,7 @@ class NNFOwithBayesianJumps(nn.Module):
 
     def ode_step(self, state, input, delta_t, current_time):
         """One solver step (reference :436-459). Returns (state, input, current_time + delta_t, eval_times, eval_ps)."""
+        self._guard_no_grad(state, input)
         n, _, h, w = state.shape
         dev = state.device
         eng = self._engine_for(h, w, n, dev)
@@ -330,21 +383,24 @@ class NNFOwithBayesianJumps(nn.Module):
         return ent["codec"]
 
     def integrate_latents(self, hx_obs, obs_counts: Sequence[int], times: Sequence[Sequence[float]],
-                          targets: Sequence[Sequence[float]], delta_t: float, obs_planes=None, return_slots: bool = False):
+                          targets: Sequence[Sequence[float]], delta_t: float, obs_planes=None, return_slots: bool = False,
+                          stamp_dtypes=("float64", "float64")):
         """Batched jump / integrate loop on already-encoded observations.
 
         hx_obs: [sum(obs_counts), C, h, w] fp32 latents, sample-major, each sample's frames in processing order -- or None
         with obs_planes = (hi, lo) NHWC bf16 planes [n, h, w, C] from the fused encoder.
         times[b] / targets[b]: python floats.  Returns (final states [B,C,h,w], selected latents [B,T,C,h,w]); with
-        return_slots the second value is (engine, flat path slots) so a fused decoder can read the path buffer directly."""
+        return_slots the second value is (engine, flat path slots) so a fused decoder can read the path buffer directly.
+        stamp_dtypes: dtypes of the (observation, target) timestamp tensors the values came from (schedule.plan_sample)."""
         B = len(obs_counts)
+        self._guard_no_grad(hx_obs)
         if obs_planes is not None:
             _, h, w, c = obs_planes[0].shape
             dev = obs_planes[0].device
         else:
             _, c, h, w = hx_obs.shape
             dev = hx_obs.device
-        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
+        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
         ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all, max_group=self.event_group)
         eng = self._engine_for(h, w, B, dev)
@@ -407,7 +463,8 @@ class NNFOwithBayesianJumps(nn.Module):
         ro.launches = ent["launches"]
         return eng.unpack_f32(eng.state32[0], B), eng.unpack_path(ent["slots"]).view(B, T, c, h, w)
 
-    def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None, join=True):
+    def integrate_latents_streamed(self, hx_host, obs_counts, times, targets, delta_t, out_host=None, join=True,
+                                   stamp_dtypes=("float64", "float64")):
         """integrate_latents for HOST buffers: ``hx_host`` is a pinned CPU tensor [sum(obs_counts), C, h, w]; returns (final
         states on device, selected latents [B, T, C, h, w] as a view of the pinned CPU tensor ``out_host`` [T, B, C, h, w]).
         Host<->device copies are pipelined against the rollout: observation k of every sample is uploaded on a copy stream
@@ -425,12 +482,12 @@ class NNFOwithBayesianJumps(nn.Module):
         T = len(targets[0])
         cache = self.__dict__.setdefault("_stream_plans", {})
         sig = (id(eng), tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times), tuple(tuple(float(x) for x in t) for t in targets),
-               float(delta_t), self.use_variable_ode_step, self.solver, bool(self.impute))
+               float(delta_t), self.use_variable_ode_step, self.solver, bool(self.impute), tuple(stamp_dtypes))
         plan = cache.get(sig)
         if plan is None:
             if len(cache) >= 8:
                 cache.clear()
-            plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver) for b in range(B)]
+            plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
             base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
             ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b)
             table, evs = eng.build_table(ro.events)
@@ -446,7 +503,8 @@ class NNFOwithBayesianJumps(nn.Module):
         ro, base, evs, tdev, slots_dev, ready_at = (plan[k] for k in ("ro", "base", "evs", "tdev", "slots", "ready_at"))
         eng.reserve_observations(kmax * B)
         eng.ensure_path_slots(ro.n_path)
-        if self.cuda_graph and plan.get("gen") != eng.alloc_gen:
+        fp = self._weights_fingerprint()
+        if self.cuda_graph and (plan.get("gen") != eng.alloc_gen or plan.get("fp") != fp):
             # one captured graph per batched event (its 15 stage launches); copies, packs and gathers stay eager around them
             plan["eps"] = torch.empty((max(ro.n_eps, 1), c, h, w), dtype=torch.float32, device=dev)
             eng.bind_eps(plan["eps"])
@@ -457,7 +515,7 @@ class NNFOwithBayesianJumps(nn.Module):
                 with torch.cuda.graph(gph):
                     plan["graph_launches"].append(eng.run_events(evs[i:i + 1], tdev))
                 plan["graphs"].append(gph)
-            plan["gen"] = eng.alloc_gen
+            plan["gen"], plan["fp"] = eng.alloc_gen, fp
         graphs = plan.get("graphs") if self.cuda_graph else None
         eng.zero_state(0)
         if graphs is not None:
@@ -544,24 +602,28 @@ class NNFOwithBayesianJumps(nn.Module):
             raise NotImplementedError("the reference calls gru_ode with one sample (obs batch 1); use FuturePredictionODE for batches")
         t_list = times.tolist() if isinstance(times, torch.Tensor) else [float(t) for t in times]
         T_list = T.tolist() if isinstance(T, torch.Tensor) else [float(t) for t in T]
+        is32 = lambda t: isinstance(t, torch.Tensor) and t.dtype == torch.float32
+        dtypes = ("float32" if is32(times) else "float64", "float32" if is32(T) else "float64")
         n_obs, H, W = obs.shape[1], obs.shape[3], obs.shape[4]
         if self.codec_available(H, W, obs.device):
-            state, x = self.encode_integrate_decode(obs[0], [n_obs], [t_list], [T_list], delta_t)
+            state, x = self.encode_integrate_decode(obs[0], [n_obs], [t_list], [T_list], delta_t, stamp_dtypes=dtypes)
             return state, 0, x
         hx_obs, _ = self.srvp_encode(obs)
-        state, sel = self.integrate_latents(hx_obs[0], [n_obs], [t_list], [T_list], delta_t)
+        state, sel = self.integrate_latents(hx_obs[0], [n_obs], [t_list], [T_list], delta_t, stamp_dtypes=dtypes)
         x = self.srvp_decode(sel)
         return state, 0, x
 
-    def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t, raw: bool = False):
+    def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t, raw: bool = False, stamp_dtypes=("float64", "float64")):
         """SmallEncoder -> jump / integrate loop -> SmallDecoder entirely on the conv-stage kernels: frames [n, C, H, W] (all
         samples' observation frames, sample-major, processing order) -> (final latent states, decoded frames [B, T, C, H, W]).
         raw=True returns the decoded frames in engine layout ((hi, lo) NHWC bf16 planes, fp32 NHWC) for the fused refinement."""
+        self._guard_no_grad(frames, *self.srvp_encoder.parameters(), *self.srvp_decoder.parameters())
         n, c, H, W = frames.shape
         B, T = len(obs_counts), len(targets[0])
         codec = self._codec_for(H, W, n, B * T, frames.device)
         planes = codec.encode(frames)
-        state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True)
+        state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True,
+                                                     stamp_dtypes=stamp_dtypes)
         slots = torch.tensor(flat, dtype=torch.int32).to(frames.device)
         x = codec.decode(eng.path, slots, unpack=not raw)
         if not raw:

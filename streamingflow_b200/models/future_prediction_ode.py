@@ -51,6 +51,11 @@ class FuturePredictionODE(nn.Module):
             self._refiners[key] = ent
         return ent["engine"]
 
+    def __getstate__(self):
+        d = dict(self.__dict__)          # the refinement engines hold ctypes plan handles: per-instance, rebuilt on first use
+        d["_refiners"] = {}
+        return d
+
     @staticmethod
     def _host_times(t):
         """Timestamps as python doubles with ONE device->host copy (the reference syncs once per dict key)."""
@@ -59,6 +64,20 @@ class FuturePredictionODE(nn.Module):
     def forward(self, future_prediction_input, camera_states, lidar_states, camera_timestamp, lidar_timestamp, target_timestamp):
         # camera_states [B, n_cam, C, H, W]; lidar_states [B, n_lidar, C, H, W] or None; timestamps [B, n] (seconds)
         B = camera_states.shape[0]
+        if B == 0:                       # an empty shard (more ranks than samples): nothing to integrate
+            T = target_timestamp.shape[1]
+            return camera_states.new_zeros((0, T) + tuple(camera_states.shape[2:])), 0
+        if torch.is_grad_enabled() and (camera_states.requires_grad or (lidar_states is not None and lidar_states.requires_grad)
+                                        or any(p.requires_grad for p in self.parameters())):
+            from .. import _lib as L
+            raise L.SfError("streamingflow_b200's FuturePredictionODE is inference only (no backward): call it under torch.no_grad(); "
+                            "with autograd recording the gradients to camera_states / lidar_states would be cut silently")
+        # dtype of the stamp tensors: the reference's loop compares / subtracts in it (schedule.plan_sample).  Its per-sample
+        # ``times = torch.tensor(list_of_0-dim_keys)`` is float32 only when every stamp is float32.
+        obs_dtype = "float32" if (camera_timestamp.dtype == torch.float32 and
+                                  (lidar_states is None or lidar_timestamp.dtype == torch.float32)) else "float64"
+        tgt_dtype = "float32" if target_timestamp.dtype == torch.float32 else "float64"
+        dtypes = (obs_dtype, tgt_dtype)
         cam_t = self._host_times(camera_timestamp)
         lid_t = self._host_times(lidar_timestamp) if lidar_states is not None else None
         tgt_t = self._host_times(target_timestamp)
@@ -75,17 +94,17 @@ class FuturePredictionODE(nn.Module):
         if fused and self.fused_refine and self.n_spatial_gru == 2 and self.n_res_layers == 1 and self.in_channels == 64:
             # encoder -> ODE loop -> decoder -> SpatialGRU / Block / SpatialGRU / DeepLabHead, all on the CUDA engine
             T = len(tgt_t[0])
-            _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True)
+            _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True, stamp_dtypes=dtypes)
             refine = self._refine_for(H, W, B, T, stacked.device)
             x = refine.run(planes, x32)
             ode.last_rollout.launches += refine.launches
             refine.launches = 0
             return x, 0
         if fused:
-            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t)      # encoder / loop / decoder on the CUDA engine
+            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)      # encoder / loop / decoder on the CUDA engine
         else:
             hx = ode.srvp_encoder(stacked)
-            _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t)
+            _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)
             x = ode.srvp_decode(sel)                                   # [B, T, C, H, W]
         hidden_state = x[:, 0]
         for gru, block in zip(self.spatial_grus, self.res_blocks):

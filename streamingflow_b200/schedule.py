@@ -53,31 +53,53 @@ def _window_pick(stamps: Sequence[float], when: float, half: float) -> int:
 
 
 def plan_sample(obs_times: Sequence[float], targets: Sequence[float], delta_t: float, variable_step: bool,
-                solver: str = "euler") -> SamplePlan:
-    """obs_times must already be in processing order (sorted by the caller exactly like the reference's dict sort)."""
+                solver: str = "euler", obs_dtype: str = "float64", target_dtype: str = "float64") -> SamplePlan:
+    """obs_times must already be in processing order (sorted by the caller exactly like the reference's dict sort).
+
+    obs_dtype / target_dtype: dtype of the timestamp TENSORS the caller passed.  The reference keeps ``current_time`` as a
+    python double but compares and subtracts it against 0-dim tensors of the stamps' own dtype (:540-545, :586-590), so with
+    float32 stamps the comparisons, the variable step ``t_next - current_time`` and ``current_time += dt`` are float32
+    arithmetic; a fixed step (``current_time += delta_t``, two python floats) stays double.  The selection (:606-620) runs on
+    ``.item()`` doubles in both cases.  numpy scalars of the stamp dtype reproduce this op for op (np.float64 == python float)."""
     if len(obs_times) == 0:
         raise ValueError("at least one observation is required (the reference takes times.min())")
+    import numpy as np
+
+    D1 = np.float32 if obs_dtype == "float32" else np.float64
+    D2 = np.float32 if target_dtype == "float32" else np.float64
     obs_times = [float(t) for t in obs_times]
     targets = [float(t) for t in targets]
-    now = min(obs_times)
+    now = min(obs_times)              # times.min().item(): a python double
     ops: List[Op] = []
     stamps: List[float] = []      # recorded times
     stamp_op: List[int] = []      # op index that produced each recorded state
     half = 0.5 * delta_t
     for k, t_obs in enumerate(obs_times):
-        while now <= t_obs - delta_t:
-            h = (t_obs - now) if variable_step else delta_t
-            now = now + h
+        t1 = D1(t_obs)
+        while D1(now) <= t1 - D1(delta_t):
+            if variable_step:
+                h = t1 - D1(now)
+                now = float(D1(now) + h)
+                h = float(h)
+            else:
+                h = delta_t
+                now = now + h
             ops.append(Op(STEP, h, -1, now))
         ops.append(Op(JUMP, 0.0, k, t_obs))
         stamps.append(t_obs)
         stamp_op.append(len(ops) - 1)
     for t_goal in targets:
-        while now < t_goal:
-            h = (t_goal - now) if variable_step else delta_t
-            now = now + h
+        t2 = D2(t_goal)
+        while D2(now) < t2:
+            if variable_step:
+                h = t2 - D2(now)
+                now = float(D2(now) + h)
+                h = float(h)
+            else:
+                h = delta_t
+                now = now + h
             ops.append(Op(STEP, h, -1, now))
-            if t_goal - half < now < t_goal + half:
+            if t2 - D2(half) < D2(now) < t2 + D2(half):
                 stamps.append(now)
                 stamp_op.append(len(ops) - 1)
     picks = [stamp_op[_window_pick(stamps, t, half)] for t in targets]

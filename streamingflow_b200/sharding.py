@@ -22,16 +22,18 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def noise_draws_before(module, camera_timestamp, lidar_timestamp, target_timestamp, lidar_present: bool, lo: int) -> int:
-    """Number of standard-normal tensors the reference would have drawn for samples [0, lo)."""
+def noise_draws_before(module, camera_timestamp, lidar_timestamp, target_timestamp, lidar_present: bool, lo: int, hi=None) -> int:
+    """Number of standard-normal tensors the reference would have drawn for samples [0, lo) (or [lo, hi) when hi is given)."""
     ode = module.gru_ode
     cam = camera_timestamp.detach().to("cpu", torch.float64).tolist()
     lid = lidar_timestamp.detach().to("cpu", torch.float64).tolist() if lidar_present else None
     tgt = target_timestamp.detach().to("cpu", torch.float64).tolist()
+    obs_dtype = "float32" if (camera_timestamp.dtype == torch.float32 and (lid is None or lidar_timestamp.dtype == torch.float32)) else "float64"
+    tgt_dtype = "float32" if target_timestamp.dtype == torch.float32 else "float64"
     n = 0
-    for b in range(lo):
+    for b in range(lo, hi) if hi is not None else range(lo):
         order = merge_observations(cam[b], None if lid is None else lid[b])
-        n += plan_sample([t for t, _, _ in order], tgt[b], module.delta_t, ode.use_variable_ode_step, ode.solver).n_noise
+        n += plan_sample([t for t, _, _ in order], tgt[b], module.delta_t, ode.use_variable_ode_step, ode.solver, obs_dtype, tgt_dtype).n_noise
     return n
 
 
@@ -49,6 +51,13 @@ def sharded_forward(module, future_prediction_input, camera_states, lidar_states
                                                    lidar_states is not None, lo)
     x, aux = module(future_prediction_input[sl], camera_states[sl], None if lidar_states is None else lidar_states[sl],
                     camera_timestamp[sl], None if lidar_timestamp is None else lidar_timestamp[sl], target_timestamp[sl])
+    # leave the generator where the single-process run would leave it: the draws of the samples AFTER this shard are skipped
+    # too, so that every rank has consumed the whole batch's stream and the next call starts from the same point everywhere
+    after = noise_draws_before(module, camera_timestamp, lidar_timestamp, target_timestamp, lidar_states is not None, hi, B)
+    after += module.gru_ode.noise_skip          # an empty shard never drew: its pending skip is still unconsumed
+    module.gru_ode.noise_skip = 0
+    if after:
+        module.gru_ode.discard_noise(after, camera_states)
     if not gather or world == 1:
         return x, aux
     sizes = [shard_bounds(B, r, world) for r in range(world)]

@@ -24,6 +24,7 @@ class OracleBackend:
         self.x32, self.params32 = z(max_images), z(max_images, 2 * C)
         self.state32 = self.state
         self.path = z(1)
+        self.obs = z(1)
         self.events_run = 0
 
     def load_weights(self, sd, prefix):

@@ -360,3 +360,122 @@ def test_fused_encoder_and_decoder_match_oracle(precision):
     with torch.no_grad():
         want = so.small_decoder(sd64, "g.srvp_decoder", z[[4, 0, 2]].permute(0, 3, 1, 2).double())
     assert out.shape == want.shape and _rel(out, want) < (tol if precision == "bf16" else 5e-4)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("solver,impute", [("euler", True), ("midpoint", True), ("euler", False)])
+def test_inner_api_matches_oracle(precision, solver, impute):
+    """The preserved inner API called the way reference code calls it -- gru_c(x, state), gru_obs(state, p, X_obs),
+    infer_state(x), ode_step(state, input, delta_t, current_time) (temporal_ode_bayes.py:92-131, 327-344, 463-477, 436-459) --
+    against the fp64 oracle: one sample (the reference's own call shape) and three independent samples."""
+    m = _nnfo(solver, True, impute, 13, 1.0, precision)
+    sd = {"g." + k: (v.double() if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    C, h, w = 64, 28, 20
+    tol = TOL[precision]
+    for n in (1, 3):
+        x = torch.tanh(so.recipe_array(f"x{n}", (n, C, h, w), 13)).cuda()
+        s = (0.5 * so.recipe_array(f"s{n}", (n, C, h, w), 13)).cuda()
+        tape = torch.stack([so.recipe_array(f"eps{n}_{i}", (C, h, w), 13) for i in range(2 * n)]).cuda()
+        drawn = []
+
+        def fixture_noise(k, hh, ww, device, _tape=tape):
+            drawn.append(k)
+            return _tape[:max(k, 1)].contiguous()
+
+        m._draw_noise = fixture_noise
+        with torch.no_grad():
+            # derivative cell: dh = f(x, state)                                                    (:92-131)
+            dh = m.gru_c(x, s)
+            want = so.ode_derivative(sd, "g.gru_c", x.double(), s.double())
+            assert dh.shape == want.shape and dh.dtype == torch.float32
+            # dh = mix - s: the error budget is on the mixed state, so scale by max(|mix|, |dh|)
+            mix = want + s.double()
+            err = ((dh.double() - want).abs().max() / torch.maximum(mix.abs().max(), want.abs().max())).item()
+            assert err < tol, f"gru_c n={n}: {err:.3e}"
+            # observation jump: (state, None) = gru_obs(state, p, X_obs)                            (:327-344)
+            got, loss = m.gru_obs(s, None, x)
+            assert loss is None and _rel(got, so.observation_jump(sd, "g.gru_obs", s.double(), x.double())) < tol
+            # latent prior sample + params                                                          (:463-477)
+            y, params = m.infer_state(s)
+            eps = tape[:n].double()
+            y_o, p_o = so.infer_state(sd, "g.p_model", s.double(), eps)
+            assert drawn[-1] == n and params.shape == (n, 2 * C, h, w)
+            assert _rel(params, p_o) < tol and _rel(y, y_o) < 2 * tol
+            # one solver step                                                                       (:436-459)
+            dt = 0.35
+            st, inp, t_new, ev_t, ev_p = m.ode_step(s, x, dt, 1.0)
+            n_draw = n * (2 if solver == "midpoint" else 1)
+            assert drawn[-1] == n_draw and t_new == 1.0 + dt and ev_t.dtype == torch.float64 and ev_p.dtype == torch.float32
+            st_o, inp_o = [], []
+            for b in range(n):      # the tape is consumed sample-major: sample b's infer_state calls see eps[per*b ...]
+                per = 2 if solver == "midpoint" else 1
+                a, bb = so.ode_step(sd, "g", s[b:b + 1].double(), x[b:b + 1].double(), dt,
+                                    [tape[per * b + j][None].double() for j in range(per)], solver, impute)
+                st_o.append(a)
+                inp_o.append(bb)
+            assert _rel(st, torch.cat(st_o)) < tol, f"ode_step state n={n} {solver}: {_rel(st, torch.cat(st_o)):.3e}"
+            assert _rel(inp, torch.cat(inp_o)) < 2 * tol
+    # a 5-D call (x [b, 1, C, h, w], state [b, 1, C, h, w]) is the same computation (:97-100)
+    with torch.no_grad():
+        assert torch.equal(m.gru_c(x[:, None], s[:, None]), m.gru_c(x, s))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_argmax_masks_match_reference_on_margin_selected_seeds(precision):
+    """The north-star end product: ``segmentation.argmax(dim=2)`` (trainer.py:230-231) of the reference Decoder applied to the
+    ODE head's output, BASELINE config-1 shapes (B = 1, BEV 200 x 200 x 64, 3 camera frames, 4 future targets), energised
+    weights.  tests/golden/argmax_c64.npz holds the masks the UNMODIFIED reference produced in fp64 for the three seeds (of 40
+    tried) whose smallest |logit_0 - logit_1| is largest among the non-constant masks (oracle/gen_golden.py::gen_argmax).
+    Accurate mode (1e-4): the masks are bit-exact.  bf16 mode (1e-2): the logit error (~5e-3 of max|logit|) exceeds the
+    smallest margins any non-constant 160 000-pixel mask offers (margin histograms in the fixture), so bit-exactness cannot be
+    demanded on every pixel; a pixel may differ only where the reference's own margin is below twice the measured logit error."""
+    import json
+
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "argmax_c64.npz"))
+    C, H, gain = 64, int(z["H"]), float(z["gain"])
+    dshapes = {k: tuple(int(t) for t in v.split(",") if t) for k, v in zip(z["dshapes_keys"], z["dshapes_vals"])}
+    ct = torch.tensor([[-1.0, -0.5, 0.0]], dtype=torch.float64)
+    tt = torch.tensor([[0.5, 1.0, 1.5, 2.0]], dtype=torch.float64)
+    report = []
+    for k, seed in enumerate(int(s) for s in z["seeds"]):
+        want = torch.from_numpy(np.unpackbits(z["masks"][k], axis=-1)[..., :H].astype(np.int64))       # [1, 4, H, H]
+        m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval()
+        sd32 = so.recipe_state_dict({kk: tuple(v.shape) for kk, v in m.state_dict().items()}, seed, gain)
+        m.load_state_dict(sd32, strict=True)
+        m = m.cuda()
+        m.gru_ode.precision = precision
+        cam = so.recipe_array("cam", (1, 3, C, H, H), seed).cuda()
+        tape = torch.stack([so.recipe_array(f"eps{i}", (C, H // 4, H // 4), seed) for i in range(int(z["n_eps"][k]))]).cuda()
+        m.gru_ode._draw_noise = lambda n, h, w, device, _t=tape: _t[:n].contiguous()
+        with torch.no_grad():
+            x, _ = m(torch.zeros(1, 1, C, H, H, device="cuda"), cam, None, ct, None, tt)
+        dsd = {"d." + kk: (v.double().cuda() if v.is_floating_point() else v.cuda()) for kk, v in so.recipe_state_dict(dshapes, seed, gain).items()}
+        sd64 = {kk: (v.double().cuda() if v.is_floating_point() else v.cuda()) for kk, v in sd32.items()}
+        with torch.no_grad():
+            seg_got = so.seg_decoder(dsd, "d", x.double())
+            xo = so.future_prediction_forward(sd64, cam.double(), None, ct, None, tt, 0.05, iter(tape.double()[:, None]))
+            seg_ref = so.seg_decoder(dsd, "d", xo)
+        # the oracle reproduces the reference's masks exactly (its fp64 logits agree with the reference's to ~1e-12)
+        assert torch.equal(seg_ref.argmax(2).cpu(), want), "oracle vs reference masks"
+        assert abs(float((seg_ref[:, :, 0] - seg_ref[:, :, 1]).abs().min()) - float(z["min_margin"][k])) < 1e-6
+        minority = min(int(want.sum()), int(want.numel() - want.sum()))
+        assert minority >= 20, "constant mask: the comparison would be trivial"
+        got = seg_got.argmax(2).cpu()
+        flips = got != want
+        dmax = float((seg_got - seg_ref).abs().max())
+        margin = (seg_ref[:, :, 0] - seg_ref[:, :, 1]).abs().cpu()
+        report.append(dict(seed=seed, precision=precision, minority_pixels=minority, min_margin=float(margin.min()), max_logit=float(seg_ref.abs().max()),
+                           logit_err=dmax, logit_rel_err=dmax / float(seg_ref.abs().max()), flips=int(flips.sum()),
+                           pixels_within_2err=int((margin < 2 * dmax).sum())))
+        assert dmax / float(seg_ref.abs().max()) < 5 * TOL[precision], report[-1]
+        if precision == "bf16x3":
+            assert torch.equal(got, want), report[-1]
+        else:
+            assert not bool((flips & (margin > 2 * dmax)).any()), report[-1]
+            assert int(flips.sum()) <= max(2, int((margin < 2 * dmax).sum())), report[-1]
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"argmax_report_{precision}.json"), "w") as f:
+            json.dump(dict(all_seeds=json.loads(str(z["all_seeds"])), results=report), f, indent=1)

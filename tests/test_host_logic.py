@@ -30,6 +30,18 @@ def test_product_schedule_matches_reference_traces(golden_dir):
         assert plan.picks == c["selected"], c["tag"]
 
 
+def test_product_schedule_with_float32_stamps_matches_reference_traces(golden_dir):
+    """float32 timestamp tensors make the reference's loop compare / subtract in float32; plan_sample reproduces it."""
+    cases = json.load(open(os.path.join(golden_dir, "sched_f32.json")))["cases"]
+    for c in cases:
+        plan = sc.plan_sample(c["times"], c["targets"], c["delta_t"], c["variable"], c["solver"], obs_dtype="float32", target_dtype="float32")
+        assert [("step" if o.kind == sc.STEP else "jump") for o in plan.ops] == c["kinds"], c["tag"]
+        for o, dt, ta in zip(plan.ops, c["dts"], c["t_after"]):
+            if o.kind == sc.STEP:
+                assert o.dt == dt and o.t == ta, (c["tag"], o.dt, dt)
+        assert plan.picks == c["selected"], c["tag"]
+
+
 def test_schedule_matches_oracle_on_random_stamps():
     rng = np.random.RandomState(0)
     for trial in range(200):
@@ -470,3 +482,86 @@ def test_refinement_stage_graph_reproduces_reference_refinement():
         want = so.deeplab_head(sd64, "res_blocks.1", y.reshape(B * T, 64, H, W)).view(B, T, 64, H, W)
     assert got.shape == want.shape
     assert ((got - want).abs().max() / want.abs().max()).item() < 5e-4
+
+
+def test_module_can_be_deep_copied_and_pickled(golden_dir):
+    """EMA copies (copy.deepcopy) and whole-module saves (pickle / torch.save) must work before AND after the
+    first forward; the copy owns its cells (inner API routed to the copy, not the original) and rebuilds its engines."""
+    import copy
+    import io
+    import pickle
+
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C, H = int(z["C"]), int(z["H"])
+    m = _tiny_module(z, torch.float64)
+    c0 = copy.deepcopy(m)
+    assert c0.gru_ode.gru_c._owner() is c0.gru_ode and c0.gru_ode.gru_obs.gru_d._owner() is c0.gru_ode
+    assert m.gru_ode.gru_c._owner() is m.gru_ode
+    args = (torch.zeros(1, 1, C, H, H, dtype=torch.float64), so.recipe_array("cam", (1, 3, C, H, H), 1, torch.float64), None,
+            torch.tensor([[-1.0, -0.5, 0.0]], dtype=torch.float64), None, torch.tensor([[0.5, 1.0]], dtype=torch.float64))
+    with torch.no_grad():
+        torch.manual_seed(5)
+        want, _ = m(*args)
+    assert m.gru_ode._engines                       # the first forward built an engine (here: the checker backend)
+    c1 = copy.deepcopy(m)                           # ... which a copy must not share
+    assert c1.gru_ode._engines == {} and c1._refiners == {} and c1.gru_ode.gru_c._owner() is c1.gru_ode
+    m.gru_ode.__dict__["_engine_factory"] = None    # lambdas do not pickle; the product never sets a factory
+    blob = pickle.dumps(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    for c in (pickle.loads(blob), torch.load(io.BytesIO(buf.getvalue()), weights_only=False)):
+        assert c.gru_ode._engines == {} and c.gru_ode.gru_c._owner() is c.gru_ode
+        assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
+    c1.gru_ode.__dict__["_engine_factory"] = lambda sd, h, w, n, prec, dev: OracleBackend(sd, h, w, n, prec, dev, torch.float64)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        got, _ = c1(*args)
+        dh = c1.gru_ode.gru_c(torch.zeros(1, C, 4, 4, dtype=torch.float64), torch.zeros(1, C, 4, 4, dtype=torch.float64))
+    assert torch.equal(got, want) and dh.shape == (1, C, 4, 4)
+
+
+def test_module_refuses_to_cut_gradients(golden_dir):
+    """ADVICE r1 / SURVEY 7.3: the engine has no backward; with autograd recording and anything that requires grad in reach the
+    module raises instead of returning tensors without a grad_fn."""
+    from streamingflow_b200._lib import SfError
+
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C, H = int(z["C"]), int(z["H"])
+    m = _tiny_module(z, torch.float64)
+    cam = so.recipe_array("cam", (1, 3, C, H, H), 1, torch.float64)
+    args = lambda c: (torch.zeros(1, 1, C, H, H, dtype=torch.float64), c, None, torch.tensor([[-1.0, -0.5, 0.0]], dtype=torch.float64), None,
+                      torch.tensor([[0.5]], dtype=torch.float64))
+    with pytest.raises(SfError, match="no_grad"):
+        m(*args(cam))                                            # parameters require grad, autograd is recording
+    for p in m.parameters():
+        p.requires_grad_(False)
+    with pytest.raises(SfError, match="no_grad"):
+        m(*args(cam.clone().requires_grad_(True)))               # frozen module, but the input wants a gradient
+    x, _ = m(*args(cam))                                         # frozen module, plain input: fine without no_grad
+    assert x.shape == (1, 1, C, H, H)
+    with pytest.raises(SfError):
+        m.gru_ode.infer_state(torch.zeros(1, C, 4, 4, dtype=torch.float64, requires_grad=True))
+    with torch.no_grad():
+        empty, aux = m(torch.zeros(0, 1, C, H, H), cam[:0], None, torch.zeros(0, 3, dtype=torch.float64), None, torch.zeros(0, 2, dtype=torch.float64))
+    assert empty.shape == (0, 2, C, H, H) and aux == 0
+
+
+def test_float32_stamps_follow_the_reference_float32_schedule(golden_dir):
+    """FuturePredictionODE.forward / NNFOwithBayesianJumps.forward pass the stamp tensors' dtype to the scheduler: float32 stamps
+    give the float32-arithmetic schedule of the reference (tests/golden/sched_f32.json), not the float64 one."""
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C, H = int(z["C"]), int(z["H"])
+    m = _tiny_module(z, torch.float64)
+    cases = json.load(open(os.path.join(golden_dir, "sched_f32.json")))["cases"]
+    c = next(c for c in cases if c["variable"] and
+             [e.kind for e in so.build_schedule(c["times"], c["targets"], 0.05, True).events] != c["kinds"])
+    obs = so.recipe_array("obs", (1, len(c["times"]), C, H, H), 2, torch.float64)
+    with torch.no_grad():
+        m.gru_ode(torch.tensor(c["times"], dtype=torch.float32), torch.zeros(1, 1, C, H, H, dtype=torch.float64), obs, 0.05,
+                  torch.tensor(c["targets"], dtype=torch.float32))
+    ro = m.gru_ode.last_rollout
+    assert ro.n_state_steps == sum(k == "step" for k in c["kinds"]) and ro.n_jumps == sum(k == "jump" for k in c["kinds"])
+    with torch.no_grad():
+        m.gru_ode(torch.tensor(c["times"], dtype=torch.float64), torch.zeros(1, 1, C, H, H, dtype=torch.float64), obs, 0.05,
+                  torch.tensor(c["targets"], dtype=torch.float64))
+    assert m.gru_ode.last_rollout.n_state_steps != ro.n_state_steps

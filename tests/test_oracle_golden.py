@@ -35,6 +35,23 @@ def test_schedule_traces_match_reference(golden_dir):
     assert n_micro >= 3, "fixture must contain micro-step cases (SURVEY F6)"
 
 
+def test_schedule_with_float32_stamps_matches_reference_traces(golden_dir):
+    """Reference traces with float32 timestamp tensors (tests/golden/sched_f32.json): comparisons and variable steps are
+    float32 arithmetic there; most of these schedules differ from the float64 arithmetic on the same stamps."""
+    cases = json.load(open(os.path.join(golden_dir, "sched_f32.json")))["cases"]
+    differ = 0
+    for c in cases:
+        sch = so.build_schedule(c["times"], c["targets"], c["delta_t"], c["variable"], stamp_dtype=np.float32)
+        assert [e.kind for e in sch.events] == c["kinds"], c["tag"]
+        for e, dt, ta in zip(sch.events, c["dts"], c["t_after"]):
+            if e.kind == "step":
+                assert e.dt == dt and e.t_after == ta, (c["tag"], e.dt, dt, e.t_after, ta)
+        assert [sch.path_ev[i] for i in sch.select] == c["selected"], c["tag"]
+        s64 = so.build_schedule(c["times"], c["targets"], c["delta_t"], c["variable"])
+        differ += [(e.kind, e.dt) for e in s64.events] != [(e.kind, e.dt) for e in sch.events]
+    assert differ >= 10
+
+
 def test_known_answer_counts():
     """SURVEY 8(c) known-answer schedule counts, probed on the reference."""
     times = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
