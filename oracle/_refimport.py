@@ -16,11 +16,49 @@ import sys
 import types
 from types import SimpleNamespace as NS
 
-REFERENCE_ROOT = os.environ.get("SF_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The files of the reference that the ODE head needs, relative to the reference root.  ``stage_reference()``
+# (called by ``__graft_entry__.build()`` in the builder container) copies them UNMODIFIED into the git-ignored
+# ``baseline/_ref/`` so that ``bench.py --impl reference`` can time the reference itself on the GPU box's host cores,
+# where /root/reference does not exist.  Nothing of it is ever part of the repository history or of the product.
+REFERENCE_FILES = ("streamingflow/layers/temporal_ode_bayes.py", "streamingflow/layers/res_models.py",
+                   "streamingflow/layers/convolutions.py", "streamingflow/layers/temporal.py",
+                   "streamingflow/models/model_utils.py", "streamingflow/models/future_prediction_ode.py",
+                   "streamingflow/models/decoder.py", "streamingflow/utils/geometry.py", "LICENSE")
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _has_tree(root) -> bool:
+    return os.path.isdir(os.path.join(root, "streamingflow", "layers"))
+
+
+def _pick_root() -> str:
+    env = os.environ.get("SF_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has_tree("/root/reference") else STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "streamingflow", "layers"))
+    return _has_tree(REFERENCE_ROOT)
+
+
+def stage_reference(src: str = "/root/reference") -> bool:
+    """Copies REFERENCE_FILES from ``src`` to baseline/_ref/ (byte-identical).  Returns False when ``src`` is absent."""
+    import shutil
+
+    if not _has_tree(src):
+        return False
+    for rel in REFERENCE_FILES:
+        a, b = os.path.join(src, rel), os.path.join(STAGED_ROOT, rel)
+        if not os.path.exists(a):
+            continue
+        os.makedirs(os.path.dirname(b), exist_ok=True)
+        shutil.copyfile(a, b)
+    return True
 
 
 def _install_stubs():

@@ -479,3 +479,57 @@ def test_argmax_masks_match_reference_on_margin_selected_seeds(precision):
     if os.path.isdir(out):
         with open(os.path.join(out, f"argmax_report_{precision}.json"), "w") as f:
             json.dump(dict(all_seeds=json.loads(str(z["all_seeds"])), results=report), f, indent=1)
+
+
+def test_captured_graphs_retire_when_weights_or_buffers_are_rebound():
+    """with CUDA graphs on, (a) reloading / updating the weights re-packs them into new device buffers --
+    the graphs captured with the old pointers must not be replayed (resident and streamed paths); (b) alternating the fused
+    encoder path (observation slot bound to the codec's planes) with the latent-level path (engine-owned observation buffer)
+    must not leave a graph reading a buffer it no longer owns.  Every result is compared with an eager engine."""
+    h = w = 24
+    times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])] * 2
+    targets = [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]] * 2
+    hx = torch.tanh(so.recipe_array("hx1", (16, 64, h, w), 5)).cuda()
+    tape = torch.stack([so.recipe_array(f"eps{i}", (64, h, w), 5) for i in range(40)]).cuda()
+    noise = lambda n, hh, ww, device: tape[:max(n, 1)].contiguous()
+
+    def run(m, streamed):
+        with torch.no_grad():
+            if streamed:
+                out = m.integrate_latents_streamed(hx.cpu().pin_memory(), [8, 8], times, targets, 0.05)
+                torch.cuda.synchronize()
+                return out[1].clone().cuda()
+            return m.integrate_latents(hx, [8, 8], times, targets, 0.05)[1].clone()
+
+    mg = _nnfo("euler", True, True, 5, 1.0, "bf16")
+    mg.cuda_graph = True
+    mg._draw_noise = noise
+    first = {s: run(mg, s) for s in (False, True)}
+    again = {s: run(mg, s) for s in (False, True)}                 # replays
+    assert all(torch.equal(first[s], again[s]) for s in first)
+    # (a) new weights, same module, graphs stay on
+    new_sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in mg.state_dict().items()}, 6, 1.0)
+    mg.load_state_dict(new_sd, strict=True)
+    got = {s: run(mg, s) for s in (False, True)}
+    me = _nnfo("euler", True, True, 6, 1.0, "bf16")                # eager engine with the new weights
+    me._draw_noise = noise
+    want = run(me, False)
+    assert not torch.equal(want, first[False])
+    assert torch.equal(got[False], want) and torch.equal(got[True], want)
+    with torch.no_grad():                                          # an in-place update (optimizer / EMA style) bumps the version counters
+        for p in mg.gru_c.parameters():
+            p.mul_(0.5)
+        for p in me.gru_c.parameters():
+            p.mul_(0.5)
+    assert torch.equal(run(mg, False), run(me, False)) and torch.equal(run(mg, True), run(me, False))
+    # (b) fused encoder path <-> latent-level graph path on one engine (same latent size: BEV 96 -> 24)
+    obs = so.recipe_array("obs", (1, 8, 64, 4 * h, 4 * w), 5).cuda()
+    t64, T64 = torch.tensor(times[0], dtype=torch.float64), torch.tensor(targets[0], dtype=torch.float64)
+
+    def fwd(m):
+        with torch.no_grad():
+            return m(t64, torch.zeros(1, 1, 64, 4 * h, 4 * w, device="cuda"), obs, 0.05, T64)[2].clone()
+
+    seq_g = [fwd(mg), run(mg, False), fwd(mg), run(mg, False), run(mg, True), fwd(mg)]
+    seq_e = [fwd(me), run(me, False), fwd(me), run(me, False), run(me, False), fwd(me)]
+    assert all(torch.equal(a, b) for a, b in zip(seq_g, seq_e))
