@@ -1,6 +1,8 @@
-"""torchrun worker: row-sharded rollout on WORLD_SIZE GPUs vs the unsharded engine on rank 0's GPU.
+"""torchrun worker: row-sharded rollout on WORLD_SIZE GPUs vs (a) the fp64 ORACLE evaluated on rank 0's GPU and (b) the
+unsharded engine.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_row_sharding.py [H W B precision C]
-Prints one JSON line from rank 0 (max relative error of the gathered latents, timing)."""
+Prints one JSON line from rank 0 (max relative errors of the gathered latents, timing).  tests/test_gpu_row_sharding.py spawns
+it and asserts the oracle error against the north-star tolerance."""
 import json
 import os
 import sys
@@ -55,7 +57,21 @@ with torch.no_grad():
         torch.cuda.synchronize()
         dt_single = time.perf_counter() - t0
         err = ((full.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
+        # the oracle (fp64, same ATen calls as the reference) on the same observations and noise tape, sample by sample
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sd64 = {"g." + k: (v.double() if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+        it = iter(tape.double()[:, None])
+        want = []
+        for b in range(B):
+            sch = so.build_schedule(times[b], targets[b], 0.05, True)
+            _, path = so.integrate_latent(sd64, "g", hx[8 * b:8 * b + 8].double(), sch, it)
+            want.append(torch.stack([path[i][0] for i in sch.select]))
+        want = torch.stack(want)
+        err_oracle = ((full.double() - want).abs().max() / want.abs().max()).item()
+        err_single_oracle = ((ref.double() - want).abs().max() / want.abs().max()).item()
         print(json.dumps(dict(test="row_sharding", world=world, H=H, W=W, B=B, C=C, precision=precision, max_rel_err=err,
+                              max_rel_err_vs_oracle=err_oracle, single_gpu_max_rel_err_vs_oracle=err_single_oracle,
                               ms_sharded=1e3 * dt_sharded, ms_single_gpu=1e3 * dt_single, events=len(ro.events),
                               halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo,
                               launch="graph segments" if use_graphs else "eager")), flush=True)
