@@ -206,6 +206,10 @@ int sf_diag_umma(const void* a_bf16, const void* b_bf16, float* d, int n, int k_
 int sf_diag_umma_shift(const void* a_bf16, const void* b_bf16, float* d, int n, int rows_a, int shift, int sbo_rows, int base_mode,
                        void* stream);
 
+/* bring-up of the back-to-back GEMM in the fused trunk epilogue: A [128 x 64] bf16 written to tensor memory by the threads
+ * (tcgen05.st, two elements per column, at column a_col >= n), B [n x 64] from shared memory; d [128 x n] fp32 */
+int sf_diag_umma_ts(const void* a_bf16, const void* b_bf16, float* d, int n, int a_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

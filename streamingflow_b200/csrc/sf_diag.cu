@@ -142,6 +142,64 @@ __global__ void __launch_bounds__(128) diag_umma_shift_kernel(const __grid_const
     tmem_dealloc(tmem, 256);
   }
 }
+
+// Experiment / bring-up for back-to-back GEMMs in an epilogue: the A operand of tcgen05.mma read from TENSOR MEMORY.
+// Each thread (= TMEM lane = row m) packs its row of A [128 x 64] bf16 two elements per 32-bit column (element 2c in the low
+// half of column c) and writes the 32 columns with tcgen05.st at column a_col; B [n x 64] comes from shared memory (TMA,
+// SWIZZLE_128B).  D[m][j] = sum_k A[m][k] B[j][k] lands at column 0.  K step kk (16 elements) reads A columns a_col + 8 kk.
+__global__ void __launch_bounds__(128) diag_umma_ts_kernel(const __nv_bfloat16* a, const __grid_constant__ CUtensorMap bmap, float* d, int n, int a_col) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full, done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&full), 1);
+    mbar_init(smem_u32(&done), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int m = warp * 32 + lane;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(a + (size_t)m * 64);     // 32 packed pairs
+    float lo[16], hi[16];
+    for (int i = 0; i < 16; ++i) { lo[i] = __uint_as_float(row[i]); hi[i] = __uint_as_float(row[16 + i]); }
+    tmem_st16(lane_addr + a_col, lo);
+    tmem_st16(lane_addr + a_col + 16, hi);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    mbar_expect_tx(smem_u32(&full), (uint32_t)n * 128);
+    for (int j = 0; j < n / 64; ++j) tma_load_2d(smem_u32(sb) + j * 64 * 128, &bmap, smem_u32(&full), 0, j * 64);
+    mbar_wait(smem_u32(&full), 0, nullptr, 8);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n);
+    for (int kk = 0; kk < 4; ++kk) umma_bf16_ts(tmem, tmem + a_col + 8 * kk, make_sw128_desc(smem_u32(sb) + kk * 32), idesc, kk ? 1u : 0u);
+    umma_commit(smem_u32(&done));
+    mbar_wait(smem_u32(&done), 0, nullptr, 9);
+  }
+  __syncthreads();
+  tc_fence_after();
+  for (int j = 0; j < n / 16; ++j) {
+    float v[16];
+    tmem_ld16(lane_addr + j * 16, v);
+    for (int i = 0; i < 16; ++i) d[(size_t)m * n + j * 16 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -165,6 +223,23 @@ int sf_diag_umma_shift(const void* a_bf16, const void* b_bf16, float* d, int n, 
   const int smem = 65536 + 32768 + 1024;
   cudaFuncSetAttribute(reinterpret_cast<const void*>(diag_umma_shift_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   diag_umma_shift_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(am, bm, d, n, rows_a, shift, sbo_rows, base_mode);
+  return cudaGetLastError() == cudaSuccess ? SF_OK : SF_ERR_CUDA;
+}
+
+int sf_diag_umma_ts(const void* a_bf16, const void* b_bf16, float* d, int n, int a_col, void* stream) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || n % 64 || n > 256 || n <= 0 || a_col < n || a_col + 32 > 512) return SF_ERR_INVALID;
+  CUtensorMap bm;
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t stride[1] = {128};
+  cuuint64_t bdims[2] = {64, (cuuint64_t)n};
+  if (enc(&bm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b_bf16), bdims, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return SF_ERR_CUDA;
+  const int smem = 32768 + 1024;
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(diag_umma_ts_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  diag_umma_ts_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16), bm, d, n, a_col);
   return cudaGetLastError() == cudaSuccess ? SF_OK : SF_ERR_CUDA;
 }
 

@@ -71,6 +71,20 @@ def test_single_umma_tile_product(n, kc):
     assert (d.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("n,a_col", [(64, 64), (64, 96), (128, 128)])
+def test_umma_a_operand_from_tensor_memory(n, a_col):
+    """The back-to-back GEMM of the fused trunk epilogue: A [128, 64] written to TMEM by the epilogue threads (two bf16 per
+    32-bit column, row m on lane m), B from shared memory -> D[128, n] in TMEM."""
+    L, lib = _lib()
+    a = torch.randn(128, 64, device="cuda").to(torch.bfloat16)
+    b = torch.randn(n, 64, device="cuda").to(torch.bfloat16)
+    d = torch.zeros(128, n, device="cuda")
+    L.check(lib.sf_diag_umma_ts(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, a_col, _stream()), "diag_umma_ts")
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    assert (d.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_layout_kernels_roundtrip():
     L, lib = _lib()
     n, Cc, H, W = 3, 64, 50, 50
