@@ -69,7 +69,7 @@ typedef struct {
   int32_t ox, oy;   /* pixel offset of the chunk's input window (dilated taps are R = 1 chunks at (kx-1)*d, (ky-1)*d) */
 } sf_chunk;
 
-#define SF_MAX_CHUNKS 24
+#define SF_MAX_CHUNKS 40
 #define SF_MAX_ACT_BUFS 32
 #define SF_MAX_STAGES 32
 
@@ -138,7 +138,13 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
    adjacent taps [dy = 1 | 0], [3 | 2], ... (+ the last tap alone when R is odd), per rep [tap_hi rows | tap_lo rows]; the kernel
    issues one MMA of twice the width per pair and folds the second column block back one row in the epilogue;
    bit 7 (res_id) the residual input is multiplied by the per-sample channel scales of SE layer (flags >> 8) & 1 (the SE
-   layer was folded into its consumers, see sf_plan_define_stage_fold).                                                  */
+   layer was folded into its consumers, see sf_plan_define_stage_fold);
+   bit 12 (propose) the output is the GRU-ODE derivative u (s~ - s) instead of the blend; with activation code 2 in bits 1-3 the
+   proposal is ReLU(conv + bias) (the plain SpatialGRUODECell / SpatialGRUCell, temporal_ode_bayes.py:14-61, 165-208);
+   bit 11 (res_id) the activation is applied after the residual add: out = act(conv + bias + residual) (ResNet BasicBlock);
+   bit 10 (lngelu, C = 64) a 1x1 convolution + LayerNorm + GELU fused behind the stage (convolutions.py:356-361 in ONE launch):
+   its [C][64] weights (hi rows, then lo rows in BF16X3) are the LAST rows of w_packed and vec = [LN1 w, LN1 b, LN2 w, LN2 b];
+   the epilogue keeps the first LN+GELU result in tensor memory as the A operand of a back-to-back GEMM.                */
 int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, const sf_chunk* chunks,
                          const void* w_packed, int w_rows, const float* vec, int n_vec,
                          const int32_t* io_bufs, const int32_t* io_choff, int n_io, int flags);
@@ -205,6 +211,17 @@ int sf_diag_umma(const void* a_bf16, const void* b_bf16, float* d, int n, int k_
 /* experiment: 128 operand rows starting `shift` rows into a swizzled box, 8-row groups `sbo_rows` rows apart */
 int sf_diag_umma_shift(const void* a_bf16, const void* b_bf16, float* d, int n, int rows_a, int shift, int sbo_rows, int base_mode,
                        void* stream);
+
+/* BEV Decoder head (streamingflow/models/decoder.py:91-140), the kernels next to the conv stages:
+ * space to depth for the stride-2 convolutions: dst[img][i][j][(2 py + px) C + c] = src[img][2i + py][2j + px][c] (one plane);
+ * UpsamplingAdd with its 1x1 conv + BN hoisted to the low resolution: dst = bilinear_x2(src) + skip (planes hi [+ lo]);
+ * a head's output 1x1 conv (64 -> K <= 4, + bias, optional sigmoid) -> fp32 NCHW [img][K][H][W] and, with mask != NULL,
+ * the per-pixel arg-max over the K channels as uint8 [img][H][W] (trainer.py:230-231).                                  */
+int sf_space_to_depth2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream);
+int sf_bilinear_up2_add(const void* src_hi, const void* src_lo, const void* skip_hi, const void* skip_lo, void* dst_hi, void* dst_lo,
+                        int n_images, int H, int W, int C, void* stream);
+int sf_head_1x1(const void* src_hi, const void* src_lo, const float* w, const float* b, int K, int sigmoid_out, float* out,
+                unsigned char* mask, int n_images, int H, int W, void* stream);
 
 /* bring-up of the back-to-back GEMM in the fused trunk epilogue: A [128 x 64] bf16 written to tensor memory by the threads
  * (tcgen05.st, two elements per column, at column a_col >= n), B [n x 64] from shared memory; d [128 x n] fp32 */

@@ -277,6 +277,17 @@ def gen_decoder(ref, out_dir):
     np.savez_compressed(os.path.join(out_dir, "decoder_seg_c64.npz"), seed=17, gain=1.0, seg_f64=seg.numpy(),
                         shapes_keys=np.array(list(shapes.keys())), shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
     print("decoder_seg_c64.npz:", tuple(seg.shape), "argmax class-1 fraction", float((seg.argmax(2) == 1).double().mean()))
+    # every head (all predict gates on), n_present = 2: pins oracle.bev_decoder
+    gate = {k: True for k in gate}
+    d = dec_mod.Decoder(in_channels=64, n_classes=2, n_present=2, n_hdmap=2, predict_gate=gate).eval().double()
+    shapes = {k: tuple(v.shape) for k, v in d.state_dict().items()}
+    d.load_state_dict(so.recipe_state_dict(shapes, 19, 1.0, torch.float64), strict=True)
+    x = so.recipe_array("dec_in", (1, 3, 64, 32, 32), 19, torch.float64)
+    with torch.no_grad():
+        out = d(x)
+    np.savez_compressed(os.path.join(out_dir, "decoder_all_c64.npz"), seed=19, gain=1.0, n_present=2, **{k: v.numpy() for k, v in out.items()},
+                        shapes_keys=np.array(list(shapes.keys())), shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
+    print("decoder_all_c64.npz:", {k: tuple(v.shape) for k, v in out.items()})
 
 
 ARGMAX_SEEDS = tuple(range(101, 141))

@@ -481,6 +481,13 @@ def _upsampling_add(sd: SD, p: str, x: Tensor, skip: Tensor) -> Tensor:
 
 def seg_decoder(sd: SD, p: str, x: Tensor) -> Tensor:
     """decoder.py:91-140, segmentation output only: x [B,S,C,H,W] -> logits [B,S,n_classes,H,W]."""
+    return bev_decoder(sd, p, x, 1)["segmentation"]
+
+
+def bev_decoder(sd: SD, p: str, x: Tensor, n_present: int) -> Dict[str, Optional[Tensor]]:
+    """decoder.py:91-140 Decoder.forward with every head whose parameters are in ``sd`` (the predict_gate of the constructor
+    decides which exist): shared ResNet-18 trunk + UpsamplingAdd x3, then per head conv3x3-BN-ReLU-conv1x1 (+ Sigmoid for the
+    instance centre); hdmap on the present frame only (:126), costvolume squeezed (:130)."""
     b, s, c, h, w = x.shape
     x = x.reshape(b * s, c, h, w)
     skip1 = x
@@ -493,10 +500,21 @@ def seg_decoder(sd: SD, p: str, x: Tensor) -> Tensor:
     x = _upsampling_add(sd, p + ".up3_skip", x, skip3)
     x = _upsampling_add(sd, p + ".up2_skip", x, skip2)
     x = _upsampling_add(sd, p + ".up1_skip", x, skip1)
-    y = F.conv2d(x, sd[p + ".segmentation_head.0.weight"], None, padding=1)
-    y = torch.relu(_bn_eval(sd, p + ".segmentation_head.1", y))
-    y = F.conv2d(y, sd[p + ".segmentation_head.3.weight"], sd[p + ".segmentation_head.3.bias"])
-    return y.view(b, s, *y.shape[1:])
+    def head(name, inp):
+        if (p + f".{name}.0.weight") not in sd:
+            return None
+        y = F.conv2d(inp, sd[p + f".{name}.0.weight"], None, padding=1)
+        y = torch.relu(_bn_eval(sd, p + f".{name}.1", y))
+        return F.conv2d(y, sd[p + f".{name}.3.weight"], sd[p + f".{name}.3.bias"])
+
+    view = lambda t: None if t is None else t.view(b, s, *t.shape[1:])
+    center = head("instance_center_head", x)
+    cost = head("costvolume_head", x)
+    return {"segmentation": view(head("segmentation_head", x)), "pedestrian": view(head("pedestrian_head", x)),
+            "hdmap": head("hdmap_head", x.view(b, s, *x.shape[1:])[:, n_present - 1]),
+            "instance_center": view(None if center is None else torch.sigmoid(center)),
+            "instance_offset": view(head("instance_offset_head", x)), "instance_flow": view(head("instance_future_head", x)),
+            "costvolume": None if cost is None else cost.squeeze(1).view(b, s, *cost.shape[2:])}
 
 
 # --------------------------------------------------------------------------------------------

@@ -16,6 +16,9 @@ PREC_BF16, PREC_BF16X3 = 0, 1
 ACT_LRELU, ACT_TANH, ACT_RELU, ACT_NONE, ACT_GELU = 0, 1, 2, 3, 4
 FLAG_KEEP_A32, FLAG_OUT32, FLAG_SINGLE, FLAG_IMG_BIAS, FLAG_RES_SE_SCALE = 1, 16, 32, 64, 128   # bit 8: which SE layer scales the residual
 FLAG_PAIR_ROWS = 512          # lngelu stages at C = 64: vertically adjacent taps paired into one MMA of twice the width
+FLAG_ACT_AFTER_RES = 2048     # res_id: out = act(conv + bias + residual) (ResNet BasicBlock) instead of act(conv + bias) + residual
+FLAG_DERIV = 4096             # propose: output u (s~ - s) (GRU-ODE derivative) instead of the blended state
+FLAG_B2B = 1024               # lngelu stages at C = 64: a 1x1 conv + LN + GELU fused behind the stage (weights appended to w_packed)
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
 SE_ITEM_BASE = 1000          # event-graph item: SE reduce + apply (activation pass)
 SE_FOLD_ITEM_BASE = 2000     # event-graph item: SE reduce + scales folded into the consumers' weights
@@ -62,6 +65,10 @@ EXPORTS = {
     "sf_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_upsample2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_cast_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_space_to_depth2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_bilinear_up2_add": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_head_1x1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p]),
     "sf_dwconv7_ln": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_aspp_pool_bias": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),

@@ -66,6 +66,8 @@ struct EpiArgs {
   int n_out;      // output channels written by this launch (64 or 128)
   int kind;       // event kind (0 derivative step, 1 jump)
   int act;        // bias_act / residual epilogues: 0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU
+  int act_after_res;   // res_id: the activation is applied to conv + bias + residual (stage flag 2048)
+  int deriv;           // propose: write u (s~ - s) instead of the blend (stage flag 4096)
   int pairs;      // gate pairs / proposals handled by this launch (2 at C = 64 in the dual cell, else 1)
   const float* res_scale;  // optional SE scales [active sample][res_scale_ch] multiplied into the residual input (res_id)
   int res_scale_ch;
@@ -91,6 +93,8 @@ struct alignas(64) StageParams {
   int pair_rows;             // 1: vertically adjacent taps are paired into one MMA of twice the width (see conv_stage_kernel)
   int wg_scratch;            // floats of shared scratch per epilogue warpgroup
   int w_rows_per_sample;     // > 0: per-sample weights (SE layer folded in): active sample bi reads rows [bi * this, (bi+1) * this)
+  int b2b_wrow;              // lngelu_b2b: first row of the 1x1 follow-up conv's weights [CG n x 64 k] (hi, then lo in the split mode)
+  int b2b_bytes;             // ... and their size in shared memory (loaded once per CTA)
   int* err;
   EpiArgs e;
 };
@@ -150,7 +154,16 @@ __device__ __forceinline__ void store_f32x16(float* p, const float (&v)[16]) {
 // SF_EPI_BIAS_LRELU / SF_EPI_RES_ID instantiations; launch_stage picks the variant from the stage flags.
 constexpr int SF_EPI_BIAS_ACT = 9;
 constexpr int SF_EPI_RES_ID_ACT = 10;
-constexpr int SF_EPI_KERNELS = 11;
+// lngelu followed, inside the same epilogue, by a 1x1 convolution + LayerNorm + GELU (the Bottleblock's layers 0..5 in one
+// launch): a back-to-back GEMM whose A operand is written to tensor memory by the epilogue threads (stage flag 1024)
+constexpr int SF_EPI_LNGELU_B2B = 11;
+constexpr int SF_EPI_KERNELS = 12;
+
+// per-warpgroup state of the back-to-back GEMM (shared-window addresses; phase = parity of the group's completion barrier)
+struct B2BCtx {
+  uint32_t w_smem, w_full, done_bar, phase;
+  bool w_ready;
+};
 
 // v = act(v + b) on a 16-channel slice; the activation code is uniform per launch, so the switch is taken once per slice
 template <bool ANYACT>
@@ -223,7 +236,7 @@ struct PixelCtx {
 // as their last tcgen05.ld has completed (returning true), so the next tile's MMAs overlap that tail; otherwise the caller
 // arrives after the epilogue returns.
 template <int EPI, bool X3, int CG>
-__device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c, uint32_t acc_empty) {
+__device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c, uint32_t acc_empty, B2BCtx& b2b) {
   const EpiArgs& e = p.e;
   constexpr int NJ = CG / 16;                      // 16-channel slices of one CG-channel tensor
   const size_t pc = c.pix * CG;                    // this pixel in a CG-channel NHWC tensor
@@ -278,8 +291,20 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
           float t[16], b[16];
           tmem_ld16(taddr + k * CG + j * 16, t);
           vec16(vec, k * CG + j * 16, b);
+          if (e.act == 2 || e.deriv) {
+            // the plain ConvGRU cells (temporal_ode_bayes.py:14-61, 165-208): ReLU proposal (BatchNorm folded into the conv),
+            // and for the ODE variant the derivative u (s~ - s) instead of the blended state
+            const bool relu = e.act == 2, deriv = e.deriv != 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) t[i] = fmaf(u[k][i], (t[i] + b[i]) - s[i], s[i]);      // (1 - u) s + u s~
+            for (int i = 0; i < 16; ++i) {
+              float st = t[i] + b[i];
+              st = relu ? fmaxf(st, 0.0f) : st;
+              t[i] = deriv ? u[k][i] * (st - s[i]) : fmaf(u[k][i], st - s[i], s[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = fmaf(u[k][i], (t[i] + b[i]) - s[i], s[i]);      // (1 - u) s + u s~
+          }
           if (c.valid) {
             if (k == 0 && e.a32) store_f32x16(e.a32 + pc + j * 16, t);
             store_act16<X3>(e.out_h[k], e.out_l[k], pc + j * 16, t);
@@ -301,7 +326,7 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
         store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, b);
       }
     }
-  } else if constexpr (EPI == SF_EPI_LNGELU) {
+  } else if constexpr (EPI == SF_EPI_LNGELU || EPI == SF_EPI_LNGELU_B2B) {
     if (p.pair_rows) {
       // Row-paired taps: column block 1 [CG, 2CG) of lane m holds the partial sum that belongs to the pixel ONE ROW BELOW
       // (lane m + 8).  Fold it in: block0[m] += block1[m - 8].  Inside a warp that is a shuffle by 8 lanes; the first row of a
@@ -335,15 +360,82 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
     }
     float mean, rstd;
     ln_stats<CG>(taddr, mean, rstd);
+    if constexpr (EPI == SF_EPI_LNGELU) {
 #pragma unroll 1
-    for (int j = 0; j < NJ; ++j) {
-      float v[16], w[16], b[16];
-      tmem_ld16(taddr + j * 16, v);
-      vec16(vec, j * 16, w);
-      vec16(vec, CG + j * 16, b);
+      for (int j = 0; j < NJ; ++j) {
+        float v[16], w[16], b[16];
+        tmem_ld16(taddr + j * 16, v);
+        vec16(vec, j * 16, w);
+        vec16(vec, CG + j * 16, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
-      if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, v);
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
+        if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, v);
+      }
+    } else {
+      // Back-to-back GEMM.  t1 = GELU(LN(conv)) never leaves the SM: every thread writes its pixel's CG channels as bf16 pairs
+      // into the tensor-memory columns [CG, CG + CG/2) of its lane (block 1 is dead after the fold) -- the A operand [128 pixels
+      // x CG] of the 1x1 convolution, whose weights [CG x CG] sit in shared memory for the whole launch.  One thread of the
+      // warpgroup issues the MMAs (K = CG) into columns [0, CG) (every lane has read its conv result by then), everybody waits
+      // for their completion barrier, and the second LayerNorm + GELU runs on the new accumulator.  Split mode: the residual
+      // plane goes to [CG + CG/2, 2 CG) and three products are issued (t1h Wh + t1h Wl + t1l Wh).
+      static_assert(CG == 64, "the fused trunk is built for 64 channels (128 columns per accumulator slot)");
+#pragma unroll 1
+      for (int j = 0; j < NJ; ++j) {
+        float v[16], w[16], b[16];
+        tmem_ld16(taddr + j * 16, v);
+        vec16(vec, j * 16, w);
+        vec16(vec, CG + j * 16, b);
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        tmem_st8(taddr + CG + j * 8, h);
+        if (X3) {
+          uint32_t l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) l[i] = pack_bf16x2(v[2 * i] - bf16_lo_f(h[i]), v[2 * i + 1] - bf16_hi_f(h[i]));
+          tmem_st8(taddr + CG + CG / 2 + j * 8, l);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
+      if (c.m == 0) {
+        tc_fence_after();
+        if (!b2b.w_ready) mbar_wait(b2b.w_full, 0, p.err, 7);
+        constexpr uint32_t B_HI = 64u | (1u << 14) | (2u << 29);       // SBO = 1024 B, version 1, SWIZZLE_128B
+        const uint32_t idesc = make_idesc_bf16(128, CG);
+        const uint32_t w_lo = (b2b.w_smem & 0x3FFFFu) >> 4;
+#pragma unroll
+        for (uint32_t k = 0; k < CG / 16; ++k)
+          umma_bf16_ts(taddr, taddr + CG + 8 * k, ((uint64_t)B_HI << 32) | (w_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
+        if (X3) {
+          const uint32_t wl_lo = w_lo + ((CG * ROW_BYTES) >> 4);
+#pragma unroll
+          for (uint32_t k = 0; k < CG / 16; ++k)
+            umma_bf16_ts(taddr, taddr + CG + 8 * k, ((uint64_t)B_HI << 32) | (wl_lo + 2 * k), idesc, 1u);
+#pragma unroll
+          for (uint32_t k = 0; k < CG / 16; ++k)
+            umma_bf16_ts(taddr, taddr + CG + CG / 2 + 8 * k, ((uint64_t)B_HI << 32) | (w_lo + 2 * k), idesc, 1u);
+        }
+        umma_commit(b2b.done_bar);
+      }
+      b2b.w_ready = true;
+      mbar_wait(b2b.done_bar, b2b.phase, p.err, 8);
+      b2b.phase ^= 1;
+      tc_fence_after();
+      ln_stats<CG>(taddr, mean, rstd);
+#pragma unroll 1
+      for (int j = 0; j < NJ; ++j) {
+        float v[16], w[16], b[16];
+        tmem_ld16(taddr + j * 16, v);
+        vec16(vec, 2 * CG + j * 16, w);
+        vec16(vec, 3 * CG + j * 16, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(fmaf(w[i], (v[i] - mean) * rstd, b[i]));
+        if (c.valid) store_act16<X3>(e.out_h[0], e.out_l[0], pc + j * 16, v);
+      }
     }
   } else if constexpr (EPI == SF_EPI_MIX) {
     // columns: [0,CG) 3x3 trunk conv | [CG,2CG) 1x1 projection of cat[a,b];
@@ -465,6 +557,10 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
       tmem_ld16(taddr + j * 16, v);
       vec16(vec, j * 16, b);
       if (c.valid) {
+        if (EPI == SF_EPI_RES_ID_ACT && e.act_after_res) {       // ResNet BasicBlock: act(conv + bias + residual)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] += r[i]; r[i] = 0.0f; }
+        }
         bias_act16<EPI == SF_EPI_RES_ID_ACT>(v, b, e.act);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
@@ -523,7 +619,8 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   const int nA = p.nA, nB = p.nB;
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + (size_t)nA * p.a_slot_bytes;
-  float* vec_s = reinterpret_cast<float*>(b_base + (size_t)nB * p.b_slot_bytes);
+  uint8_t* b2b_w = b_base + (size_t)nB * p.b_slot_bytes;                 // weights of the fused 1x1 follow-up conv (1024-aligned)
+  float* vec_s = reinterpret_cast<float*>(b2b_w + (EPI == SF_EPI_LNGELU_B2B ? p.b2b_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX + p.wg_scratch * NGROUPS);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + nA;
@@ -531,7 +628,9 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   uint64_t* b_empty = b_full + nB;
   uint64_t* acc_full = b_empty + nB;
   uint64_t* acc_empty = acc_full + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S);
+  uint64_t* b2b_full = acc_empty + S;                 // 1 + NGROUPS barriers of the back-to-back GEMM (unused by the other epilogues)
+  uint64_t* b2b_done = b2b_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b2b_done + NGROUPS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably warp-uniform
   // warp roles: [0, 4*NGROUPS) epilogue warpgroups (warp % 4 = TMEM lane quadrant), then producer, MMA issuer, TMEM allocator
@@ -541,6 +640,10 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
     for (int i = 0; i < nA; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128 * MT); }
+    if (EPI == SF_EPI_LNGELU_B2B) {
+      mbar_init(smem_u32(b2b_full), 1);
+      for (int i = 0; i < NGROUPS; ++i) mbar_init(smem_u32(b2b_done + i), 1);
+    }
     mbar_fence_init();
   }
   if (warp == W_ALLOC) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -580,6 +683,11 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       if (elect_one()) {
         for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
         tma_prefetch_desc(&p.wmap);
+        if (EPI == SF_EPI_LNGELU_B2B) {          // the follow-up conv's weights: resident for the whole launch
+          mbar_expect_tx(smem_u32(b2b_full), (uint32_t)p.b2b_bytes);
+          for (int q = 0; q * 64 * ROW_BYTES < p.b2b_bytes; ++q)
+            tma_load_2d(smem_u32(b2b_w) + q * 64 * ROW_BYTES, &p.wmap, smem_u32(b2b_full), 0, p.b2b_wrow + q * 64);
+        }
       }
       uint32_t sa = 0, pa = 1, sb = 0, pb = 1;      // slot index and the parity to wait for on the EMPTY barrier
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -741,6 +849,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
     const int r = m >> 3, cx = m & 7;
     const uint32_t taddr = tmem_base + (uint32_t)st * STAGE_COLS + (uint32_t)mt * SLOT_COLS + ((uint32_t)(q * 32) << 16);
     uint32_t aph = 0;
+    B2BCtx b2b{smem_u32(b2b_w), smem_u32(b2b_full), smem_u32(b2b_done + g), 0u, false};
     // pixel of this thread in tile t (index into per-sample NHWC tensors), or -1 outside the image / past the last tile
     auto pixel_of = [&](int w, PixelCtx* out) -> long long {
       if (w >= nwork) return -1;
@@ -762,7 +871,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       mbar_wait(smem_u32(acc_full + st), aph, p.err, 6);
       tc_fence_after();
       bool released = false;
-      if (mine && !(p.debug & 1)) released = run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c, smem_u32(acc_empty + st));
+      if (mine && !(p.debug & 1)) released = run_epilogue<EPI, X3, CG>(p, vec_addr, taddr, c, smem_u32(acc_empty + st), b2b);
       if (!released) {
         tc_fence_before();
         mbar_arrive(smem_u32(acc_empty + st));

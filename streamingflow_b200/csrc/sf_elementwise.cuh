@@ -514,4 +514,122 @@ __global__ void __launch_bounds__(256) unpack_nhwc_kernel(const float* __restric
     if (p0 + lane < hw) dst[((size_t)o * C + cb + c) * hw + p0 + lane] = tile[lane][c];
 }
 
+// ---- kernels of the BEV Decoder head (models/decoder.py:91-140) ------------------------------------------------
+__device__ __forceinline__ void load8(const __nv_bfloat16* h, const __nv_bfloat16* l, size_t off, bool x3, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(h + off);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo_f(w[i]); f[2 * i + 1] = bf16_hi_f(w[i]); }
+  if (x3) {
+    const uint4 u = *reinterpret_cast<const uint4*>(l + off);
+    const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] += bf16_lo_f(x[i]); f[2 * i + 1] += bf16_hi_f(x[i]); }
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* h, __nv_bfloat16* l, size_t off, bool x3, const float (&f)[8]) {
+  uint32_t a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(h + off) = make_uint4(a[0], a[1], a[2], a[3]);
+  if (x3) {
+    uint32_t b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = pack_bf16x2(f[2 * i] - bf16_lo_f(a[i]), f[2 * i + 1] - bf16_hi_f(a[i]));
+    *reinterpret_cast<uint4*>(l + off) = make_uint4(b[0], b[1], b[2], b[3]);
+  }
+}
+
+// Space to depth for the stride-2 convolutions: dst[img][i][j][(2 py + px) C + c] = src[img][2 i + py][2 j + px][c].  A
+// stride-2 convolution then is a stride-1 convolution over the four phase images (channel blocks of dst), which the implicit
+// GEMM stage kernel runs as ordinary chunks with shifted windows.  Pure copy of 16-byte groups, per plane.
+__global__ void __launch_bounds__(256) space_to_depth2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_img, int H, int W, int G) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)n_img * Ho * Wo * 4 * G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    size_t r = idx / G;
+    const int ph = (int)(r % 4); r /= 4;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    dst[idx] = src[(((size_t)img * H + 2 * yo + (ph >> 1)) * W + 2 * xo + (ph & 1)) * G + g];
+  }
+}
+
+// UpsamplingAdd (convolutions.py:204-215) after its 1x1 conv + BN were applied at the LOW resolution (they commute with the
+// bilinear interpolation, whose weights sum to one): dst = bilinear_x2(src, align_corners=False) + skip.
+// One thread = 8 channels of one output pixel.  out[2k] = .25 in[k-1] + .75 in[k], out[2k+1] = .75 in[k] + .25 in[k+1], clamped.
+template <bool X3>
+__global__ void __launch_bounds__(256) bilinear_up2_add_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                               const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kl,
+                                                               __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl, int n_img, int H,
+                                                               int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W, G = C / 8;
+  const size_t total = (size_t)n_img * Ho * Wo * G;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    size_t r = idx / G;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    // torch: s = max(0, (o + 0.5) / 2 - 0.5); i0 = floor(s); i1 = min(i0 + 1, n - 1); lambda = s - i0
+    const float sy = fmaxf(0.0f, (yo + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.0f, (xo + 0.5f) * 0.5f - 0.5f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    float v00[8], v01[8], v10[8], v11[8], k[8], o[8];
+    const size_t base = (size_t)img * H;
+    load8(sh, sl, ((base + y0) * W + x0) * C + g * 8, X3, v00);
+    load8(sh, sl, ((base + y0) * W + x1) * C + g * 8, X3, v01);
+    load8(sh, sl, ((base + y1) * W + x0) * C + g * 8, X3, v10);
+    load8(sh, sl, ((base + y1) * W + x1) * C + g * 8, X3, v11);
+    const size_t off = (((size_t)img * Ho + yo) * Wo + xo) * C + g * 8;
+    load8(kh, kl, off, X3, k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float top = v00[i] + lx * (v01[i] - v00[i]), bot = v10[i] + lx * (v11[i] - v10[i]);
+      o[i] = top + ly * (bot - top) + k[i];
+    }
+    store8(dh, dl, off, X3, o);
+  }
+}
+
+// Output 1x1 convolution of a Decoder head (64 -> K <= 4 channels, + bias, optional sigmoid) on NHWC planes -> fp32 NCHW
+// [img][K][H][W]; with mask != nullptr also the arg-max over the K channels per pixel (first maximum wins, like torch.argmax),
+// written as uint8: the graded occupancy mask never needs the 64-channel tensor to leave the device.
+template <bool X3>
+__global__ void __launch_bounds__(256) head_1x1_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                       const float* __restrict__ w, const float* __restrict__ b, int K, int sigmoid_out,
+                                                       float* __restrict__ out, unsigned char* __restrict__ mask, int n_img, int hw) {
+  __shared__ float ws[4 * 64 + 4];
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < K) ws[256 + threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const size_t total = (size_t)n_img * hw;
+  for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float f[8];
+      load8(sh, sl, px * 64 + g * 8, X3, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < K) acc[k] = fmaf(ws[k * 64 + g * 8 + i], f[i], acc[k]);
+    }
+    const size_t img = px / hw, p = px % hw;
+    int best = 0;
+    float bv = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      float v = acc[k] + ws[256 + k];
+      if (sigmoid_out) v = 1.0f / (1.0f + expf(-v));
+      out[(img * K + k) * hw + p] = v;
+      if (v > bv) { bv = v; best = k; }
+    }
+    if (mask) mask[px] = (unsigned char)best;
+  }
+}
+
 }  // namespace sf

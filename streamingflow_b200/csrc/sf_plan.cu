@@ -60,6 +60,7 @@ struct Stage {
   CUtensorMap wmap;
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
   std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
+  int b2b_wrow = 0, b2b_bytes = 0;   // fused 1x1 follow-up conv of a lngelu stage (flag 1024): its weights are the last rows of w
   // SE layer folded into this stage's weights (sf_plan_define_stage_fold)
   int fold_se = -1;
   const float* w32 = nullptr;
@@ -153,6 +154,9 @@ StageKernel kernel_for(int epi) {
     case SF_EPI_SAMPLE: return conv_stage_kernel<SF_EPI_SAMPLE, X3, CG>;
     case SF_EPI_BIAS_ACT: return conv_stage_kernel<SF_EPI_BIAS_ACT, X3, CG>;
     case SF_EPI_RES_ID_ACT: return conv_stage_kernel<SF_EPI_RES_ID_ACT, X3, CG>;
+    case SF_EPI_LNGELU_B2B:
+      if constexpr (CG == 64) return conv_stage_kernel<SF_EPI_LNGELU_B2B, X3, CG>;
+      else return nullptr;
   }
   return nullptr;
 }
@@ -219,7 +223,10 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.nA = st.nA;
   sp.nB = st.nB;
   sp.w_rows_per_sample = st.fold_se >= 0 ? st.w_rows : 0;
-  { const char* v = getenv("SF_DEBUG_STAGE"); sp.debug = v ? atoi(v) : 0; }
+  sp.b2b_wrow = st.b2b_wrow;
+  sp.b2b_bytes = st.b2b_bytes;
+  static const int debug_stage = [] { const char* v = getenv("SF_DEBUG_STAGE"); return v ? atoi(v) : 0; }();    // read once, not per launch
+  sp.debug = debug_stage;
   sp.err = reinterpret_cast<int*>(p->f32[SF_F32_COUNT]);
   EpiArgs& e = sp.e;
   e.kind = ev->kind;
@@ -280,6 +287,8 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
       break;
   }
   e.act = (st.flags >> 1) & 7;                                        // bias_act activation code
+  e.act_after_res = (st.flags & 2048) ? 1 : 0;
+  e.deriv = (st.flags & 4096) ? 1 : 0;
   e.out32 = (st.flags & 16) ? reinterpret_cast<float*>(p->f32[SF_F32_OUT]) : nullptr;
   e.img_bias = (st.flags & 64) ? reinterpret_cast<const float*>(p->f32[SF_F32_IMG_BIAS]) : nullptr;
   e.res_scale = nullptr;
@@ -298,9 +307,10 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   // the ODE loop's LeakyReLU-only stages run the lean instantiations; any other activation, an fp32 copy or a per-image bias
   // selects the general variant of the same epilogue
   int kepi = st.epi;
-  const bool general = e.act != 0 || e.out32 || e.img_bias;
+  const bool general = e.act != 0 || e.out32 || e.img_bias || e.act_after_res;
   if (kepi == SF_EPI_BIAS_LRELU && general) kepi = SF_EPI_BIAS_ACT;
   if (kepi == SF_EPI_RES_ID && general) kepi = SF_EPI_RES_ID_ACT;
+  if (kepi == SF_EPI_LNGELU && st.b2b_bytes) kepi = SF_EPI_LNGELU_B2B;
   StageKernel k = kernel_for(kepi, x3, p->g.C);
   if (!k) return fail(SF_ERR_INVALID, "unknown epilogue");
   void* args[] = {&sp};
@@ -518,7 +528,15 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
       return fail(SF_ERR_INVALID, "row-paired taps need the lngelu epilogue, 64 channels and n = 64 chunks at column 0");
   }
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
-  const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA;
+  // flag 1024: a 1x1 convolution + LayerNorm + GELU fused behind a lngelu stage (back-to-back GEMM in the epilogue); its
+  // [C x C] weights (hi, then lo in the split mode) are the last rows of the packed matrix and stay in shared memory
+  const bool b2b = (flags & 1024) != 0;
+  const int b2b_rows = b2b ? p->g.C * (p->g.precision == SF_PREC_BF16X3 ? 2 : 1) : 0;
+  if (b2b && (epilogue != SF_EPI_LNGELU || p->g.C != 64 || n_vec != 4 * p->g.C || w_rows < b2b_rows))
+    return fail(SF_ERR_INVALID, "the fused 1x1 follow-up needs the lngelu epilogue, 64 channels, a [LN1 w, LN1 b, LN2 w, LN2 b] vector and its weights appended");
+  for (const sf_chunk& c : st.chunks)
+    if (b2b && c.wrow + c.R * c.R * c.nrep * c.n > w_rows - b2b_rows) return fail(SF_ERR_INVALID, "chunk weight rows overlap the follow-up conv's rows");
+  const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA + b2b_rows * ROW_BYTES;
   // Weight tiles: as many taps of a dx column per tile as the cap allows (fewer producer <-> issuer barrier round trips per MMA;
   // measured: 48 KB tiles are worth 4 % of the rollout over 24 KB ones), shrunk until at least two weight slots fit next to
   // the activation ring.  Activation ring: one slot = one chunk's tile + halo, 3 slots when they leave room, up to 4.
@@ -554,6 +572,8 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   st.n_out = 0;
   for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
   st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
+  st.b2b_bytes = b2b_rows * ROW_BYTES;
+  st.b2b_wrow = w_rows - b2b_rows;
   st.smem = fixed + nA * a_slot + nB * b_slot;
   int rc = encode_weight_map(w_packed, w_rows, &st.wmap);
   if (rc) return rc;
@@ -594,8 +614,10 @@ int sf_plan_finalize(sf_plan* p) {
   for (const Stage& st : p->stage)
     if (st.defined && st.smem > max_smem) max_smem = st.smem;
   for (int epi = 0; epi < SF_EPI_KERNELS; ++epi)
-    for (int x3 = 0; x3 < 2; ++x3)
-      SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel_for(epi, x3 != 0, p->g.C)), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    for (int x3 = 0; x3 < 2; ++x3) {
+      const void* k = reinterpret_cast<const void*>(kernel_for(epi, x3 != 0, p->g.C));
+      if (k) SF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));      // null: no such variant at this width
+    }
   p->finalized = true;
   return SF_OK;
 }
@@ -711,6 +733,45 @@ int sf_upsample2(const void* src, void* dst, int n_images, int H, int W, int C, 
   const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   upsample2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
                                                                            n_images, H, W, C / 8);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_space_to_depth2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream) {
+  if (!src || !dst || C % 8 || (H & 1) || (W & 1) || n_images <= 0) return fail(SF_ERR_INVALID, "bad space-to-depth arguments");
+  const size_t total = (size_t)n_images * (H / 2) * (W / 2) * 4 * (C / 8);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  space_to_depth2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+                                                                                 n_images, H, W, C / 8);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_bilinear_up2_add(const void* src_hi, const void* src_lo, const void* skip_hi, const void* skip_lo, void* dst_hi, void* dst_lo,
+                        int n_images, int H, int W, int C, void* stream) {
+  if (!src_hi || !skip_hi || !dst_hi || C % 8 || n_images <= 0 || H <= 0 || W <= 0) return fail(SF_ERR_INVALID, "bad bilinear arguments");
+  const bool x3 = src_lo && skip_lo && dst_lo;
+  const size_t total = (size_t)n_images * (2 * H) * (2 * W) * (C / 8);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
+  auto kh = reinterpret_cast<const __nv_bfloat16*>(skip_hi); auto kl = reinterpret_cast<const __nv_bfloat16*>(skip_lo);
+  auto dh = reinterpret_cast<__nv_bfloat16*>(dst_hi); auto dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
+  if (x3) bilinear_up2_add_kernel<true><<<grid, 256, 0, s>>>(sh, sl, kh, kl, dh, dl, n_images, H, W, C);
+  else bilinear_up2_add_kernel<false><<<grid, 256, 0, s>>>(sh, sl, kh, kl, dh, dl, n_images, H, W, C);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_head_1x1(const void* src_hi, const void* src_lo, const float* w, const float* b, int K, int sigmoid_out, float* out, unsigned char* mask,
+                int n_images, int H, int W, void* stream) {
+  if (!src_hi || !w || !b || !out || K < 1 || K > 4 || n_images <= 0) return fail(SF_ERR_INVALID, "bad head arguments");
+  const size_t total = (size_t)n_images * H * W;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
+  if (src_lo) head_1x1_kernel<true><<<grid, 256, 0, s>>>(sh, sl, w, b, K, sigmoid_out, out, mask, n_images, H * W);
+  else head_1x1_kernel<false><<<grid, 256, 0, s>>>(sh, sl, w, b, K, sigmoid_out, out, mask, n_images, H * W);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -28,7 +28,7 @@ from . import _lib as L
 _BUF_CHANNELS = {BUF_S0: 1, BUF_S1: 1, BUF_X: 1, BUF_U1: 1, BUF_U2: 1, BUF_G1: 1, BUF_G2: 1, BUF_A: 1, BUF_B: 1, BUF_HH: 1,
                  BUF_T1: 1, BUF_T2: 1, BUF_Q1: 1, BUF_Z1: 2, BUF_Y1: 2, BUF_Q3: 2, BUF_Z2: 2, BUF_Y2: 2}
 KIND_STEP, KIND_JUMP = 0, 1
-CELL_STAGE_NAMES = {64: ("gates", "propose", "decode", "trunk7", "trunk1", "mix"),
+CELL_STAGE_NAMES = {64: ("gates", "propose", "decode", "trunk", "mix"),        # SF_B2B=0: "trunk" splits into "trunk7", "trunk1"
                     128: ("gates_1", "gates_2", "propose_1", "propose_2", "decode", "trunk7", "trunk1", "mix")}
 
 
@@ -49,6 +49,7 @@ class StageDef:
         self.io_off = list(io_off) if io_off is not None else [0] * len(self.io)
         self.chunks: List[Tuple[int, int, torch.Tensor, int, int, int, int]] = []
         self.fold_se: Optional[int] = None      # SE layer whose per-sample scales are folded into this stage's weights
+        self.b2b_w: Optional[torch.Tensor] = None   # [C, 64] weights of a fused 1x1 follow-up conv (FLAG_B2B)
 
     def add(self, buf, w, col, init, c0=0, ox=0, oy=0):
         """w: [n, cin, R, R] with cin a multiple of 64: one chunk per 64 input channels of buffer ``buf`` starting at c0.
@@ -69,8 +70,9 @@ class StageDef:
         return self
 
 
-def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True) -> List[StageDef]:
-    """The conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters; C = 64 or 128."""
+def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True, b2b: bool = True) -> List[StageDef]:
+    """The conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters; C = 64 or 128.
+    b2b (C = 64): the Bottleblock's 7x7 conv + LN + GELU + 1x1 conv + LN + GELU run as ONE stage ("trunk")."""
     g = lambda k: sd[f"{p}.{k}"].float()
     C_ = g("conv_update_1.weight").shape[0]
     assert C_ in (64, 128)
@@ -101,11 +103,19 @@ def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True)
     t = "trusting_gate.0."
     w7 = g(t + "layers.0.weight")
     # 64 channels: vertically adjacent taps of the 7x7 conv are paired into N = 128 MMAs (the MMA issue cost is ~41 + N/2 cycles)
-    out.append(StageDef("trunk7", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1],
-                        flags=L.FLAG_PAIR_ROWS if (C_ == 64 and pair_rows) else 0)
-               .add(BUF_A, w7[:, :C_], 0, 1).add(BUF_B, w7[:, C_:], 0, 0))
-    out.append(StageDef("trunk1", L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
-               .add(BUF_T1, g(t + "layers.3.weight"), 0, 1))
+    if C_ == 64 and b2b:
+        st = StageDef("trunk", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias"), g(t + "layers.4.weight"),
+                                                        g(t + "layers.4.bias")]), [BUF_T2],
+                      flags=L.FLAG_B2B | (L.FLAG_PAIR_ROWS if pair_rows else 0))
+        st.add(BUF_A, w7[:, :C_], 0, 1).add(BUF_B, w7[:, C_:], 0, 0)
+        st.b2b_w = g(t + "layers.3.weight")[:, :, 0, 0]
+        out.append(st)
+    else:
+        out.append(StageDef("trunk7", L.EPI_LNGELU, torch.cat([g(t + "layers.1.weight"), g(t + "layers.1.bias")]), [BUF_T1],
+                            flags=L.FLAG_PAIR_ROWS if (C_ == 64 and pair_rows) else 0)
+                   .add(BUF_A, w7[:, :C_], 0, 1).add(BUF_B, w7[:, C_:], 0, 0))
+        out.append(StageDef("trunk1", L.EPI_LNGELU, torch.cat([g(t + "layers.4.weight"), g(t + "layers.4.bias")]), [BUF_T2])
+                   .add(BUF_T1, g(t + "layers.3.weight"), 0, 1))
     wp = g(t + "projection.0.weight")
     wg = g("trusting_gate.1.weight")[:, :, 0, 0]
     out.append(StageDef("mix", L.EPI_MIX, torch.cat([g(t + "layers.7.weight"), g(t + "layers.7.bias"), wg[0], wg[1]]), [])
@@ -184,6 +194,14 @@ def pack_stage(sdef: StageDef, x3: bool):
     """Packs a stage's weights into the [rows, 64] bf16 matrix the TMA weight ring streams, in consumption order:
     chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed).
     Row-paired stages (FLAG_PAIR_ROWS): chunk -> dx -> pair -> rep -> [tap_hi n rows | tap_lo n rows]."""
+    if sdef.flags & L.FLAG_B2B:
+        plain = StageDef(sdef.name, sdef.epilogue, sdef.vec, sdef.io, sdef.io_off, sdef.flags & ~L.FLAG_B2B)
+        plain.chunks = sdef.chunks
+        chunks, wp = pack_stage(plain, x3)
+        w = sdef.b2b_w.float()                                       # [n, k] = the K-major B operand of the follow-up GEMM
+        hi = w.to(torch.bfloat16)
+        tail = [hi] + ([(w - hi.float()).to(torch.bfloat16)] if x3 else [])
+        return chunks, torch.cat([wp] + tail, 0).contiguous()
     if sdef.flags & L.FLAG_PAIR_ROWS:
         return _pack_stage_paired(sdef, x3)
     chunks, blocks, row = [], [], 0
@@ -407,7 +425,8 @@ class OdeEngine:
         self.stage_defs: Dict[int, StageDef] = {}
         self.stage_names: Dict[int, str] = {}
         pair = os.environ.get("SF_PAIR_ROWS", "1") != "0"
-        cells = [cell_stage_defs(sd, pre + "gru_c", pair), cell_stage_defs(sd, pre + "gru_obs.gru_d", pair)]
+        b2b = os.environ.get("SF_B2B", "1") != "0"
+        cells = [cell_stage_defs(sd, pre + "gru_c", pair, b2b), cell_stage_defs(sd, pre + "gru_obs.gru_d", pair, b2b)]
         n_cell = len(cells[0])
         cell_slots = [list(range(ws * n_cell, (ws + 1) * n_cell)) for ws in range(2)]
         for ws in range(2):

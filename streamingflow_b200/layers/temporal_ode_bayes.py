@@ -30,7 +30,62 @@ from ..schedule import JUMP, STEP, plan_sample
 from .convolutions import Bottleblock
 from .res_models import ConvNet, SmallDecoder, SmallEncoder
 
-__all__ = ["DualGRUODECell", "DualGRUCell", "GRUObservationCell", "NNFOwithBayesianJumps", "init_weights"]
+__all__ = ["SpatialGRUODECell", "SpatialGRUCell", "DualGRUODECell", "DualGRUCell", "GRUObservationCell", "NNFOwithBayesianJumps", "init_weights"]
+
+
+class _PlainGRUBase(nn.Module):
+    """The reference's plain ConvGRU cells (:14-61 ``SpatialGRUODECell``, :165-208 ``SpatialGRUCell``): defined there but not
+    wired into the model.  Same constructor, parameter names and forward(x, state); evaluated on the CUDA
+    engine's gate / proposal stages (plain_gru_engine.py), eval mode (the proposal's BatchNorm is folded), CUDA tensors only."""
+    _DERIV = False
+
+    def __init__(self, input_size, hidden_size, gru_bias_init=0.0, norm='bn', activation='relu', bias=True):
+        super().__init__()
+        from .res_models import ConvBlock
+
+        if norm != 'bn' or activation != 'relu':
+            raise L.SfError("the CUDA ConvGRU cells implement the reference's defaults: norm='bn', activation='relu'")
+        self.input_size, self.hidden_size, self.bias, self.gru_bias_init = input_size, hidden_size, bias, gru_bias_init
+        self.conv_update = nn.Conv2d(input_size + hidden_size, hidden_size, kernel_size=3, bias=True, padding=1)
+        self.conv_reset = nn.Conv2d(input_size + hidden_size, hidden_size, kernel_size=3, bias=True, padding=1)
+        self.conv_state_tilde = ConvBlock(input_size + hidden_size, hidden_size, kernel_size=3, bias=False, norm=norm, activation=activation)
+        self.precision = "bf16"
+        self.__dict__["_engines"] = {}
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engines"] = {}
+        return d
+
+    def forward(self, x, state):
+        from ..plain_gru_engine import PlainGruEngine
+
+        if self.training:
+            raise L.SfError("the CUDA ConvGRU cells implement inference (eval mode, BatchNorm folded); call .eval()")
+        if x.device.type != "cuda":
+            raise L.SfError("streamingflow_b200 evaluates the ConvGRU cells on a B200 GPU only; got a tensor on " + str(x.device))
+        if torch.is_grad_enabled() and (x.requires_grad or state.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise L.SfError("the CUDA ConvGRU cells have no backward: call them under torch.no_grad()")
+        n, _, h, w = x.shape
+        key = (str(x.device), n, h, w, self.precision)
+        fp = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        ent = self._engines.get(key)
+        if ent is None or ent["fp"] != fp:
+            if len(self._engines) >= 2:
+                self._engines.clear()
+            ent = dict(engine=PlainGruEngine(self.state_dict(), self.gru_bias_init, h, w, n, self.precision, x.device, self._DERIV), fp=fp)
+            self._engines[key] = ent
+        return ent["engine"].run(x, state)
+
+
+class SpatialGRUODECell(_PlainGRUBase):
+    """dh = u * (s~ - s) (reference :35-61)."""
+    _DERIV = True
+
+
+class SpatialGRUCell(_PlainGRUBase):
+    """(1 - u) * s + u * s~ (reference :186-208)."""
+    _DERIV = False
 
 
 class _DualGRUBase(nn.Module):
@@ -153,6 +208,9 @@ class NNFOwithBayesianJumps(nn.Module):
     _RUNTIME_CACHES = ("_engines", "_codecs", "_graphs", "_stream_plans", "_copy_streams", "_stage_bufs", "download_done")
 
     def _wire_cells(self):
+        from .. import ops
+
+        self.__dict__["_op_handle"] = ops.register_module(self)       # key of this instance for the torch.ops.sf_b200.* operators
         me = weakref.ref(self)
         self.gru_c.__dict__["_owner"] = me
         self.gru_obs.gru_d.__dict__["_owner"] = me
@@ -303,7 +361,12 @@ class NNFOwithBayesianJumps(nn.Module):
         return ev
 
     def _cell_call(self, cell, x, state, derivative):
+        if cell is not (self.gru_c if derivative else self.gru_obs.gru_d):
+            raise RuntimeError("derivative cell is not this module's gru_c" if derivative else "jump cell is not this module's gru_obs.gru_d")
         self._guard_no_grad(x, state)
+        return torch.ops.sf_b200.dual_gru_cell(x, state, self._op_handle, derivative)
+
+    def _cell_impl(self, x, state, derivative):
         n, _, h, w = x.shape
         eng = self._engine_for(h, w, n, x.device)
         eng.set_state(0, state)
@@ -312,18 +375,17 @@ class NNFOwithBayesianJumps(nn.Module):
             # dh = 0 + 1.0 * (mix - state): Euler epilogue with a zero base buffer and dt = 1
             eng.zero_state(1)
             ev = self._single_event(eng, n, kind=STEP, dt=[1.0] * n, s_in=0, s_base=1, s_out=1)
-            if cell is not self.gru_c:
-                raise RuntimeError("derivative cell is not this module's gru_c")
         else:
             ev = self._single_event(eng, n, kind=JUMP)
-            if cell is not self.gru_obs.gru_d:
-                raise RuntimeError("jump cell is not this module's gru_obs.gru_d")
         eng.run_rollout([ev])
         return eng.unpack_f32(eng.state32[1 if derivative else 0], n)
 
     def infer_state(self, x, deterministic=False):
         """(sample, params) of the latent prior at state x (reference :463-477)."""
         self._guard_no_grad(x)
+        return torch.ops.sf_b200.infer_state(x, self._op_handle)
+
+    def _infer_state_impl(self, x):
         n, _, h, w = x.shape
         eng = self._engine_for(h, w, n, x.device)
         eng.set_state(0, x)
@@ -334,10 +396,15 @@ class NNFOwithBayesianJumps(nn.Module):
     def ode_step(self, state, input, delta_t, current_time):
         """One solver step (reference :436-459). Returns (state, input, current_time + delta_t, eval_times, eval_ps)."""
         self._guard_no_grad(state, input)
+        new_state, new_input = torch.ops.sf_b200.ode_step(state, input, float(delta_t), self._op_handle)
+        eval_times = torch.tensor([0], device=state.device, dtype=torch.float64)
+        eval_ps = torch.tensor([0], device=state.device, dtype=torch.float32)
+        return new_state, new_input, current_time + delta_t, eval_times, eval_ps
+
+    def _ode_step_impl(self, state, input, dt):
         n, _, h, w = state.shape
         dev = state.device
         eng = self._engine_for(h, w, n, dev)
-        dt = float(delta_t)
         eng.set_state(0, state)
         x_buf = 2
         if self.impute is False:
@@ -356,10 +423,7 @@ class NNFOwithBayesianJumps(nn.Module):
                    self._single_event(eng, n, x_buf=2, dt=[dt] * n, s_in=1, s_base=0, s_out=0, run_prior=1, want_f32=1,
                                       eps=[2 * i + 1 for i in range(n)])]
         eng.run_rollout(evs)
-        eval_times = torch.tensor([0], device=dev, dtype=torch.float64)
-        eval_ps = torch.tensor([0], device=dev, dtype=torch.float32)
-        current_time = current_time + delta_t
-        return eng.unpack_f32(eng.state32[0], n), eng.unpack_f32(eng.x32, n), current_time, eval_times, eval_ps
+        return eng.unpack_f32(eng.state32[0], n), eng.unpack_f32(eng.x32, n)
 
     # ------------------------------------------------------------------ the rollout
     def codec_available(self, H, W, device) -> bool:
@@ -392,8 +456,16 @@ class NNFOwithBayesianJumps(nn.Module):
         times[b] / targets[b]: python floats.  Returns (final states [B,C,h,w], selected latents [B,T,C,h,w]); with
         return_slots the second value is (engine, flat path slots) so a fused decoder can read the path buffer directly.
         stamp_dtypes: dtypes of the (observation, target) timestamp tensors the values came from (schedule.plan_sample)."""
-        B = len(obs_counts)
         self._guard_no_grad(hx_obs)
+        if obs_planes is None and not return_slots:
+            # the tensor-in / tensor-out form goes through the registered operator (opaque to the dispatcher / torch.compile)
+            from .. import ops
+            key = ops.stash_plan((list(obs_counts), [list(t) for t in times], [list(t) for t in targets], float(delta_t), tuple(stamp_dtypes)))
+            return torch.ops.sf_b200.integrate_latents(hx_obs, self._op_handle, key)
+        return self._integrate_impl(hx_obs, obs_counts, times, targets, delta_t, obs_planes, return_slots, stamp_dtypes)
+
+    def _integrate_impl(self, hx_obs, obs_counts, times, targets, delta_t, obs_planes=None, return_slots=False, stamp_dtypes=("float64", "float64")):
+        B = len(obs_counts)
         if obs_planes is not None:
             _, h, w, c = obs_planes[0].shape
             dev = obs_planes[0].device

@@ -54,6 +54,7 @@ class FuturePredictionODE(nn.Module):
     def __getstate__(self):
         d = dict(self.__dict__)          # the refinement engines hold ctypes plan handles: per-instance, rebuilt on first use
         d["_refiners"] = {}
+        d.pop("last_output_planes", None)
         return d
 
     @staticmethod
@@ -97,9 +98,13 @@ class FuturePredictionODE(nn.Module):
             _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True, stamp_dtypes=dtypes)
             refine = self._refine_for(H, W, B, T, stacked.device)
             x = refine.run(planes, x32)
+            # the same frames in engine layout ((hi, lo) NHWC bf16 [B*T, H, W, C], views of the refinement's output buffer, valid
+            # until the next forward): streamingflow_b200.models.decoder.Decoder.forward(x, planes=...) consumes them directly
+            self.__dict__["last_output_planes"] = refine.output_planes()
             ode.last_rollout.launches += refine.launches
             refine.launches = 0
             return x, 0
+        self.__dict__["last_output_planes"] = None
         if fused:
             _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)      # encoder / loop / decoder on the CUDA engine
         else:

@@ -160,6 +160,10 @@ class RefineEngine:
             if dst is not None:
                 dst.copy_(src[idx])
 
+    def output_planes(self):
+        """The refined frames in engine layout: (hi, lo) NHWC bf16 [B*T, H, W, 64] (image index b*T + t)."""
+        return self.plan.bufs[R_OUT]
+
     def run(self, x_planes, x32: torch.Tensor) -> torch.Tensor:
         """x_planes: (hi, lo) NHWC bf16 [B*T, H, W, 64] decoded frames, image index b*T + t; x32: the same frames in fp32 NHWC.
         Returns the refined frames [B, T, 64, H, W] fp32 NCHW."""

@@ -533,3 +533,35 @@ def test_captured_graphs_retire_when_weights_or_buffers_are_rebound():
     seq_g = [fwd(mg), run(mg, False), fwd(mg), run(mg, False), run(mg, True), fwd(mg)]
     seq_e = [fwd(me), run(me, False), fwd(me), run(me, False), run(me, False), fwd(me)]
     assert all(torch.equal(a, b) for a, b in zip(seq_g, seq_e))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_plain_convgru_cells_match_the_reference_formula(precision):
+    """SpatialGRUODECell / SpatialGRUCell (temporal_ode_bayes.py:14-61, 165-208; defined but unwired in the
+    reference) on the CUDA gate / proposal stages vs their formula in fp64 torch: u, r = sigmoid(conv(cat[x, s]) + b + bias_init);
+    s~ = ReLU(BN(conv(cat[x, (1 - r) s]))); dh = u (s~ - s)  |  out = (1 - u) s + u s~."""
+    import torch.nn.functional as F
+    from streamingflow_b200.layers.temporal_ode_bayes import SpatialGRUCell, SpatialGRUODECell
+
+    n, h, w = 2, 28, 20
+    x = torch.tanh(so.recipe_array("px", (n, 64, h, w), 3)).cuda()
+    s = (0.5 * so.recipe_array("ps", (n, 64, h, w), 3)).cuda()
+    for cls, deriv in ((SpatialGRUODECell, True), (SpatialGRUCell, False)):
+        m = cls(64, 64, gru_bias_init=0.3).eval()
+        sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 8, 1.0)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda()
+        m.precision = precision
+        with torch.no_grad():
+            got = m(x, s)
+        d = {k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd.items()}
+        xs = torch.cat([x, s], 1).double()
+        u = torch.sigmoid(F.conv2d(xs, d["conv_update.weight"], d["conv_update.bias"], padding=1) + 0.3)
+        r = torch.sigmoid(F.conv2d(xs, d["conv_reset.weight"], d["conv_reset.bias"], padding=1) + 0.3)
+        t = F.conv2d(torch.cat([x.double(), (1 - r) * s.double()], 1), d["conv_state_tilde.conv.weight"], None, padding=1)
+        t = torch.relu(F.batch_norm(t, d["conv_state_tilde.norm.running_mean"], d["conv_state_tilde.norm.running_var"],
+                                    d["conv_state_tilde.norm.weight"], d["conv_state_tilde.norm.bias"], False, 0.0, 1e-5))
+        want = u * (t - s.double()) if deriv else (1 - u) * s.double() + u * t
+        scale = torch.maximum(want.abs().max(), s.double().abs().max())
+        err = ((got.double() - want).abs().max() / scale).item()
+        assert got.shape == want.shape and err < TOL[precision], f"{cls.__name__}: {err:.3e} ({precision})"

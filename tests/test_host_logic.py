@@ -112,10 +112,23 @@ def test_packed_stage_plans_reproduce_the_convolutions(x3):
     ref = torch.cat([conv(torch.cat([x, g1], 1), "gru_c.conv_state_tilde_1.weight", 1),
                      conv(torch.cat([s, g2], 1), "gru_c.conv_state_tilde_2.weight", 1)])
     assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 10
-    acc = en.emulate_stage(cell[3], x3, src)
+    by_name = {d.name: d for d in cell}
+    assert list(by_name) == list(en.CELL_STAGE_NAMES[64]) == ["gates", "propose", "decode", "trunk", "mix"]
+    acc = en.emulate_stage(by_name["trunk"], x3, src)
     ref = conv(torch.cat([a, b], 1), "gru_c.trusting_gate.0.layers.0.weight", 3)
     assert (acc[:64] - ref).abs().max() < max(tol, 1e-9) * 30
-    acc = en.emulate_stage(cell[5], x3, src)
+    # the fused 1x1 follow-up conv: its [n, k] weights are the last 64 (x3: 128 = hi, lo) rows of the packed matrix, and the
+    # stage vector is [LN1 w, LN1 b, LN2 w, LN2 b]; the unfused pair of stages (SF_B2B=0) packs the same 7x7 rows
+    _, wp = en.pack_stage(by_name["trunk"], x3)
+    w1 = sd["gru_c.trusting_gate.0.layers.3.weight"][:, :, 0, 0]
+    tail = wp[-(128 if x3 else 64):].float()
+    assert torch.equal(tail[:64], w1.to(torch.bfloat16).float())
+    if x3:
+        assert torch.equal(tail[64:], (w1 - w1.to(torch.bfloat16).float()).to(torch.bfloat16).float())
+    split = {d.name: d for d in en.cell_stage_defs(sd, "gru_c", b2b=False)}
+    assert "trunk7" in split and "trunk1" in split and torch.equal(en.pack_stage(split["trunk7"], x3)[1], wp[:-(128 if x3 else 64)])
+    assert torch.equal(by_name["trunk"].vec, torch.cat([split["trunk7"].vec, split["trunk1"].vec])) and by_name["trunk"].io == split["trunk1"].io
+    acc = en.emulate_stage(by_name["mix"], x3, src)
     ref = torch.cat([conv(g2, "gru_c.trusting_gate.0.layers.6.weight", 1),
                      conv(torch.cat([a, b], 1), "gru_c.trusting_gate.0.projection.0.weight", 0)])
     assert (acc[:128] - ref).abs().max() < max(tol, 1e-9) * 10
@@ -565,3 +578,79 @@ def test_float32_stamps_follow_the_reference_float32_schedule(golden_dir):
         m.gru_ode(torch.tensor(c["times"], dtype=torch.float64), torch.zeros(1, 1, C, H, H, dtype=torch.float64), obs, 0.05,
                   torch.tensor(c["targets"], dtype=torch.float64))
     assert m.gru_ode.last_rollout.n_state_steps != ro.n_state_steps
+
+
+def test_decoder_head_stage_graph_reproduces_reference_decoder(golden_dir):
+    """The BEV Decoder head as a conv-stage graph (seg_head_engine.decoder_graph: stride-2 convs as phase chunks over the
+    space-to-depth buffers, BasicBlocks with fused shortcuts, 1x1 conv hoisted below the bilinear up-sampling), interpreted on
+    the host, == the segmentation logits the UNMODIFIED reference Decoder produced (tests/golden/decoder_seg_c64.npz)."""
+    from streamingflow_b200 import _lib as L, engine as en, seg_head_engine as sh
+    import torch.nn.functional as F
+
+    z = np.load(os.path.join(golden_dir, "decoder_seg_c64.npz"))
+    shapes = {k: tuple(int(t) for t in v.split(",") if t) for k, v in zip(z["shapes_keys"], z["shapes_vals"])}
+    sd = so.recipe_state_dict(shapes, int(z["seed"]), float(z["gain"]), torch.float32)
+    x = so.recipe_array("dec_in", (1, 2, 64, 32, 32), 17, torch.float64)
+    want = torch.from_numpy(z["seg_f64"])
+    g = sh.decoder_graph(sd, ["segmentation"])
+    H = W = 32
+    dims = [(H >> i, W >> i) for i in range(4)]
+    outs = []
+    for f in range(2):
+        bufs = [{b: torch.zeros(1, ch, *dims[l], dtype=torch.float64) for b, ch in chans.items()} for l, chans in enumerate(sh.LEVEL_BUFS)]
+        bufs[0][sh.X] = x[:, f]
+        for op in g:
+            if op[0] == "s2d":
+                (ls, bs), (ld, bd), ch = op[1], op[2], op[3]
+                src = bufs[ls][bs]
+                bufs[ld][bd] = torch.cat([src[:, :, py::2, px::2] for py in range(2) for px in range(2)], dim=1)
+            elif op[0] == "upadd":
+                (ls, bs), (lk, bk), (ld, bd), ch = op[1], op[2], op[3], op[4]
+                bufs[ld][bd] = F.interpolate(bufs[ls][bs], scale_factor=2, mode="bilinear", align_corners=False) + bufs[lk][bk]
+            elif op[0] == "head":
+                _, key, mod, sig = op
+                outs.append(F.conv2d(bufs[0][sh.HD], sd[mod + ".3.weight"].double(), sd[mod + ".3.bias"].double()))
+            else:
+                _, lvl, sdef = op
+                assert len(sdef.chunks) * 2 <= 40, (sdef.name, len(sdef.chunks))      # split mode: two kernel chunks per logical chunk
+                acc = en.emulate_stage(sdef, True, {b: t.float() for b, t in bufs[lvl].items()})
+                n = max(ck[2].shape[0] for ck in sdef.chunks if ck[3] == 0)
+                v = acc[:n] + sdef.vec.double()[:n, None, None]
+                relu = ((sdef.flags >> 1) & 7) == L.ACT_RELU
+                if sdef.epilogue == L.EPI_RES_ID:
+                    assert sdef.flags & L.FLAG_ACT_AFTER_RES
+                    v = v + bufs[lvl][sdef.io[0]][0, sdef.io_off[0]:sdef.io_off[0] + n]
+                    dst, off = sdef.io[1], sdef.io_off[1]
+                else:
+                    dst, off = sdef.io[0], sdef.io_off[0]
+                bufs[lvl][dst][0, off:off + n] = torch.relu(v) if relu else v
+    got = torch.stack(outs, dim=1)
+    assert got.shape == want.shape
+    err = ((got - want).abs().max() / want.abs().max()).item()
+    assert err < 2e-4, err           # the split-bf16 replay carries ~2^-16 per conv
+    assert torch.equal(got.argmax(2), want.argmax(2))
+
+
+def test_inner_api_is_registered_as_torch_custom_ops(golden_dir):
+    """north star / SURVEY 8b: the entry points are torch.library operators (torch.ops.sf_b200.*) with fake kernels, and the
+    nn.Module methods route through them (here with the checker backend standing in for the CUDA engine on CPU)."""
+    import streamingflow_b200.ops  # noqa: F401  (registers the operators)
+
+    for name in ("dual_gru_cell", "infer_state", "ode_step", "integrate_latents"):
+        assert hasattr(torch.ops.sf_b200, name)
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C = int(z["C"])
+    m = _tiny_module(z, torch.float32).gru_ode               # fp32 checker backend: same dtypes as the CUDA engine returns
+    x, s = torch.randn(1, C, 4, 4), torch.randn(1, C, 4, 4)
+    calls = []
+    orig = m._cell_impl
+    m._cell_impl = lambda *a: (calls.append(1) or orig(*a))
+    with torch.no_grad():
+        dh = m.gru_c(x, s)                                   # module method -> operator -> engine
+        dh2 = torch.ops.sf_b200.dual_gru_cell(x, s, m._op_handle, True)
+    assert len(calls) == 2 and torch.equal(dh, dh2)
+    torch.library.opcheck(torch.ops.sf_b200.dual_gru_cell, (x, s, m._op_handle, True), test_utils=("test_schema", "test_faketensor"))
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():                                   # shapes without running anything (tracing / torch.compile)
+        y, params = torch.ops.sf_b200.infer_state(torch.empty(2, C, 4, 4), m._op_handle)
+    assert y.shape == (2, C, 4, 4) and params.shape == (2, 2 * C, 4, 4)

@@ -156,3 +156,16 @@ def test_decoder_segmentation_branch_matches_reference(golden_dir):
     with torch.no_grad():
         seg = so.seg_decoder(sd, "d", x)
     assert (seg - torch.from_numpy(z["seg_f64"])).abs().max().item() < 1e-11
+
+
+def test_decoder_all_heads_match_reference(golden_dir):
+    """models/decoder.py with every predict gate on (reference run: tests/golden/decoder_all_c64.npz): pins oracle.bev_decoder,
+    the checker of the CUDA Decoder head."""
+    z = np.load(os.path.join(golden_dir, "decoder_all_c64.npz"))
+    sd = {"d." + k: v for k, v in so.recipe_state_dict(_shapes(z), int(z["seed"]), float(z["gain"]), torch.float64).items()}
+    x = so.recipe_array("dec_in", (1, 3, 64, 32, 32), int(z["seed"]), torch.float64)
+    with torch.no_grad():
+        out = so.bev_decoder(sd, "d", x, int(z["n_present"]))
+    for k in ("segmentation", "pedestrian", "hdmap", "instance_center", "instance_offset", "instance_flow", "costvolume"):
+        want = torch.from_numpy(z[k])
+        assert out[k].shape == want.shape and (out[k] - want).abs().max().item() < 1e-11, k
