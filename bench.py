@@ -167,6 +167,15 @@ def make_model(device, C=64):
     return m.to(device)
 
 
+def make_decoder(device):
+    import torch
+    from streamingflow_b200.models.decoder import Decoder
+
+    torch.manual_seed(1)
+    gates = dict(perceive_hdmap=False, predict_pedestrian=False, predict_instance=False, predict_future_flow=False, planning=False)
+    return Decoder(64, 2, 3, 2, gates).eval().to(device)
+
+
 def workload_config(args, hw, batch):
     return dict(workload=f"config2: Prediction_LC_ODE_Variable ODE head, batch {batch}/GPU, camera 2Hz + LiDAR 5Hz synthetic BEV "
                          f"observations (8 jumps + 10 variable Euler state-steps per sample), ODE grid {hw}x{hw}x64 "
@@ -407,6 +416,7 @@ def main():
     e2e = e2e_forward_host(c, model, B, args.steps)
     if args.workload == "config2" and args.grid == "cell" and not args.quick:
         e2e["latent_level"] = e2e_latent_streamed(c, ode, hx_dev, B, n_obs, times, hw, steps_per_rollout, min(args.steps, 5))
+        e2e["to_occupancy_masks"] = e2e_forward_host(c, model, B, min(args.steps, 5), decoder=make_decoder(dev))
 
     # ---------------- per-stage roofline (rank 0)
     peaks = load_peaks()
@@ -451,7 +461,7 @@ def main():
         dist.destroy_process_group()
 
 
-def e2e_forward_host(c, model, B, steps):
+def e2e_forward_host(c, model, B, steps, decoder=None):
     """The call a user of the reference makes -- FuturePredictionODE.forward(future_prediction_input, camera_states,
     lidar_states, camera_timestamp, lidar_timestamp, target_timestamp) -- with the BEV states in pinned HOST memory and the
     output read back to pinned host memory, every step: H2D on a copy stream into one of two device buffers (the copy of
@@ -462,7 +472,8 @@ def e2e_forward_host(c, model, B, steps):
     g = torch.Generator().manual_seed(3 + c.rank)
     cam_h = torch.randn(B, 3, 64, H, H, generator=g).pin_memory()
     lid_h = torch.randn(B, 5, 64, H, H, generator=g).pin_memory()
-    out_h = torch.empty((B, len(TARGETS), 64, H, H), dtype=torch.float32).pin_memory()
+    out_h = (torch.empty((B, len(TARGETS), 64, H, H), dtype=torch.float32) if decoder is None else
+             torch.empty((B, len(TARGETS), H, H), dtype=torch.uint8)).pin_memory()
     ct = torch.tensor([CAM_T] * B, dtype=torch.float64)
     lt = torch.tensor([LIDAR_T] * B, dtype=torch.float64)
     tt = torch.tensor([TARGETS] * B, dtype=torch.float64)
@@ -492,6 +503,8 @@ def e2e_forward_host(c, model, B, steps):
         main.wait_event(up[k])
         with torch.no_grad():
             x, _ = model(fpi, bufs[k][0], bufs[k][1], ct, lt, tt)
+            if decoder is not None:      # the step after the head: BEV Decoder + arg-max on the engine, frames handed over in engine layout
+                x = decoder(x, planes=model.last_output_planes)["segmentation_argmax"].view(B, len(TARGETS), H, H)
         e = torch.cuda.Event()
         e.record(main)
         free[k] = e
@@ -520,6 +533,11 @@ def e2e_forward_host(c, model, B, steps):
     c.barrier()
     ms = max_over_ranks(a.elapsed_time(b), dev, c.world)
     n_steps = model.gru_ode.last_rollout.n_state_steps
+    if decoder is not None:
+        return dict(value=c.world * n_steps * steps / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=(cam_h.numel() + lid_h.numel()) * 4,
+                    d2h_bytes_per_step=out_h.numel(), ms_per_step=ms / steps, steps=steps,
+                    api="FuturePredictionODE.forward -> Decoder.forward(x, planes=...) -> segmentation arg-max (trainer.py:230-231), all on the "
+                        "engine; H2D of the BEV states and D2H of the uint8 occupancy masks [B, 7, 200, 200] inside the timed region")
     return dict(value=c.world * n_steps * steps / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=(cam_h.numel() + lid_h.numel()) * 4,
                 d2h_bytes_per_step=out_h.numel() * 4, ms_per_step=ms / steps, steps=steps,
                 launches_per_step=model.gru_ode.last_rollout.launches,
@@ -702,15 +720,19 @@ def config5_row_sharded(c, steps=3, full_line=False):
     value = n * steps / (ms * 1e-3)
     flops = flops_per_state_step_px(C) * H * H * (n + ro.n_jumps)
     out = dict(workload=f"config5: 400x400x128 ODE state, B = 1, row-sharded over {c.world} GPU(s) ({sh.own_hi - sh.own_lo} rows + 12-row halos per rank), "
-                        "per event one NCCL send/recv pair per neighbour + two [B,2C] all-reduces, graph segments between the NCCL calls",
+                        "per event one NCCL send/recv pair per neighbour + two [B,2C] all-reduces, replayed as CUDA graph(s)",
                value=value, unit=UNIT, ms_per_rollout=ms / steps, steps=steps, scaling="strong", n_gpus=c.world,
-               tflops_algorithmic=flops * steps / (ms * 1e-3) / 1e12, band_rows=sh.own_hi - sh.own_lo, halo_rows=12)
+               tflops_algorithmic=flops * steps / (ms * 1e-3) / 1e12, band_rows=sh.own_hi - sh.own_lo, halo_rows=12, launch=sh.graph_mode,
+               whole_graph_error=sh.__dict__.get("_whole_graph_error"))
+    launches = sh.launches
+    sh.release_graphs()          # graphs with captured NCCL kernels must be destroyed before the process group
+    del sh
     if not full_line:
         return out
     peaks = load_peaks()
     return dict(metric=METRIC, value=value, unit=UNIT, n_gpus=c.world, steps=steps, warmup=2, ms_per_step=ms / steps, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="bf16", data="synthetic", config=dict(workload=out["workload"]), clocks=clocks.summary(),
-                gpu_launches=sh.launches, e2e=None, cpu_baseline=None,
+                gpu_launches=launches, e2e=None, cpu_baseline=None,
                 roofline=dict(bound="tensor", kernel="whole event (all conv stages)", achieved=out["tflops_algorithmic"] / c.world, peak=peaks["bf16"],
                               unit="TFLOP/s", frac=out["tflops_algorithmic"] / c.world / peaks["bf16"], traffic=None,
                               peak_source=peaks["source"] + "; per GPU, algorithmic FLOPs of the owned rows only"))

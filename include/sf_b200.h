@@ -72,6 +72,7 @@ typedef struct {
 #define SF_MAX_CHUNKS 40
 #define SF_MAX_ACT_BUFS 32
 #define SF_MAX_STAGES 32
+#define SF_SE_MAX_PARTIALS 160   /* per-block partial channel sums of one SE layer and sample (SF_F32_SE_SUMS layout) */
 
 typedef struct {
   int32_t max_images;   /* capacity (samples) of the per-sample buffers                                  */
@@ -88,7 +89,7 @@ typedef enum {
   SF_F32_A = 2,         /* rnn_state1 (GRU-1 output)                                                      */
   SF_F32_B = 3,         /* rnn_state2 (decoder of GRU-2)                                                  */
   SF_F32_PATH = 4,      /* recorded states [slot][H][W][C]                                                */
-  SF_F32_SE_SUMS = 5,   /* SE scratch: partial sums [2][max_images][64][2C] | scales [2][max_images][2C] |
+  SF_F32_SE_SUMS = 5,   /* SE scratch: partial sums [2][max_images][SF_SE_MAX_PARTIALS][2C] | scales [2][max_images][2C] |
                            uint32 block counters [2][max_images]; zero-initialised by the caller                */
   SF_F32_EPS = 6,       /* standard-normal noise, NCHW [slot][C][H][W] (torch's generation order)         */
   SF_F32_X = 7,         /* optional fp32 copy of the sampled input x  (infer_state API)                   */

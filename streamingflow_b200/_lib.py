@@ -20,6 +20,7 @@ FLAG_ACT_AFTER_RES = 2048     # res_id: out = act(conv + bias + residual) (ResNe
 FLAG_DERIV = 4096             # propose: output u (s~ - s) (GRU-ODE derivative) instead of the blended state
 FLAG_B2B = 1024               # lngelu stages at C = 64: a 1x1 conv + LN + GELU fused behind the stage (weights appended to w_packed)
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
+SE_MAX_PARTIALS = 160        # SF_SE_MAX_PARTIALS in include/sf_b200.h
 SE_ITEM_BASE = 1000          # event-graph item: SE reduce + apply (activation pass)
 SE_FOLD_ITEM_BASE = 2000     # event-graph item: SE reduce + scales folded into the consumers' weights
 

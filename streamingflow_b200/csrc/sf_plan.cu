@@ -331,8 +331,8 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   return SF_OK;
 }
 
-constexpr int SE_MAX_PARTIALS = 64;
-// layout of the caller's SF_F32_SE_SUMS buffer (floats): partial sums [2][max_images][64][2C] | scales [2][max_images][2C] |
+constexpr int SE_MAX_PARTIALS = SF_SE_MAX_PARTIALS;
+// layout of the caller's SF_F32_SE_SUMS buffer (floats): partial sums [2][max_images][SF_SE_MAX_PARTIALS][2C] | scales [2][max_images][2C] |
 // block counters [2][max_images] (uint32, must start zeroed)
 float* se_scale_ptr(sf_plan* p, int which) {
   const size_t CH = 2 * p->g.C, B = p->g.max_images;
@@ -357,7 +357,11 @@ int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* t
   if (!zi.hi) return fail(SF_ERR_STATE, "SE buffers not bound");
   if (px0 < 0 || px1 > hw || px0 >= px1) return fail(SF_ERR_INVALID, "bad SE pixel window");
   const int* sid = table + ev->table_off;
-  int bpi = (px1 - px0 + 32 * 4 * 2 - 1) / (32 * 4 * 2);     // ~2 iterations of 4 x 32 pixels per block
+  // one balanced wave: 4 resident 256-thread blocks per SM over all samples (8 samples x 74 blocks = 592 = 4 x 148), at least
+  // ~1 iteration of 4 x 32 pixels per block
+  int bpi = (4 * p->num_sms + ev->n_active - 1) / ev->n_active;
+  const int cap = (px1 - px0 + 32 * 4 - 1) / (32 * 4);
+  if (bpi > cap) bpi = cap;
   if (bpi > SE_MAX_PARTIALS) bpi = SE_MAX_PARTIALS;
   if (bpi < 1) bpi = 1;
   dim3 grid(bpi, ev->n_active);

@@ -388,9 +388,10 @@ class OdeEngine:
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
         self.state32 = [f32(B, H, W, Cc), f32(B, H, W, Cc)]
         self.a32, self.b32 = f32(B, H, W, Cc), f32(B, H, W, Cc)
-        # SE scratch: partial channel sums [2][B][64][2C] | scales [2][B][2C] | block counters [2][B] (zero-initialised)
-        self.se_scratch = f32(2 * B * 64 * 2 * Cc + 2 * B * 2 * Cc + 2 * B)
-        self.se_sums = self.se_scratch[: 2 * B * 64 * 2 * Cc].view(2, B, 64, 2 * Cc)
+        # SE scratch: partial channel sums [2][B][SE_MAX_PARTIALS][2C] | scales [2][B][2C] | block counters [2][B] (zero-initialised)
+        P = L.SE_MAX_PARTIALS
+        self.se_scratch = f32(2 * B * P * 2 * Cc + 2 * B * 2 * Cc + 2 * B)
+        self.se_sums = self.se_scratch[: 2 * B * P * 2 * Cc].view(2, B, P, 2 * Cc)
         self.x32, self.params32 = f32(B, H, W, Cc), f32(B, H, W, 2 * Cc)
         self.errflag = torch.zeros(1, dtype=torch.int32, device=self.device)
         for slot, t in ((L.F32_STATE0, self.state32[0]), (L.F32_STATE1, self.state32[1]), (L.F32_A, self.a32), (L.F32_B, self.b32),

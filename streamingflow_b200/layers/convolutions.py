@@ -1,7 +1,9 @@
 """Convolutional building blocks with the reference's parameter names
 (reference: streamingflow/layers/convolutions.py).  ``Bottleblock`` / channels-first ``LayerNorm`` belong to the
-trusting gate of the dual-GRU cells and are evaluated by the CUDA engine (stages trunk7 / trunk1 / mix); ``Block``
-and ``DeepLabHead`` belong to the post-ODE refinement, which stays PyTorch in this round."""
+trusting gate of the dual-GRU cells and are evaluated by the CUDA engine (stages trunk / mix); ``Block`` and
+``DeepLabHead`` belong to the post-ODE refinement: at the shipped width (64 channels, two SpatialGRU blocks, one ConvNeXt
+block) FuturePredictionODE runs them on the CUDA engine too (refine_engine.py); their PyTorch ``forward``
+below is only reached for other widths / block counts (e.g. the 128-channel modules of BASELINE config 5)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

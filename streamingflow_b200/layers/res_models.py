@@ -1,8 +1,9 @@
 """Encoder / decoder / prior-network containers with the reference's parameter names
 (reference: streamingflow/layers/res_models.py).
 
-``SmallEncoder`` / ``SmallDecoder`` sit inside the module boundary but outside the ODE loop; in this round they
-run as ordinary PyTorch (cuDNN) modules ("next" rows of SURVEY.md 8f).  ``ConvNet`` (= p_model) and ``SELayer``
+``SmallEncoder`` / ``SmallDecoder`` sit inside the module boundary but outside the ODE loop; at the shipped width (64
+channels, SKIPCO off) NNFOwithBayesianJumps runs them on the CUDA engine (codec_engine.py, "next" row 1 of SURVEY.md 8f) and
+their PyTorch ``forward`` is only reached for other widths / SKIPCO.  ``ConvNet`` (= p_model) and ``SELayer``
 are on the hot path: they only HOLD the parameters (state_dict contract); their arithmetic runs in
 the CUDA engine (engine.prior_stage_defs), so calling their ``forward`` directly is an error by design -- there is
 no PyTorch fallback for the ODE path.

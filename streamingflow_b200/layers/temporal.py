@@ -1,6 +1,7 @@
 """Post-ODE refinement GRU with the reference's parameter names (reference: streamingflow/layers/temporal.py:11-57).
-Stays PyTorch in this round ("next" row 2 of SURVEY.md 8f); its gate / proposal pattern is the one the engine's
-gates / propose stages already implement."""
+At the shipped width (64 channels) FuturePredictionODE evaluates it on the CUDA engine (refine_engine.py: the gate /
+proposal stages of the ODE cell's kernels with a single pair, "next" row 2 of SURVEY.md 8f); the PyTorch ``forward`` below is
+only reached for other widths (e.g. the 128-channel module of BASELINE config 5)."""
 import torch
 import torch.nn as nn
 

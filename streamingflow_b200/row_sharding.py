@@ -96,7 +96,8 @@ class RowShardedOde:
         self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev, se_fold=False)
         self.device = dev
         self.launches = 0
-        self.use_graphs = bool(use_graphs)      # replay captured segments between the NCCL calls (eager stage launches if False)
+        self.use_graphs = bool(use_graphs)      # replay captured graphs (eager stage launches if False)
+        self.graph_mode = "eager"
 
     # ------------------------------------------------------------------ noise shared by all ranks
     def draw_noise(self, n: int) -> torch.Tensor:
@@ -242,9 +243,14 @@ class RowShardedOde:
             self.se_total = [torch.zeros((self.B, 2 * eng.C), dtype=torch.float32, device=self.device) for _ in range(2)]
 
     def _run_rollout_graphed(self, evs, tdev, key):
-        """Replays the rollout as CUDA-graph segments: everything between two NCCL calls (stage launches, the SE glue, the
-        byte-packing of the halo rows) is one captured graph, so an event costs 4 graph launches + 3 NCCL calls on the host
-        instead of ~60 kernel launches -- at 8 ranks the stages on a 74-row band are shorter than their launch overhead."""
+        """Replays the rollout as CUDA graphs.  Preferred: ONE graph for the whole rollout with the NCCL calls (two [B, 2C]
+        all-reduces and one send/recv group per event) captured inside it -- a single host launch per rollout, no stream
+        hand-over between the stage kernels and the collectives (at 8 ranks the ~60 kernels of an event on a 74-row band are
+        shorter than their launch overhead, and each eager NCCL call costs a host round trip).  If the installed NCCL / torch
+        refuses to capture collectives, falls back to graph segments between the NCCL calls (4 graph launches + 3 NCCL calls per
+        event on the host).  The whole-rollout capture is opt-in (SF_ROWSHARD_GRAPH=whole) until it is proven on this NCCL build."""
+        import os
+
         self._ensure_exchange_buffers()
         cache = self.__dict__.setdefault("_graph_cache", {})
         ent = cache.get(key)
@@ -252,31 +258,60 @@ class RowShardedOde:
             if len(cache) >= 4:
                 cache.clear()
             torch.cuda.synchronize(self.device)
-            prog = []                                    # ("graph", g) | ("nccl", op, ev)
-            n_launch = 0
-            for ev in evs:
-                seg = []
-                for op in self._event_ops(ev) + [("flush", 0)]:
-                    if op[0] in ("allreduce", "p2p", "flush"):
-                        if seg:
-                            g = torch.cuda.CUDAGraph()
-                            with torch.cuda.graph(g, capture_error_mode="thread_local"):     # the NCCL watchdog thread keeps polling events
-                                for o in seg:
-                                    self._run_op(o, ev, tdev)
-                            prog.append(("graph", g, None))
-                            n_launch += sum(1 for o in seg if o[0] in ("stage", "se_reduce", "se_apply"))
-                            seg = []
-                        if op[0] != "flush":
-                            prog.append(("nccl", op, ev))
-                    else:
-                        seg.append(op)
-            ent = cache[key] = dict(prog=prog, gen=self.eng.alloc_gen, launches=n_launch)
+            n_launch = sum(1 for ev in evs for o in self._event_ops(ev) if o[0] in ("stage", "se_reduce", "se_apply"))
+            prog, mode = None, "segments"
+            if self.world > 1 and os.environ.get("SF_ROWSHARD_GRAPH", "segments") == "whole" and self.__dict__.get("_whole_graph_ok", True):
+                try:
+                    # warm the communicator outside the capture (the first collective of a process group initialises it)
+                    # and so does the first send/recv with each neighbour; both only touch scratch buffers
+                    dist.all_reduce(self.se_total[0][:1], group=self.group)
+                    self._run_op(("p2p", 0), evs[0], tdev)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        for ev in evs:
+                            for op in self._event_ops(ev):
+                                self._run_op(op, ev, tdev)
+                    prog, mode = [("graph", g, None)], "whole rollout incl. NCCL"
+                except Exception as e:      # capture of collectives unsupported here: remember and use segments
+                    self.__dict__["_whole_graph_ok"] = False
+                    self.__dict__["_whole_graph_error"] = str(e)[:200]
+                    torch.cuda.synchronize(self.device)
+            if prog is None:
+                prog = []                                    # ("graph", g) | ("nccl", op, ev)
+                for ev in evs:
+                    seg = []
+                    for op in self._event_ops(ev) + [("flush", 0)]:
+                        if op[0] in ("allreduce", "p2p", "flush"):
+                            if seg:
+                                g = torch.cuda.CUDAGraph()
+                                with torch.cuda.graph(g, capture_error_mode="thread_local"):     # the NCCL watchdog thread keeps polling events
+                                    for o in seg:
+                                        self._run_op(o, ev, tdev)
+                                prog.append(("graph", g, None))
+                                seg = []
+                            if op[0] != "flush":
+                                prog.append(("nccl", op, ev))
+                        else:
+                            seg.append(op)
+            ent = cache[key] = dict(prog=prog, gen=self.eng.alloc_gen, launches=n_launch, mode=mode)
+        self.graph_mode = ent["mode"]
         for kind, x, ev in ent["prog"]:
             if kind == "graph":
                 x.replay()
             else:
                 self._run_op(x, ev, tdev)
         self.launches += ent["launches"]
+
+    def release_graphs(self):
+        """Destroys the captured graphs.  A graph that contains NCCL kernels must be gone BEFORE its process group is destroyed
+        (``dist.destroy_process_group()`` otherwise blocks forever -- observed with NCCL 2.28.9): call this (or drop the
+        object) before tearing the group down."""
+        import gc
+
+        self.__dict__.pop("_graph_cache", None)
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     def integrate(self, hx_obs: torch.Tensor, obs_counts: Sequence[int], times, targets, delta_t: float,
                   noise: Optional[torch.Tensor] = None):

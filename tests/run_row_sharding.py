@@ -74,5 +74,6 @@ with torch.no_grad():
                               max_rel_err_vs_oracle=err_oracle, single_gpu_max_rel_err_vs_oracle=err_single_oracle,
                               ms_sharded=1e3 * dt_sharded, ms_single_gpu=1e3 * dt_single, events=len(ro.events),
                               halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo,
-                              launch="graph segments" if use_graphs else "eager")), flush=True)
+                              launch=sharded.graph_mode, whole_graph_error=sharded.__dict__.get("_whole_graph_error"))), flush=True)
+sharded.release_graphs()          # graphs with NCCL kernels must die before their process group
 dist.destroy_process_group()
