@@ -798,8 +798,11 @@ int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* ds
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
   auto dh = reinterpret_cast<__nv_bfloat16*>(dst_hi); auto dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
-  if (src_lo && dst_lo) dwconv7_ln_kernel<true><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
-  else dwconv7_ln_kernel<false><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
+  // 146 KB of dynamic shared memory (fp32 halo tile + filter): opt in per call (a per-device attribute; the call is cheap)
+  SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(src_lo && dst_lo ? dwconv7_ln_kernel<true> : dwconv7_ln_kernel<false>),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
+  if (src_lo && dst_lo) dwconv7_ln_kernel<true><<<grid, 256, DW_SMEM_BYTES, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
+  else dwconv7_ln_kernel<false><<<grid, 256, DW_SMEM_BYTES, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
