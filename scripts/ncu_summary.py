@@ -1,7 +1,7 @@
 """Summarise an ncu report (.ncu-rep) + launch list (.csv) into a small text file for profiles/."""
 import csv, subprocess, sys, io
 rep, launches, out = sys.argv[1], sys.argv[2], sys.argv[3]
-names = {0: "gates", 1: "propose", 2: "decode", 3: "lngelu(trunk7/trunk1)", 4: "mix", 5: "bias_lrelu(q1/q3)", 6: "res_proj(q2)", 7: "res_id(q4)", 8: "sample(q5)"}
+names = {0: "gates", 1: "propose", 2: "decode", 3: "lngelu(trunk7/trunk1)", 11: "lngelu_b2b(trunk: 7x7+LN+GELU+1x1+LN+GELU)", 4: "mix", 5: "bias_lrelu(q1/q3)", 6: "res_proj(q2)", 7: "res_id(q4)", 8: "sample(q5)"}
 lines = []
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
 h = rows[0]; ki, vi = h.index("Kernel Name"), h.index("Metric Value")

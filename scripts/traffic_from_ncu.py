@@ -8,7 +8,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rr = list(csv.reader(io.StringIO(raw)))
 h, units = rr[0], rr[1]
 rows = [r for r in rr[2:] if "conv_stage_kernel" in r[h.index("Kernel Name")]]
-names = ["gates", "propose", "decode", "trunk7", "trunk1", "mix", "q1", "q2", "q3", "q4", "q5"]
+names = ["gates", "propose", "decode", "trunk", "mix", "q1", "q2", "q3", "q4", "q5"]      # launch order of one event (fused trunk stage)
 assert len(rows) == len(names), (len(rows), "conv stage launches in the report")
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
