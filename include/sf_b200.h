@@ -177,6 +177,19 @@ int sf_plan_last_launches(sf_plan* p);
    (n_partials = 0: the scales were already produced by a whole-image sf_plan_run_* reduce)                          */
 int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream);
 int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream);
+/* Row sharding, one squeeze-excite layer in three steps with ONE collective in between: (1) this rank's band totals per
+ * (active sample, channel) over the pixel window [px0, px1) land in a [n_active][2C] fp32 array inside the SE scratch
+ * (sf_plan_se_totals_ptr returns its address); (2) the caller all-reduces that array across the ranks (ncclAllReduce, sum);
+ * (3) sf_plan_se_finish turns the totals into scales in place (mean = total * inv_n, two FCs, sigmoid) and folds them into the
+ * consuming stages' weights (sf_plan_define_stage_fold) -- or, for a plan without folded stages, applies them (y = z * scale). */
+int sf_plan_se_reduce_totals(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream);
+int sf_plan_se_totals_ptr(sf_plan* p, int which, float** out);
+int sf_plan_se_finish(sf_plan* p, int which, const sf_event* ev, const int32_t* table, float inv_n, void* stream);
+/* Row sharding, halo exchange staging: rows [row0, row0 + nrows) of up to 6 NHWC tensors [B][rows][row_bytes] <-> one flat byte
+ * buffer per direction (tensor-major, then batch), both directions (a = towards the upper neighbour, b = lower; NULL skips one)
+ * in ONE launch; to_flat = 1 packs, 0 unpacks.  The flat buffers are what ncclSend / ncclRecv move. */
+int sf_halo_copy(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* flat_a, int row0_a, void* flat_b, int row0_b, int to_flat, void* stream);
 
 /* layout kernels (HBM-bound, 128-bit vectorised) */
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);

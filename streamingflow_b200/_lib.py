@@ -59,6 +59,11 @@ EXPORTS = {
     "sf_plan_last_launches": (C.c_int, [C.c_void_p]),
     "sf_plan_se_reduce": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_plan_se_apply": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "sf_plan_se_reduce_totals": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "sf_plan_se_totals_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "sf_plan_se_finish": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_float, C.c_void_p]),
+    "sf_halo_copy": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_pack_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_normal_policy": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

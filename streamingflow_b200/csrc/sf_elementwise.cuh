@@ -56,7 +56,8 @@ template <int CH, bool X3>
 __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl,
                                                         float* __restrict__ sums, const int* __restrict__ sample_id, int hw, int px0, int px1,
                                                         unsigned int* __restrict__ counters, float* __restrict__ scale_out,
-                                                        const float* __restrict__ fc1, const float* __restrict__ fc2, float inv_n) {
+                                                        const float* __restrict__ fc1, const float* __restrict__ fc2, float inv_n,
+                                                        float* __restrict__ totals) {
   static_assert(CH == 128 || CH == 256, "SE layers of the prior network have 2C = 128 or 256 channels");
   constexpr int GROUPS = CH / 16;           // 8
   constexpr int LANES = 256 / GROUPS;       // 32 pixels per block iteration
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
     // per-block partial sums, combined in a fixed order below: deterministic (no float atomics)
     sums[((size_t)bi * gridDim.x + blockIdx.x) * CH + threadIdx.x] = s;
   }
-  if (scale_out == nullptr) return;            // caller combines the partials itself (row sharding: all-reduce in between)
+  if (scale_out == nullptr && totals == nullptr) return;      // caller combines the partials itself
   // last block of this sample: mean -> FC(2C -> 2C/8) -> ReLU -> FC -> sigmoid, written once for se_apply to stream with
   __shared__ bool last;
   __threadfence();
@@ -116,6 +117,17 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const __nv_bfloat16* __r
   __syncthreads();
   if (!last) return;
   __threadfence();
+  if (totals != nullptr) {
+    // row sharding: this rank's band total per (sample, channel), partials added in a fixed order; the caller all-reduces the
+    // [n_active][CH] totals across the ranks and then runs the scale + fold / apply step (sf_plan_se_finish)
+    if (threadIdx.x < CH) {
+      float t = 0.0f;
+      for (int k = 0; k < (int)gridDim.x; ++k) t += sums[((size_t)bi * gridDim.x + k) * CH + threadIdx.x];
+      totals[(size_t)bi * CH + threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) counters[bi] = 0;
+    return;
+  }
   se_scale_from_partials<CH>(sums + (size_t)bi * gridDim.x * CH, gridDim.x, inv_n, fc1, fc2, scale_out + (size_t)bi * CH, &red[0][0]);
   if (threadIdx.x == 0) counters[bi] = 0;      // ready for the next launch
 }
@@ -673,6 +685,39 @@ __global__ void __launch_bounds__(256) head_1x1_kernel(const __nv_bfloat16* __re
       if (v > bv) { bv = v; best = k; }
     }
     if (mask) mask[px] = (unsigned char)best;
+  }
+}
+
+// ---- row sharding: the halo rows of up to 6 NHWC tensors <-> one flat byte buffer, both directions in ONE launch ------------
+// Tensor t is [B][rows_local][row_bytes_t]; range r copies rows [row0[r], row0[r] + nrows) of every tensor and batch entry
+// to / from flat[r] (layout: tensor-major, then batch, then the nrows * row_bytes_t bytes), 16 bytes per thread step.
+struct HaloCopy {
+  char* base[6];
+  long long batch_stride[6], row_bytes[6];      // bytes
+  char* flat[2];
+  int row0[2];
+  int n_tensors, B, nrows, to_flat;
+};
+__global__ void __launch_bounds__(256) halo_copy_kernel(const HaloCopy h) {
+  long long per_range = 0;
+  for (int t = 0; t < h.n_tensors; ++t) per_range += (long long)h.B * h.nrows * h.row_bytes[t];
+  const long long units = per_range >> 4;
+  for (int r = 0; r < 2; ++r) {
+    if (h.flat[r] == nullptr) continue;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+      long long off = u << 4, rem = off;
+      int t = 0;
+      for (; t < h.n_tensors - 1; ++t) {
+        const long long sz = (long long)h.B * h.nrows * h.row_bytes[t];
+        if (rem < sz) break;
+        rem -= sz;
+      }
+      const long long chunk = (long long)h.nrows * h.row_bytes[t];
+      const long long b = rem / chunk, inner = rem - b * chunk;
+      uint4* g = reinterpret_cast<uint4*>(h.base[t] + b * h.batch_stride[t] + (long long)h.row0[r] * h.row_bytes[t] + inner);
+      uint4* f = reinterpret_cast<uint4*>(h.flat[r] + off);
+      if (h.to_flat) *f = *g; else *g = *f;
+    }
   }
 }
 

@@ -344,7 +344,8 @@ unsigned int* se_counter_ptr(sf_plan* p, int which) {
 }
 
 // SE step 1 over the pixel window [px0, px1) of every active sample; returns the number of per-block partials (> 0) or < 0
-int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, bool fused_scale, cudaStream_t stream) {
+int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, bool fused_scale, cudaStream_t stream,
+                     bool band_totals = false) {
   const SeDef& se = p->se[which];
   if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
   const bool x3 = p->g.precision == SF_PREC_BF16X3;
@@ -371,13 +372,14 @@ int launch_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* t
   float* scale = se_scale_ptr(p, which);
   unsigned int* counters = se_counter_ptr(p, which);
   float* scale_arg = fused_scale ? scale : nullptr;
+  float* totals = band_totals ? scale : nullptr;          // band totals land in the scale slot [n_active][2C] until sf_plan_se_finish
   const float inv_n = 1.0f / (float)hw;
   if (CH == 256) {
-    if (x3) se_reduce_kernel<256, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
-    else se_reduce_kernel<256, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+    if (x3) se_reduce_kernel<256, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n, totals);
+    else se_reduce_kernel<256, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n, totals);
   } else {
-    if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
-    else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n);
+    if (x3) se_reduce_kernel<128, true><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n, totals);
+    else se_reduce_kernel<128, false><<<grid, 256, 0, stream>>>(zh, zl, sums, sid, hw, px0, px1, counters, scale_arg, se.fc1, se.fc2, inv_n, totals);
   }
   SF_CUDA(cudaGetLastError());
   p->last_launches += 1;
@@ -664,6 +666,67 @@ int sf_plan_last_launches(sf_plan* p) { return p ? p->last_launches : 0; }
 int sf_plan_se_reduce(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream) {
   if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
   return launch_se_reduce(p, which, ev, table, px0, px1, false, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sf_plan_se_reduce_totals(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int px0, int px1, void* stream) {
+  if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
+  int n = launch_se_reduce(p, which, ev, table, px0, px1, false, reinterpret_cast<cudaStream_t>(stream), true);
+  return n < 0 ? n : SF_OK;
+}
+
+int sf_plan_se_totals_ptr(sf_plan* p, int which, float** out) {
+  if (!p || !out || which < 0 || which > 1 || !p->f32[SF_F32_SE_SUMS]) return fail(SF_ERR_INVALID, "bad argument");
+  *out = se_scale_ptr(p, which);
+  return SF_OK;
+}
+
+int sf_plan_se_finish(sf_plan* p, int which, const sf_event* ev, const int32_t* table, float inv_n, void* stream) {
+  if (!p || !ev || !table || which < 0 || which > 1) return fail(SF_ERR_INVALID, "bad argument");
+  if (ev->n_active <= 0) return SF_OK;
+  const SeDef& se = p->se[which];
+  if (!se.defined) return fail(SF_ERR_STATE, "SE layer not defined");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* scale = se_scale_ptr(p, which);       // holds the (all-reduced) channel totals [n_active][2C]; the scales replace them in place
+  const int CH = 2 * p->g.C;
+  if (CH == 256) se_scale_kernel<256><<<ev->n_active, 256, 0, s>>>(scale, 1, inv_n, se.fc1, se.fc2, scale);
+  else se_scale_kernel<128><<<ev->n_active, 256, 0, s>>>(scale, 1, inv_n, se.fc1, se.fc2, scale);
+  SF_CUDA(cudaGetLastError());
+  p->last_launches += 1;
+  bool folded = false;
+  for (Stage& st : p->stage) {
+    if (!st.defined || st.fold_se != which) continue;
+    dim3 grid((st.w_rows * 8 + 255) / 256, ev->n_active);
+    se_fold_kernel<<<grid, 256, 0, s>>>(st.w32, st.row_meta, scale, reinterpret_cast<__nv_bfloat16*>(st.w_scaled), st.w_rows, CH);
+    SF_CUDA(cudaGetLastError());
+    p->last_launches += 1;
+    folded = true;
+  }
+  if (folded) return SF_OK;
+  return launch_se_apply(p, which, ev, table, 0, inv_n, s);      // unfolded plan: y = z * scale
+}
+
+int sf_halo_copy(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* flat_a, int row0_a, void* flat_b, int row0_b, int to_flat, void* stream) {
+  if (!tensors || !batch_stride_bytes || !row_bytes || n_tensors < 1 || n_tensors > 6 || B < 1 || nrows < 1 || (!flat_a && !flat_b))
+    return fail(SF_ERR_INVALID, "bad halo copy arguments");
+  HaloCopy h;
+  memset(&h, 0, sizeof(h));
+  long long total = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    if (!tensors[t] || (row_bytes[t] & 15) || (batch_stride_bytes[t] & 15) || (reinterpret_cast<uintptr_t>(tensors[t]) & 15))
+      return fail(SF_ERR_INVALID, "halo tensors must be 16-byte aligned with row sizes that are multiples of 16 bytes");
+    h.base[t] = reinterpret_cast<char*>(tensors[t]);
+    h.batch_stride[t] = batch_stride_bytes[t];
+    h.row_bytes[t] = row_bytes[t];
+    total += (long long)B * nrows * row_bytes[t];
+  }
+  h.flat[0] = reinterpret_cast<char*>(flat_a); h.row0[0] = row0_a;
+  h.flat[1] = reinterpret_cast<char*>(flat_b); h.row0[1] = row0_b;
+  h.n_tensors = n_tensors; h.B = B; h.nrows = nrows; h.to_flat = to_flat;
+  const int grid = (int)std::min<long long>(((total >> 4) + 255) / 256, 148 * 8);
+  halo_copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(h);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
 }
 
 int sf_plan_se_apply(sf_plan* p, int which, const sf_event* ev, const int32_t* table, int n_partials, float inv_n, void* stream) {

@@ -92,8 +92,12 @@ class RowShardedOde:
         dev = next(ode.parameters()).device
         if ode.training:
             raise L.SfError("eval mode only")
-        # the SE channel sums are all-reduced across the ranks between reduce and apply: keep the two-kernel SE layers
-        self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev, se_fold=False)
+        # squeeze-excite: band totals (sf_plan_se_reduce_totals) -> all-reduce across the ranks -> scales folded into the consuming
+        # convs' weights (sf_plan_se_finish), like the single-GPU engine: no pass over the activation tensor
+        self.eng = OdeEngine(ode._hot_state_dict(), "", self.hi - self.lo, w, batch, ode.precision, dev, se_fold=True)
+        P, CH = L.SE_MAX_PARTIALS, 2 * self.eng.C
+        off = 2 * batch * P * CH
+        self.se_totals = [self.eng.se_scratch[off + k * batch * CH: off + (k + 1) * batch * CH].view(batch, CH) for k in range(2)]
         self.device = dev
         self.launches = 0
         self.use_graphs = bool(use_graphs)      # replay captured graphs (eager stage launches if False)
@@ -115,41 +119,11 @@ class RowShardedOde:
 
     # ------------------------------------------------------------------ one engine event with the collectives in place
     def _run_event(self, ev, tdev):
-        from .engine import BUF_S0, BUF_X
-
-        eng, lib = self.eng, self.eng.lib
-        stream = eng._stream()
-        rows_own0, rows_own1 = (self.own_lo - self.lo) * self.w, (self.own_hi - self.lo) * self.w
-        n = ev.n_active
-        ch = 2 * eng.C
-        with torch.cuda.device(self.device):
-            if ev.run_cell:
-                for st in eng.cell_slots[ev.kind]:
-                    L.check(lib.sf_plan_run_stage(eng.plan, st, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
-                self.launches += len(eng.cell_slots[ev.kind])
-            if ev.run_prior:
-                for item in eng.prior_items:
-                    if item < L.SE_ITEM_BASE:
-                        L.check(lib.sf_plan_run_stage(eng.plan, item, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
-                        self.launches += 1
-                        continue
-                    which = item - L.SE_ITEM_BASE
-                    npart = L.check(lib.sf_plan_se_reduce(eng.plan, which, C.byref(ev), tdev.data_ptr(), rows_own0, rows_own1, stream),
-                                    "se_reduce")
-                    flat = eng.se_sums[which].view(-1)                  # kernel layout: [active sample][partial][2C], packed
-                    total = flat[: n * npart * ch].view(n, npart, ch).sum(dim=1)      # this rank's band
-                    if self.world > 1:
-                        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
-                    flat[: n * ch].view(n, ch).copy_(total)           # one "partial" per sample = the whole-image sum
-                    L.check(lib.sf_plan_se_apply(eng.plan, which, C.byref(ev), tdev.data_ptr(), 1, C.c_float(1.0 / (self.h * self.w)),
-                                                 stream), "se_apply")
-                    self.launches += 2
-        # halos of everything the next event reads: new state (fp32 master + operand planes) and the sampled input
-        s = ev.s_out
-        xs = [eng.state32[s]] + [p for p in eng.act[BUF_S0 + s] if p is not None]
-        if ev.run_prior:
-            xs += [p for p in eng.act[BUF_X] if p is not None]
-        exchange_halo_rows(xs, self.own_lo, self.own_hi, self.lo, self.hi, self.rank, self.world, self.group)
+        """Eager form: the event's op list (_event_ops) executed in order."""
+        self._ensure_exchange_buffers()
+        for op in self._event_ops(ev):
+            self._run_op(op, ev, tdev)
+            self.launches += op[0] in ("stage", "se_reduce", "se_apply")
 
     # ------------------------------------------------------------------ the same event as replayed CUDA-graph segments
     def _event_ops(self, ev):
@@ -163,7 +137,7 @@ class RowShardedOde:
                 if item < L.SE_ITEM_BASE:
                     ops.append(("stage", item))
                 else:
-                    w = item - L.SE_ITEM_BASE
+                    w = item % 1000          # SE_ITEM_BASE + which (apply form) or SE_FOLD_ITEM_BASE + which (folded form)
                     ops += [("se_reduce", w)] + ([("allreduce", w)] if self.world > 1 else []) + [("se_apply", w)]
         if self.world > 1:
             ops += [("pack", 0), ("p2p", 0), ("unpack", 0)]
@@ -178,19 +152,27 @@ class RowShardedOde:
             xs += [p for p in eng.act[BUF_X] if p is not None]
         return xs
 
-    def _halo_copy(self, ev, buf, rows, to_buffer):
-        """Byte-packed copy of the given local rows of every halo tensor into / out of a flat uint8 buffer (no allocation)."""
-        off = 0
-        for t in self._halo_tensors(ev):
-            view = t[:, rows]
-            n = view.numel() * view.element_size()
-            flat = buf[off:off + n].view(t.dtype).view(view.shape)
-            if to_buffer:
-                flat.copy_(view)
-            else:
-                view.copy_(flat)
-            off += n
-        return off
+    def _halo_launch(self, ev, to_flat: bool):
+        """All halo tensors of the event, both directions, in ONE kernel (sf_halo_copy): pack the band's boundary rows into the
+        send buffers, or unpack the received rows into the halos."""
+        key = (ev.s_out, ev.run_prior)
+        cache = self.__dict__.setdefault("_halo_args", {})
+        if key not in cache:
+            ts = self._halo_tensors(ev)
+            n = len(ts)
+            cache[key] = ((C.c_void_p * n)(*[t.data_ptr() for t in ts]),
+                          (C.c_longlong * n)(*[t.stride(0) * t.element_size() for t in ts]),
+                          (C.c_longlong * n)(*[t.stride(1) * t.element_size() for t in ts]), n)
+        ptrs, bstride, rbytes, n = cache[key]
+        a, b = self.own_lo - self.lo, self.own_hi - self.lo
+        up, dn = self.rank > 0, self.rank < self.world - 1
+        if to_flat:
+            fa, ra, fb, rb = (self.send_up if up else None), a, (self.send_dn if dn else None), b - HALO
+        else:
+            fa, ra, fb, rb = (self.recv_up if up else None), a - HALO, (self.recv_dn if dn else None), b
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        L.check(self.eng.lib.sf_halo_copy(ptrs, bstride, rbytes, n, self.B, HALO, ptr(fa), ra, ptr(fb), rb, int(to_flat),
+                                          self.eng._stream()), "sf_halo_copy")
 
     def _run_op(self, op, ev, tdev):
         eng, lib = self.eng, self.eng.lib
@@ -200,21 +182,14 @@ class RowShardedOde:
         a, b = self.own_lo - self.lo, self.own_hi - self.lo
         if kind == "stage":
             L.check(lib.sf_plan_run_stage(eng.plan, arg, C.byref(ev), tdev.data_ptr(), stream), "run_stage")
-        elif kind == "se_reduce":
-            npart = L.check(lib.sf_plan_se_reduce(eng.plan, arg, C.byref(ev), tdev.data_ptr(), a * self.w, b * self.w, stream), "se_reduce")
-            flat = eng.se_sums[arg].view(-1)
-            torch.sum(flat[: n * npart * ch].view(n, npart, ch), dim=1, out=self.se_total[arg][:n])     # this rank's band
+        elif kind == "se_reduce":         # this rank's band totals per (sample, channel) -> self.se_totals[arg][:n]
+            L.check(lib.sf_plan_se_reduce_totals(eng.plan, arg, C.byref(ev), tdev.data_ptr(), a * self.w, b * self.w, stream), "se_reduce_totals")
         elif kind == "allreduce":
-            dist.all_reduce(self.se_total[arg][:n], op=dist.ReduceOp.SUM, group=self.group)
-        elif kind == "se_apply":
-            eng.se_sums[arg].view(-1)[: n * ch].view(n, ch).copy_(self.se_total[arg][:n])                # one "partial" = whole image
-            L.check(lib.sf_plan_se_apply(eng.plan, arg, C.byref(ev), tdev.data_ptr(), 1, C.c_float(1.0 / (self.h * self.w)), stream),
-                    "se_apply")
+            dist.all_reduce(self.se_totals[arg][:n], op=dist.ReduceOp.SUM, group=self.group)
+        elif kind == "se_apply":          # totals -> scales (whole-image mean) -> folded into the consumers' weights
+            L.check(lib.sf_plan_se_finish(eng.plan, arg, C.byref(ev), tdev.data_ptr(), C.c_float(1.0 / (self.h * self.w)), stream), "se_finish")
         elif kind == "pack":
-            if self.rank > 0:
-                self._halo_copy(ev, self.send_up, slice(a, a + HALO), True)
-            if self.rank < self.world - 1:
-                self._halo_copy(ev, self.send_dn, slice(b - HALO, b), True)
+            self._halo_launch(ev, True)
         elif kind == "p2p":
             peer = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
             nbytes = sum(t[:, :HALO].numel() * t.element_size() for t in self._halo_tensors(ev))
@@ -228,10 +203,7 @@ class RowShardedOde:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         elif kind == "unpack":
-            if self.rank > 0:
-                self._halo_copy(ev, self.recv_up, slice(a - HALO, a), False)
-            if self.rank < self.world - 1:
-                self._halo_copy(ev, self.recv_dn, slice(b, b + HALO), False)
+            self._halo_launch(ev, False)
 
     def _ensure_exchange_buffers(self):
         eng = self.eng
@@ -240,7 +212,7 @@ class RowShardedOde:
             nbytes = rows * (4 + 4 * 2)              # fp32 state + up to 4 bf16 planes (state hi/lo, x hi/lo)
             mk = lambda: torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.send_up, self.recv_up, self.send_dn, self.recv_dn = mk(), mk(), mk(), mk()
-            self.se_total = [torch.zeros((self.B, 2 * eng.C), dtype=torch.float32, device=self.device) for _ in range(2)]
+
 
     def _run_rollout_graphed(self, evs, tdev, key):
         """Replays the rollout as CUDA graphs.  Preferred: ONE graph for the whole rollout with the NCCL calls (two [B, 2C]
@@ -264,7 +236,7 @@ class RowShardedOde:
                 try:
                     # warm the communicator outside the capture (the first collective of a process group initialises it)
                     # and so does the first send/recv with each neighbour; both only touch scratch buffers
-                    dist.all_reduce(self.se_total[0][:1], group=self.group)
+                    dist.all_reduce(self.se_totals[0][:1], group=self.group)
                     self._run_op(("p2p", 0), evs[0], tdev)
                     torch.cuda.synchronize(self.device)
                     g = torch.cuda.CUDAGraph()
