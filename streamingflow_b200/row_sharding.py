@@ -304,7 +304,8 @@ class RowShardedOde:
             if getattr(self, "_eps_static", None) is None or self._eps_static.shape[0] < max(ro.n_eps, 1):
                 self._eps_static = torch.empty((max(ro.n_eps, 1),) + tuple(eps.shape[1:]), dtype=torch.float32, device=self.device)
                 eng.alloc_gen += 1
-            self._eps_static[: eps.shape[0]].copy_(eps)
+            k = min(eps.shape[0], ro.n_eps)          # a caller's tape may hold more slots than this schedule consumes
+            self._eps_static[:k].copy_(eps[:k])
             eng.bind_eps(self._eps_static)
             key = (B, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
                    tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), ode.solver, bool(ode.impute), eng.precision)
@@ -315,7 +316,7 @@ class RowShardedOde:
             evs, tdev = plan
             self._run_rollout_graphed(evs, tdev, key)
         else:
-            eng.bind_eps(eps.contiguous())
+            eng.bind_eps(eps[: max(ro.n_eps, 1)].contiguous())
             table, evs = eng.build_table(ro.events)          # one upload for the whole rollout
             tdev = eng.upload_table(table)
             for ev in evs:

@@ -397,3 +397,65 @@ def test_depthwise7_layernorm_kernel_matches_torch(H, W, x3):
     got = (oh.float() + (ol.float() if x3 else 0)).double().cpu()
     err = (got - want).abs().max().item() / want.abs().max().item()
     assert err < (1e-5 if x3 else 5e-3), err            # output rounding: bf16 (2^-9) or split bf16 (2^-17)
+
+
+def test_halo_copy_packs_and_unpacks_boundary_rows_in_one_launch():
+    """sf_halo_copy (row sharding): rows of several NHWC tensors of different dtypes <-> the flat byte buffers NCCL moves, both
+    directions per launch; the flat layout is tensor-major, then batch (what row_sharding.exchange_halo_rows sends)."""
+    L, lib = _lib()
+    B, R, W, Cc, H = 2, 40, 24, 64, 12
+    ts = [torch.randn(B, R, W, Cc, device="cuda"), torch.randn(B, R, W, Cc, device="cuda").to(torch.bfloat16),
+          torch.randn(B, R, W, 2 * Cc, device="cuda").to(torch.bfloat16)]
+    n = len(ts)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    bstr = (C.c_longlong * n)(*[t.stride(0) * t.element_size() for t in ts])
+    rbytes = (C.c_longlong * n)(*[t.stride(1) * t.element_size() for t in ts])
+    nbytes = sum(t[:, :H].numel() * t.element_size() for t in ts)
+    up, dn = torch.zeros(nbytes, dtype=torch.uint8, device="cuda"), torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    a, b = 12, 28          # the "band" is rows [12, 28): pack its first / last 12 rows
+    L.check(lib.sf_halo_copy(ptrs, bstr, rbytes, n, B, H, C.c_void_p(up.data_ptr()), a, C.c_void_p(dn.data_ptr()), b - H, 1, _stream()), "pack")
+    want = lambda rows: torch.cat([t[:, rows].contiguous().view(torch.uint8).reshape(-1) for t in ts])
+    assert torch.equal(up, want(slice(a, a + H))) and torch.equal(dn, want(slice(b - H, b)))
+    # unpack into the halos of fresh tensors: rows [0, 12) from `dn`-style data of the upper neighbour, rows [28, 40) from the lower one
+    zs = [torch.zeros_like(t) for t in ts]
+    ptrz = (C.c_void_p * n)(*[t.data_ptr() for t in zs])
+    L.check(lib.sf_halo_copy(ptrz, bstr, rbytes, n, B, H, C.c_void_p(dn.data_ptr()), a - H, C.c_void_p(up.data_ptr()), b, 0, _stream()), "unpack")
+    torch.cuda.synchronize()
+    for z, t in zip(zs, ts):
+        assert torch.equal(z[:, a - H:a], t[:, b - H:b]) and torch.equal(z[:, b:b + H], t[:, a:a + H]) and not z[:, a:b].any()
+    # one direction only (first / last rank)
+    up.zero_()
+    L.check(lib.sf_halo_copy(ptrs, bstr, rbytes, n, B, H, None, 0, C.c_void_p(up.data_ptr()), b - H, 1, _stream()), "pack one side")
+    assert torch.equal(up, want(slice(b - H, b)))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_single_rank_row_sharded_rollout_equals_the_engine(precision):
+    """RowShardedOde on ONE rank (no collectives): the three-step squeeze-excite (sf_plan_se_reduce_totals -> [all-reduce] ->
+    sf_plan_se_finish: scales folded into the weights) gives the rollout of the regular engine; graph segments and eager."""
+    from streamingflow_b200.layers.temporal_ode_bayes import NNFOwithBayesianJumps
+    from streamingflow_b200.config import ode_cfg
+    from streamingflow_b200.row_sharding import RowShardedOde
+
+    Cc, H, W, B = 64, 40, 24, 2
+    m = NNFOwithBayesianJumps(Cc, Cc, ode_cfg(Cc)).eval()
+    m.load_state_dict(so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 13, 1.0), strict=True)
+    m = m.cuda()
+    m.precision = precision
+    times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])] * B
+    targets = [[-1.0, 0.0, 1.0, 2.0]] * B
+    g = torch.Generator().manual_seed(13)
+    hx = torch.tanh(torch.randn(8 * B, Cc, H, W, generator=g)).cuda()
+    tape = torch.randn(18 * B, Cc, H, W, generator=g).cuda()
+    m._draw_noise = lambda n, h, w, device: tape[:max(n, 1)].contiguous()
+    with torch.no_grad():
+        _, want = m.integrate_latents(hx, [8] * B, times, targets, 0.05)
+        for graphs in (True, False):
+            sh = RowShardedOde(m, H, W, B, use_graphs=graphs)
+            got, _ = sh.integrate(hx, [8] * B, times, targets, 0.05, noise=tape)
+            got2, _ = sh.integrate(hx, [8] * B, times, targets, 0.05, noise=tape)
+            torch.cuda.synchronize()
+            # same kernels, same order of arithmetic except the SE mean (per-block partials summed in one more step): rounding-level
+            err = ((got.double() - want.double()).abs().max() / want.double().abs().max()).item()
+            assert err < (2e-3 if precision == "bf16" else 1e-5), (graphs, err)
+            assert torch.equal(got, got2)
