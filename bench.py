@@ -701,10 +701,13 @@ def config5_row_sharded(c, steps=3, full_line=False):
     sh = RowShardedOde(m, H, H, 1)
     n_eps = 18
     tape = torch.randn(n_eps, C, H, H, device=c.dev, generator=g)
+    # every rank keeps only its local image (band + halo rows) of the observations and of the noise tape resident, the way a
+    # sharded producer delivers them; the values are those of the same full grid on every rank
+    hx, tape = hx[:, :, sh.lo:sh.hi].contiguous(), tape[:, :, sh.lo:sh.hi].contiguous()
 
     def rollout():
         with torch.no_grad():
-            return sh.integrate(hx, [len(times)], [times], [TARGETS], 0.05, noise=tape)
+            return sh.integrate(hx, [len(times)], [times], [TARGETS], 0.05, noise=tape, local_rows=True)
 
     rollout(); rollout()
     c.barrier()
@@ -720,11 +723,26 @@ def config5_row_sharded(c, steps=3, full_line=False):
     value = n * steps / (ms * 1e-3)
     flops = flops_per_state_step_px(C) * H * H * (n + ro.n_jumps)
     out = dict(workload=f"config5: 400x400x128 ODE state, B = 1, row-sharded over {c.world} GPU(s) ({sh.own_hi - sh.own_lo} rows + 12-row halos per rank), "
-                        "per event one NCCL send/recv pair per neighbour + two [B,2C] all-reduces, replayed as CUDA graph(s)",
+                        "per event one halo push / pull per neighbour + two [B,2C] all-reduces (NVLink peer-memory kernels, or NCCL calls: see transport), "
+                        "replayed as CUDA graph(s)",
                value=value, unit=UNIT, ms_per_rollout=ms / steps, steps=steps, scaling="strong", n_gpus=c.world,
                tflops_algorithmic=flops * steps / (ms * 1e-3) / 1e12, band_rows=sh.own_hi - sh.own_lo, halo_rows=12, launch=sh.graph_mode,
-               whole_graph_error=sh.__dict__.get("_whole_graph_error"))
+               transport=sh.transport, peer_error=sh.peer_error, whole_graph_error=sh.__dict__.get("_whole_graph_error"))
     launches = sh.launches
+    if os.environ.get("SF_ROWSHARD_PROFILE", "0") == "1":      # one more rollout with CUDA-event marks between its phases
+        sh.profile = []
+        t0 = time.perf_counter()
+        rollout()
+        host_ms = (time.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        marks = sh.profile
+        sh.profile = None
+        out["phases_ms"] = {f"{a[0]} -> {b[0]}": round(a[1].elapsed_time(b[1]), 3) for a, b in zip(marks[:-1], marks[1:])}
+        out["phases_ms"]["host time of the call"] = round(host_ms, 3)
+    if sh.arena is not None and sh.arena.tracing:          # SF_PEER_TRACE=1: where the exchange time goes (in-kernel %globaltimer stamps)
+        out["peer_trace"] = sh.arena.trace_report()
+        if c.rank == c.world // 2 and c.rank != 0:
+            print(json.dumps(dict(rank=c.rank, peer_trace=out["peer_trace"])), file=sys.stderr, flush=True)
     sh.release_graphs()          # graphs with captured NCCL kernels must be destroyed before the process group
     del sh
     if not full_line:

@@ -21,6 +21,7 @@
 #ifndef SF_B200_H_
 #define SF_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -190,6 +191,39 @@ int sf_plan_se_finish(sf_plan* p, int which, const sf_event* ev, const int32_t* 
  * in ONE launch; to_flat = 1 packs, 0 unpacks.  The flat buffers are what ncclSend / ncclRecv move. */
 int sf_halo_copy(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
                  void* flat_a, int row0_a, void* flat_b, int row0_b, int to_flat, void* stream);
+
+/* Row sharding over NVLink peer memory -- the per-event exchanges without an NCCL call (streamingflow_b200/csrc/sf_peer.cuh).
+ * The reference has no multi-GPU form of this path (the split is this library's own); these entry points are what a
+ * host binds next to ncclSend / ncclRecv / ncclAllReduce.
+ * sf_peer_alloc: a zeroed device buffer plus its 64-byte inter-process handle (cudaIpcGetMemHandle); the other ranks of the node
+ * map it with sf_peer_open (cudaIpcOpenMemHandle, peer access enabled lazily) and unmap it with sf_peer_close before the owner
+ * calls sf_peer_free.  Handles travel between the processes by any host channel (torch.distributed.all_gather_object here). */
+int sf_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int sf_peer_open(const unsigned char* handle64, void** ptr);
+int sf_peer_close(void* ptr);
+int sf_peer_free(void* ptr);
+/* sf_halo_push: sf_halo_copy(to_flat = 1) whose flat buffers live in the NEIGHBOURS' memory (a = upper, b = lower neighbour; NULL
+ * skips one): the rows are stored straight into copy (sequence & 1) of the neighbour's receive buffer (copies parity_stride bytes
+ * apart), then the neighbour's arrival counter is released (system scope) with this launch's sequence number.  seq: two unsigned
+ * words of LOCAL device memory {launches completed, block ticket}, advanced by the kernel -- no per-call argument changes, so the
+ * launch replays inside a CUDA graph.
+ * sf_halo_pull: waits until the local counters flag_a / flag_b have reached its own sequence number, then unpacks the received
+ * rows into the halos.  A wait gives up after 10 s and latches a non-zero code in *err (device memory, zero-initialised); later
+ * waits return at once, the host checks *err after the rollout.
+ * trace (all three exchange entry points; NULL = off): a [64][4] ring of %globaltimer stamps in local device memory, entry
+ * (sequence & 63) = {launch start, wait done, launch end, -}: where an event's exchange time goes, without a profiler. */
+int sf_halo_push(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* peer_flat_a, int row0_a, void* peer_flat_b, int row0_b, long long parity_stride, unsigned* peer_flag_a,
+                 unsigned* peer_flag_b, unsigned* seq, unsigned long long* trace, void* stream);
+int sf_halo_pull(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* flat_a, int row0_a, void* flat_b, int row0_b, long long parity_stride, unsigned* flag_a, unsigned* flag_b,
+                 unsigned* seq, int* err, unsigned long long* trace, void* stream);
+/* In-place sum of data[0..n) over the ranks of the node in ONE launch of one block: the vector is stored into slot `rank` of every
+ * rank's slot arena (slots[r]: [2 copies][world][n_max] floats in rank r's memory), one counter per rank is released
+ * (flags[r]: [world] unsigned in rank r's memory), the block waits for the world's contributions and adds the slots in rank order
+ * (bit-identical result on every rank).  Replaces ncclAllReduce for the [n_active][2C] squeeze-excite sums. */
+int sf_peer_allreduce_f32(float* data, int n, int n_max, int rank, int world, void* const* slots, void* const* flags, unsigned* seq, int* err,
+                          unsigned long long* trace, void* stream);
 
 /* layout kernels (HBM-bound, 128-bit vectorised) */
 int sf_pack_nchw_f32(const float* src, void* dst_hi, void* dst_lo, int n_images, int C, int H, int W, void* stream);

@@ -25,9 +25,11 @@ def barrier():
 
 
 c.barrier = barrier
-for mode in (sys.argv[1:] or ["whole", "segments"]):
+for mode in (sys.argv[1:] or ["peer", "whole", "segments"]):          # peer = NVLink peer-memory kernels; whole / segments = NCCL graph modes
+    os.environ["SF_ROWSHARD_TRANSPORT"] = "peer" if mode == "peer" else "nccl"
     os.environ["SF_ROWSHARD_GRAPH"] = mode
     out = bench.config5_row_sharded(c, steps=5)
     if rank == 0:
-        print(json.dumps(dict(mode=mode, **{k: out[k] for k in ("value", "ms_per_rollout", "n_gpus", "launch", "whole_graph_error", "band_rows")})), flush=True)
+        print(json.dumps(dict(mode=mode, **{k: out.get(k) for k in ("value", "ms_per_rollout", "n_gpus", "launch", "transport", "peer_error",
+                                                                    "whole_graph_error", "band_rows", "peer_trace", "phases_ms")})), flush=True)
 dist.destroy_process_group()

@@ -64,6 +64,16 @@ EXPORTS = {
     "sf_plan_se_finish": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Event), C.c_void_p, C.c_float, C.c_void_p]),
     "sf_halo_copy": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "sf_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "sf_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "sf_peer_close": (C.c_int, [C.c_void_p]),
+    "sf_peer_free": (C.c_int, [C.c_void_p]),
+    "sf_halo_push": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sf_halo_pull": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sf_peer_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "sf_pack_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_normal_policy": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -699,23 +699,22 @@ struct HaloCopy {
   int n_tensors, B, nrows, to_flat;
 };
 __global__ void __launch_bounds__(256) halo_copy_kernel(const HaloCopy h) {
-  long long per_range = 0;
-  for (int t = 0; t < h.n_tensors; ++t) per_range += (long long)h.B * h.nrows * h.row_bytes[t];
-  const long long units = per_range >> 4;
+  unsigned units = 0;                                  // 16-byte units per direction; 32-bit index arithmetic (a flat buffer is < 64 GB)
+  for (int t = 0; t < h.n_tensors; ++t) units += (unsigned)h.B * (unsigned)h.nrows * (unsigned)(h.row_bytes[t] >> 4);
   for (int r = 0; r < 2; ++r) {
     if (h.flat[r] == nullptr) continue;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
-      long long off = u << 4, rem = off;
+    for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+      unsigned rem = u;
       int t = 0;
       for (; t < h.n_tensors - 1; ++t) {
-        const long long sz = (long long)h.B * h.nrows * h.row_bytes[t];
+        const unsigned sz = (unsigned)h.B * (unsigned)h.nrows * (unsigned)(h.row_bytes[t] >> 4);
         if (rem < sz) break;
         rem -= sz;
       }
-      const long long chunk = (long long)h.nrows * h.row_bytes[t];
-      const long long b = rem / chunk, inner = rem - b * chunk;
-      uint4* g = reinterpret_cast<uint4*>(h.base[t] + b * h.batch_stride[t] + (long long)h.row0[r] * h.row_bytes[t] + inner);
-      uint4* f = reinterpret_cast<uint4*>(h.flat[r] + off);
+      const unsigned chunk = (unsigned)h.nrows * (unsigned)(h.row_bytes[t] >> 4);
+      const unsigned b = rem / chunk, inner = rem - b * chunk;
+      uint4* g = reinterpret_cast<uint4*>(h.base[t] + (long long)b * h.batch_stride[t] + (long long)h.row0[r] * h.row_bytes[t] + ((long long)inner << 4));
+      uint4* f = reinterpret_cast<uint4*>(h.flat[r]) + u;
       if (h.to_flat) *f = *g; else *g = *f;
     }
   }

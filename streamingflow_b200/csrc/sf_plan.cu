@@ -11,6 +11,7 @@
 
 #include "sf_conv.cuh"
 #include "sf_elementwise.cuh"
+#include "sf_peer.cuh"
 
 namespace {
 
@@ -725,6 +726,118 @@ int sf_halo_copy(void* const* tensors, const long long* batch_stride_bytes, cons
   h.n_tensors = n_tensors; h.B = B; h.nrows = nrows; h.to_flat = to_flat;
   const int grid = (int)std::min<long long>(((total >> 4) + 255) / 256, 148 * 8);
   halo_copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(h);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+// ---- peer memory over NVLink (sf_peer.cuh): arena allocation / export / import, and the exchange kernels ----------------------
+int sf_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(SF_ERR_INVALID, "bad peer arena arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  SF_CUDA(cudaMalloc(&p, bytes));
+  SF_CUDA(cudaMemset(p, 0, bytes));
+  SF_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(SF_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return SF_OK;
+}
+int sf_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(SF_ERR_INVALID, "bad peer handle arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  SF_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SF_OK;
+}
+int sf_peer_close(void* ptr) {
+  if (!ptr) return SF_OK;
+  SF_CUDA(cudaIpcCloseMemHandle(ptr));
+  return SF_OK;
+}
+int sf_peer_free(void* ptr) {
+  if (!ptr) return SF_OK;
+  SF_CUDA(cudaFree(ptr));
+  return SF_OK;
+}
+
+namespace {
+int fill_peer_halo(sf::PeerHalo& a, void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B,
+                   int nrows, void* flat_a, int row0_a, void* flat_b, int row0_b, long long parity_stride, unsigned* flag_a, unsigned* flag_b,
+                   unsigned* seq, int* err, unsigned long long* trace, long long* total) {
+  if (!tensors || !batch_stride_bytes || !row_bytes || n_tensors < 1 || n_tensors > 6 || B < 1 || nrows < 1 || (!flat_a && !flat_b) || !seq ||
+      (flat_a && !flag_a) || (flat_b && !flag_b) || (parity_stride & 15))
+    return fail(SF_ERR_INVALID, "bad peer halo arguments");
+  memset(&a, 0, sizeof(a));
+  *total = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    if (!tensors[t] || (row_bytes[t] & 15) || (batch_stride_bytes[t] & 15) || (reinterpret_cast<uintptr_t>(tensors[t]) & 15))
+      return fail(SF_ERR_INVALID, "halo tensors must be 16-byte aligned with row sizes that are multiples of 16 bytes");
+    a.h.base[t] = reinterpret_cast<char*>(tensors[t]);
+    a.h.batch_stride[t] = batch_stride_bytes[t];
+    a.h.row_bytes[t] = row_bytes[t];
+    *total += (long long)B * nrows * row_bytes[t];
+  }
+  if (*total > parity_stride) return fail(SF_ERR_INVALID, "halo rows exceed the receive buffer");
+  a.h.flat[0] = reinterpret_cast<char*>(flat_a); a.h.row0[0] = row0_a;
+  a.h.flat[1] = reinterpret_cast<char*>(flat_b); a.h.row0[1] = row0_b;
+  a.h.n_tensors = n_tensors; a.h.B = B; a.h.nrows = nrows; a.h.to_flat = 1;
+  a.parity_stride = parity_stride;
+  a.flag[0] = flag_a; a.flag[1] = flag_b;
+  a.seq = seq; a.err = err; a.trace = trace;
+  a.timeout_ns = 10000000000ull;
+  return SF_OK;
+}
+}  // namespace
+
+int sf_halo_push(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* peer_flat_a, int row0_a, void* peer_flat_b, int row0_b, long long parity_stride, unsigned* peer_flag_a,
+                 unsigned* peer_flag_b, unsigned* seq, unsigned long long* trace, void* stream) {
+  sf::PeerHalo a;
+  long long total;
+  if (int rc = fill_peer_halo(a, tensors, batch_stride_bytes, row_bytes, n_tensors, B, nrows, peer_flat_a, row0_a, peer_flat_b, row0_b,
+                              parity_stride, peer_flag_a, peer_flag_b, seq, nullptr, trace, &total))
+    return rc;
+  const int grid = (int)std::min<long long>(((total >> 4) + 255) / 256, 148 * 4);
+  sf::halo_push_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_halo_pull(void* const* tensors, const long long* batch_stride_bytes, const long long* row_bytes, int n_tensors, int B, int nrows,
+                 void* flat_a, int row0_a, void* flat_b, int row0_b, long long parity_stride, unsigned* flag_a, unsigned* flag_b,
+                 unsigned* seq, int* err, unsigned long long* trace, void* stream) {
+  sf::PeerHalo a;
+  long long total;
+  if (!err) return fail(SF_ERR_INVALID, "sf_halo_pull needs an error word");
+  if (int rc = fill_peer_halo(a, tensors, batch_stride_bytes, row_bytes, n_tensors, B, nrows, flat_a, row0_a, flat_b, row0_b, parity_stride,
+                              flag_a, flag_b, seq, err, trace, &total))
+    return rc;
+  const int grid = (int)std::min<long long>(((total >> 4) + 255) / 256, 148 * 4);
+  sf::halo_pull_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_peer_allreduce_f32(float* data, int n, int n_max, int rank, int world, void* const* slots, void* const* flags, unsigned* seq, int* err,
+                          unsigned long long* trace, void* stream) {
+  if (!data || n < 1 || n > n_max || world < 1 || world > sf::PEER_MAX || rank < 0 || rank >= world || !slots || !flags || !seq || !err)
+    return fail(SF_ERR_INVALID, "bad peer all-reduce arguments");
+  sf::PeerReduce a;
+  memset(&a, 0, sizeof(a));
+  a.data = data; a.n = n; a.n_max = n_max; a.rank = rank; a.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (!slots[r] || !flags[r]) return fail(SF_ERR_INVALID, "peer all-reduce: missing arena pointer");
+    a.slots[r] = reinterpret_cast<float*>(slots[r]);
+    a.flags[r] = reinterpret_cast<unsigned*>(flags[r]);
+  }
+  a.seq = seq; a.err = err; a.trace = trace; a.timeout_ns = 10000000000ull;
+  sf::peer_allreduce_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -5,10 +5,16 @@ Each rank owns a contiguous band of latent rows and keeps HALO = 12 extra rows a
     series), the prior network p_model sees the new state within 5 rows; an event therefore yields a correct
     sampled input x' on a band only if (state, x) were correct within 7 + 5 = 12 rows of it;
   * per event every rank runs the UNCHANGED stage kernels on its local image (band + halos), then swaps 12 boundary rows of
-    the new state (fp32 master + bf16 operand planes) and of x' with its two neighbours (NCCL send/recv over NVLink):
+    the new state (fp32 master + bf16 operand planes) and of x' with its two neighbours:
     one exchange per event instead of one per conv stage, paid for with (24 / band) redundant rows of compute;
   * the two squeeze-excite layers need WHOLE-image channel means: each rank reduces over its own band only
-    (sf_plan_se_reduce with a pixel window), the [B, 2C] partial sums are all-reduced (sum), then sf_plan_se_apply runs.
+    (sf_plan_se_reduce_totals with a pixel window), the [B, 2C] partial sums are summed over the ranks, then sf_plan_se_finish
+    folds the scales into the consuming convs' weights;
+  * transport (default "peer"): the exchanges are KERNELS over NVLink peer memory (csrc/sf_peer.cuh, peer.py): sf_halo_push
+    stores the boundary rows straight into the neighbours' receive buffers and releases their arrival counters, sf_halo_pull
+    waits for both neighbours and fills the halos, sf_peer_allreduce_f32 sums the SE totals through per-rank slots -- three
+    launches per event, no NCCL call, and the whole rollout (stages + exchanges) replays as ONE CUDA graph.  "nccl" keeps the
+    send/recv + all-reduce calls (graph segments between them, or captured inside one graph with SF_ROWSHARD_GRAPH=whole).
 Zero padding at the true image border comes from TMA's out-of-bounds fill on the first / last rank; on interior ranks the
 local image's outer rows are halo data and whatever the fill corrupts stays inside the discarded part of the halo.
 
@@ -79,10 +85,21 @@ def exchange_halo_rows(ts, own_lo: int, own_hi: int, lo: int, hi: int, rank: int
         unpack(buf, rows)
 
 
+def _recorded_event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
 class RowShardedOde:
     """Integrates the latent rollout of a NNFOwithBayesianJumps module with the grid's rows split over the ranks of ``group``."""
 
-    def __init__(self, ode, h: int, w: int, batch: int, group=None, use_graphs: bool = True):
+    def __init__(self, ode, h: int, w: int, batch: int, group=None, use_graphs: bool = True, transport: Optional[str] = None):
+        """transport: how the per-event exchanges travel -- "peer": kernels that store into the neighbours' memory over NVLink
+        (csrc/sf_peer.cuh; the whole rollout incl. the exchanges is ONE CUDA graph), "nccl": send/recv + all-reduce calls.
+        Default: $SF_ROWSHARD_TRANSPORT or "peer", falling back to "nccl" (on all ranks together) if the arenas cannot be mapped."""
+        import os
+
         from .engine import OdeEngine
 
         self.ode, self.h, self.w, self.B, self.group = ode, h, w, batch, group
@@ -102,6 +119,22 @@ class RowShardedOde:
         self.launches = 0
         self.use_graphs = bool(use_graphs)      # replay captured graphs (eager stage launches if False)
         self.graph_mode = "eager"
+        self.transport = (transport or os.environ.get("SF_ROWSHARD_TRANSPORT", "peer")) if self.world > 1 else "none"
+        if self.transport not in ("peer", "nccl", "none"):
+            raise L.SfError(f"unknown transport {self.transport!r}")
+        self.arena = None
+        self.peer_error = None
+        self.profile = None          # a list here receives (label, CUDA event) marks from integrate()
+        if self.transport == "peer":
+            from .peer import PeerArena
+
+            try:
+                self.arena = PeerArena(self.eng.lib, self.rank, self.world, group, self._halo_bytes_max(), batch * CH)
+            except L.SfError as e:          # raised on every rank together (the set-up agrees on its outcome first)
+                self.peer_error, self.transport = str(e)[:200], "nccl"
+
+    def _halo_bytes_max(self) -> int:
+        return self.B * HALO * self.w * self.eng.C * (4 + 4 * 2)        # fp32 state + up to 4 bf16 planes (state hi/lo, x hi/lo)
 
     # ------------------------------------------------------------------ noise shared by all ranks
     def draw_noise(self, n: int) -> torch.Tensor:
@@ -117,13 +150,15 @@ class RowShardedOde:
             eps[i].copy_(full[:, self.lo:self.hi])
         return eps
 
+    _KERNEL_OPS = ("stage", "se_reduce", "se_apply", "pack", "unpack", "push", "pull", "peer_allreduce")      # ops that are launches of OUR kernels
+
     # ------------------------------------------------------------------ one engine event with the collectives in place
     def _run_event(self, ev, tdev):
         """Eager form: the event's op list (_event_ops) executed in order."""
         self._ensure_exchange_buffers()
         for op in self._event_ops(ev):
             self._run_op(op, ev, tdev)
-            self.launches += op[0] in ("stage", "se_reduce", "se_apply")
+            self.launches += op[0] in self._KERNEL_OPS
 
     # ------------------------------------------------------------------ the same event as replayed CUDA-graph segments
     def _event_ops(self, ev):
@@ -138,8 +173,11 @@ class RowShardedOde:
                     ops.append(("stage", item))
                 else:
                     w = item % 1000          # SE_ITEM_BASE + which (apply form) or SE_FOLD_ITEM_BASE + which (folded form)
-                    ops += [("se_reduce", w)] + ([("allreduce", w)] if self.world > 1 else []) + [("se_apply", w)]
-        if self.world > 1:
+                    reduce = [("peer_allreduce" if self.transport == "peer" else "allreduce", w)] if self.world > 1 else []
+                    ops += [("se_reduce", w)] + reduce + [("se_apply", w)]
+        if self.transport == "peer":
+            ops += [("push", 0), ("pull", 0)]
+        elif self.world > 1:
             ops += [("pack", 0), ("p2p", 0), ("unpack", 0)]
         return ops
 
@@ -152,18 +190,42 @@ class RowShardedOde:
             xs += [p for p in eng.act[BUF_X] if p is not None]
         return xs
 
-    def _halo_launch(self, ev, to_flat: bool):
-        """All halo tensors of the event, both directions, in ONE kernel (sf_halo_copy): pack the band's boundary rows into the
-        send buffers, or unpack the received rows into the halos."""
+    def _halo_args(self, ev):
         key = (ev.s_out, ev.run_prior)
-        cache = self.__dict__.setdefault("_halo_args", {})
+        cache = self.__dict__.setdefault("_halo_cache", {})
         if key not in cache:
             ts = self._halo_tensors(ev)
             n = len(ts)
             cache[key] = ((C.c_void_p * n)(*[t.data_ptr() for t in ts]),
                           (C.c_longlong * n)(*[t.stride(0) * t.element_size() for t in ts]),
                           (C.c_longlong * n)(*[t.stride(1) * t.element_size() for t in ts]), n)
-        ptrs, bstride, rbytes, n = cache[key]
+        return cache[key]
+
+    def _halo_peer(self, ev, push: bool):
+        """Peer transport.  push: the band's boundary rows of all halo tensors stored straight into the neighbours' receive
+        buffers + their arrival counters released (sf_halo_push); pull: wait for both neighbours' rows, unpack them into the
+        local halos (sf_halo_pull).  One launch each."""
+        from . import peer as P
+
+        ptrs, bstride, rbytes, n = self._halo_args(ev)
+        ar, r, lib = self.arena, self.rank, self.eng.lib
+        a, b = self.own_lo - self.lo, self.own_hi - self.lo
+        up, dn = r > 0, r < self.world - 1
+        if push:
+            L.check(lib.sf_halo_push(ptrs, bstride, rbytes, n, self.B, HALO,
+                                     ar.recv_dn(r - 1) if up else None, a, ar.recv_up(r + 1) if dn else None, b - HALO, ar.halo_stride,
+                                     ar.flag(r - 1, P.FLAG_DN) if up else None, ar.flag(r + 1, P.FLAG_UP) if dn else None,
+                                     ar.local(P.LOC_PUSH), ar.trace(0), self.eng._stream()), "sf_halo_push")
+        else:
+            L.check(lib.sf_halo_pull(ptrs, bstride, rbytes, n, self.B, HALO,
+                                     ar.recv_up(r) if up else None, a - HALO, ar.recv_dn(r) if dn else None, b, ar.halo_stride,
+                                     ar.flag(r, P.FLAG_UP) if up else None, ar.flag(r, P.FLAG_DN) if dn else None,
+                                     ar.local(P.LOC_PULL), ar.local(P.LOC_ERR), ar.trace(1), self.eng._stream()), "sf_halo_pull")
+
+    def _halo_launch(self, ev, to_flat: bool):
+        """NCCL transport: all halo tensors of the event, both directions, in ONE kernel (sf_halo_copy): pack the band's boundary
+        rows into the send buffers, or unpack the received rows into the halos."""
+        ptrs, bstride, rbytes, n = self._halo_args(ev)
         a, b = self.own_lo - self.lo, self.own_hi - self.lo
         up, dn = self.rank > 0, self.rank < self.world - 1
         if to_flat:
@@ -204,12 +266,21 @@ class RowShardedOde:
                 req.wait()
         elif kind == "unpack":
             self._halo_launch(ev, False)
+        elif kind == "peer_allreduce":    # the band totals summed over the ranks by ONE kernel storing into every rank's arena
+            from . import peer as P
+
+            ar = self.arena
+            L.check(lib.sf_peer_allreduce_f32(C.c_void_p(self.se_totals[arg].data_ptr()), n * ch, ar.n_max, self.rank, self.world, ar.slots,
+                                              ar.ar_flags, ar.local(P.LOC_AR), ar.local(P.LOC_ERR), ar.trace(2), stream), "sf_peer_allreduce_f32")
+        elif kind == "push":
+            self._halo_peer(ev, True)
+        elif kind == "pull":
+            self._halo_peer(ev, False)
 
     def _ensure_exchange_buffers(self):
         eng = self.eng
-        if getattr(self, "send_up", None) is None:
-            rows = self.B * HALO * self.w * eng.C
-            nbytes = rows * (4 + 4 * 2)              # fp32 state + up to 4 bf16 planes (state hi/lo, x hi/lo)
+        if self.transport == "nccl" and getattr(self, "send_up", None) is None:
+            nbytes = self._halo_bytes_max()
             mk = lambda: torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.send_up, self.recv_up, self.send_dn, self.recv_dn = mk(), mk(), mk(), mk()
 
@@ -230,9 +301,18 @@ class RowShardedOde:
             if len(cache) >= 4:
                 cache.clear()
             torch.cuda.synchronize(self.device)
-            n_launch = sum(1 for ev in evs for o in self._event_ops(ev) if o[0] in ("stage", "se_reduce", "se_apply"))
+            n_launch = sum(1 for ev in evs for o in self._event_ops(ev) if o[0] in self._KERNEL_OPS)
             prog, mode = None, "segments"
-            if self.world > 1 and os.environ.get("SF_ROWSHARD_GRAPH", "segments") == "whole" and self.__dict__.get("_whole_graph_ok", True):
+            if self.transport == "peer":
+                # every exchange is a plain kernel: the whole rollout is one graph, nothing for the host to do per event
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    for ev in evs:
+                        for op in self._event_ops(ev):
+                            self._run_op(op, ev, tdev)
+                prog, mode = [("graph", g, None)], "whole rollout incl. peer-memory exchanges (one graph)"
+                dist.barrier(group=self.group)      # capture times differ per rank: start the first replay together (the waits are bounded)
+            elif self.world > 1 and os.environ.get("SF_ROWSHARD_GRAPH", "segments") == "whole" and self.__dict__.get("_whole_graph_ok", True):
                 try:
                     # warm the communicator outside the capture (the first collective of a process group initialises it)
                     # and so does the first send/recv with each neighbour; both only touch scratch buffers
@@ -284,21 +364,51 @@ class RowShardedOde:
         self.__dict__.pop("_graph_cache", None)
         gc.collect()
         torch.cuda.synchronize(self.device)
+        if self.arena is not None:          # peer transport: a timed-out exchange surfaces here at the latest; then unmap
+            arena, self.arena = self.arena, None
+            try:
+                arena.check()
+            finally:
+                arena.close()
 
     def integrate(self, hx_obs: torch.Tensor, obs_counts: Sequence[int], times, targets, delta_t: float,
-                  noise: Optional[torch.Tensor] = None):
-        """hx_obs: the FULL [sum(obs_counts), C, h, w] encoded observations (every rank passes the same tensor; only its rows
-        are used).  noise: optional full-size tape [n, C, h, w] (tests).  Returns the selected latents restricted to this
-        rank's band: [B, T, C, own rows, w], plus the Rollout."""
+                  noise: Optional[torch.Tensor] = None, local_rows: bool = False):
+        """hx_obs: the [sum(obs_counts), C, h, w] encoded observations.  By default every rank passes the FULL grid and only its
+        rows are used; with ``local_rows=True`` hx_obs (and noise) already hold just this rank's local image, rows [lo, hi) --
+        how a sharded producer would deliver them (no per-rollout slicing pass).  noise: optional tape [n, C, rows, w] (tests,
+        benchmarks).  Returns the selected latents restricted to this rank's band: [B, T, C, own rows, w], plus the Rollout.
+        Nothing in here synchronises the host with the device: schedules, event tables and gather indices are cached per
+        schedule, so the host prepares rollout i + 1 while the device runs rollout i."""
         ode, eng = self.ode, self.eng
         B = len(obs_counts)
-        plans = [plan_sample(times[b], targets[b], delta_t, ode.use_variable_ode_step, ode.solver) for b in range(B)]
-        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-        ro = compile_rollout(plans, base, ode.solver, bool(ode.impute))
-        eng.bind_observations(hx_obs[:, :, self.lo:self.hi].contiguous())
+        prof = self.profile                          # optional: list that receives (label, cuda event) marks of this call
+        mark = (lambda label: prof.append((label, _recorded_event()))) if prof is not None else (lambda label: None)
+        mark("start")
+        if self.transport == "peer" and self.arena is None:          # released earlier: map the arenas again
+            from .peer import PeerArena
+
+            self.arena = PeerArena(eng.lib, self.rank, self.world, self.group, self._halo_bytes_max(), self.B * 2 * eng.C)
+            eng.alloc_gen += 1
+        key = (B, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
+               tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), ode.solver, bool(ode.impute), eng.precision)
+        sched = self.__dict__.setdefault("_schedules", {}).get(key)
+        if sched is None:
+            if len(self._schedules) >= 8:
+                self._schedules.clear()
+            plans = [plan_sample(times[b], targets[b], delta_t, ode.use_variable_ode_step, ode.solver) for b in range(B)]
+            base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+            ro = compile_rollout(plans, base, ode.solver, bool(ode.impute))
+            flat = torch.tensor([s for slots in ro.out_slots for s in slots], dtype=torch.int32, device=self.device)
+            sched = self._schedules[key] = (ro, flat)
+        ro, flat = sched
+        rows = slice(None) if local_rows else slice(self.lo, self.hi)
+        if local_rows and hx_obs.shape[2] != self.hi - self.lo:
+            raise L.SfError(f"local_rows: expected {self.hi - self.lo} rows, got {hx_obs.shape[2]}")
+        eng.bind_observations(hx_obs[:, :, rows].contiguous())
         eng.zero_state(0)
         eng.ensure_path_slots(ro.n_path)
-        eps = noise[:, :, self.lo:self.hi] if noise is not None else self.draw_noise(ro.n_eps)
+        eps = noise[:, :, rows] if noise is not None else self.draw_noise(ro.n_eps)
+        mark("inputs bound")
         if self.use_graphs:
             # static noise buffer and event table: the captured segments hold their addresses
             if getattr(self, "_eps_static", None) is None or self._eps_static.shape[0] < max(ro.n_eps, 1):
@@ -307,25 +417,29 @@ class RowShardedOde:
             k = min(eps.shape[0], ro.n_eps)          # a caller's tape may hold more slots than this schedule consumes
             self._eps_static[:k].copy_(eps[:k])
             eng.bind_eps(self._eps_static)
-            key = (B, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
-                   tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), ode.solver, bool(ode.impute), eng.precision)
             plan = self.__dict__.setdefault("_tables", {}).get(key)
             if plan is None:
                 table, evs = eng.build_table(ro.events)          # one upload for the whole rollout
                 plan = self._tables[key] = (evs, eng.upload_table(table))
             evs, tdev = plan
+            mark("noise bound")
             self._run_rollout_graphed(evs, tdev, key)
         else:
             eng.bind_eps(eps[: max(ro.n_eps, 1)].contiguous())
             table, evs = eng.build_table(ro.events)          # one upload for the whole rollout
             tdev = eng.upload_table(table)
+            mark("noise bound")
             for ev in evs:
                 self._run_event(ev, tdev)
+        mark("events done")
+        if self.arena is not None:
+            self.arena.poll()
         T = len(targets[0])
-        flat = [s for slots in ro.out_slots for s in slots]
         sel = eng.unpack_path(flat).view(B, T, eng.C, self.hi - self.lo, self.w)
         ro.launches = self.launches
-        return sel[:, :, :, self.own_lo - self.lo:self.own_hi - self.lo].contiguous(), ro
+        band = sel[:, :, :, self.own_lo - self.lo:self.own_hi - self.lo].contiguous()
+        mark("outputs gathered")
+        return band, ro
 
     def gather_rows(self, band: torch.Tensor) -> torch.Tensor:
         """all_gather of the bands along the row axis -> the full [B, T, C, h, w] tensor on every rank."""

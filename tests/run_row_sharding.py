@@ -1,6 +1,6 @@
 """torchrun worker: row-sharded rollout on WORLD_SIZE GPUs vs (a) the fp64 ORACLE evaluated on rank 0's GPU and (b) the
 unsharded engine.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_row_sharding.py [H W B precision C]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_row_sharding.py [H W B precision C graph|eager peer|nccl]
 Prints one JSON line from rank 0 (max relative errors of the gathered latents, timing).  tests/test_gpu_row_sharding.py spawns
 it and asserts the oracle error against the north-star tolerance."""
 import json
@@ -37,7 +37,8 @@ g = torch.Generator().manual_seed(seed)
 hx = torch.tanh(torch.randn(sum(counts), C, H, W, generator=g)).to(dev)
 tape = torch.randn(18 * B, C, H, W, generator=g).to(dev)
 use_graphs = not (len(sys.argv) > 6 and sys.argv[6] == "eager")
-sharded = RowShardedOde(m, H, W, B, use_graphs=use_graphs)
+transport = sys.argv[7] if len(sys.argv) > 7 else None          # "peer" (NVLink peer-memory kernels, the default) | "nccl"
+sharded = RowShardedOde(m, H, W, B, use_graphs=use_graphs, transport=transport)
 with torch.no_grad():
     band, ro = sharded.integrate(hx, counts, times, targets, 0.05, noise=tape)
     torch.cuda.synchronize()
@@ -74,6 +75,6 @@ with torch.no_grad():
                               max_rel_err_vs_oracle=err_oracle, single_gpu_max_rel_err_vs_oracle=err_single_oracle,
                               ms_sharded=1e3 * dt_sharded, ms_single_gpu=1e3 * dt_single, events=len(ro.events),
                               halo_rows=12, band_rows=sharded.own_hi - sharded.own_lo,
-                              launch=sharded.graph_mode, whole_graph_error=sharded.__dict__.get("_whole_graph_error"))), flush=True)
-sharded.release_graphs()          # graphs with NCCL kernels must die before their process group
+                              launch=sharded.graph_mode, transport=sharded.transport, peer_error=sharded.peer_error, whole_graph_error=sharded.__dict__.get("_whole_graph_error"))), flush=True)
+sharded.release_graphs()          # graphs with NCCL kernels must die before their process group; raises if a peer exchange timed out
 dist.destroy_process_group()

@@ -29,14 +29,17 @@ def _run(world, *argv):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row sharding needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("H,W,B,precision,C,launch", [(96, 80, 2, "bf16x3", 64, "graph"), (96, 80, 2, "bf16", 64, "graph"),
                                                       (64, 48, 1, "bf16x3", 128, "graph"), (96, 80, 2, "bf16x3", 64, "eager")])
-def test_row_sharded_rollout_matches_oracle(H, W, B, precision, C, launch):
-    """Two ranks, each a band of rows + 12-row halos, halo exchange + SE all-reduce per event over NCCL, full config-2 schedule
-    (8 jumps + 10 steps): the gathered selected latents vs the fp64 oracle, and vs the unsharded engine."""
-    d = _run(2, H, W, B, precision, C, launch)
+def test_row_sharded_rollout_matches_oracle(H, W, B, precision, C, launch, transport):
+    """Two ranks, each a band of rows + 12-row halos, halo exchange + SE all-reduce per event -- as kernels over NVLink peer
+    memory ("peer": sf_halo_push / sf_halo_pull / sf_peer_allreduce_f32) or as NCCL calls -- full config-2 schedule (8 jumps + 10
+    steps): the gathered selected latents vs the fp64 oracle, and vs the unsharded engine."""
+    d = _run(2, H, W, B, precision, C, launch, transport)
     tol = 1e-2 if precision == "bf16" else 1e-4
     assert d["world"] == 2 and d["events"] == 18
+    assert d["transport"] == transport, d          # no silent fall-back to NCCL when the peer arenas cannot be mapped
     assert d["max_rel_err_vs_oracle"] < tol, d
     assert d["single_gpu_max_rel_err_vs_oracle"] < tol, d
     out = os.path.join(ROOT, "gpurun_out")

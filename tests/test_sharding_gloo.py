@@ -116,7 +116,7 @@ def test_row_sharded_event_program_splits_at_the_nccl_calls():
 
     eng = NS(cell_slots=[[0, 1, 2, 3, 4, 5], [6, 7, 8, 9, 10, 11]], prior_items=[12, 13, L.SE_ITEM_BASE, 14, 15, L.SE_ITEM_BASE + 1, 16])
     ev = NS(kind=1, run_cell=1, run_prior=1)
-    ops = RowShardedOde._event_ops(NS(eng=eng, world=4), ev)
+    ops = RowShardedOde._event_ops(NS(eng=eng, world=4, transport="nccl"), ev)
     kinds = [k for k, _ in ops]
     assert kinds == ["stage"] * 8 + ["se_reduce", "allreduce", "se_apply"] + ["stage"] * 2 + ["se_reduce", "allreduce", "se_apply", "stage",
                                                                                       "pack", "p2p", "unpack"]
@@ -130,5 +130,9 @@ def test_row_sharded_event_program_splits_at_the_nccl_calls():
         else:
             cur.append(k)
     assert len(segments) == 4 and segments[-1] == ["unpack"] and segments[2][-1] == "pack"
-    single = RowShardedOde._event_ops(NS(eng=eng, world=1), NS(kind=0, run_cell=1, run_prior=0))
+    # peer transport: the same event with every exchange a kernel (nothing splits the graph)
+    peer = [k for k, _ in RowShardedOde._event_ops(NS(eng=eng, world=4, transport="peer"), ev)]
+    assert peer == ["stage"] * 8 + ["se_reduce", "peer_allreduce", "se_apply"] + ["stage"] * 2 + ["se_reduce", "peer_allreduce", "se_apply", "stage",
+                                                                                         "push", "pull"]
+    single = RowShardedOde._event_ops(NS(eng=eng, world=1, transport="none"), NS(kind=0, run_cell=1, run_prior=0))
     assert [k for k, _ in single] == ["stage"] * 6          # one rank: no collectives, no halo exchange
