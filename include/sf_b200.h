@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 1
+#define SF_ABI_VERSION 2
 
 typedef enum {
   SF_OK = 0,
@@ -244,13 +244,14 @@ int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long
 int sf_maxpool2(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, int n_images, int H, int W, int C, void* stream);
 int sf_upsample2(const void* src, void* dst, int n_images, int H, int W, int C, void* stream);
 int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void* dst_lo, int n_out, int C, int H, int W, void* stream);
-/* post-ODE refinement glue: ConvNeXt depthwise 7x7 conv + bias + channels-last LayerNorm (convolutions.py:327-333) on 64-channel
-   NHWC bf16 planes; ASPP image-pooling branch folded into a per-image bias of the projection conv (convolutions.py:198-240):
-   out[img][128] = proj_w[128][128] . relu(pool_w[128][64] . mean(img) + pool_b) + proj_b                              */
+/* post-ODE refinement glue on C-channel NHWC bf16 planes, C = 64 or 128 (FuturePredictionODE's in_channels):
+   ConvNeXt depthwise 7x7 conv + bias + channels-last LayerNorm (convolutions.py:327-333); ASPP image-pooling branch folded into a
+   per-image bias of the projection conv (convolutions.py:198-240):
+   out[img][128] = proj_w[128][128] . relu(pool_w[128][C] . mean(img) + pool_b) + proj_b;  scratch: [n_images][32][C] floats */
 int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, const float* dw_w, const float* dw_b,
-                  const float* ln_w, const float* ln_b, int n_images, int H, int W, void* stream);
+                  const float* ln_w, const float* ln_b, int n_images, int C, int H, int W, void* stream);
 int sf_aspp_pool_bias(const void* src_hi, const void* src_lo, const float* pool_w, const float* pool_b, const float* proj_w,
-                      const float* proj_b, float* scratch, float* out, int n_images, int H, int W, void* stream);
+                      const float* proj_b, float* scratch, float* out, int n_images, int C, int H, int W, void* stream);
 
 /* self-test kernels for bring-up: TMA tile dump and a single UMMA tile product */
 int sf_diag_tma_dump(const void* act_bf16, int n_images, int H, int W, int C, int img, int y0, int x0, int c0,

@@ -61,7 +61,7 @@ with torch.no_grad():
     o0, dw = P.bufs[rf.R_O0], P.bufs[rf.R_DW]
     ptr = lambda t: t.data_ptr() if t is not None else None
     parts["block.dwconv7+LN"] = timed(lambda: L.check(lib.sf_dwconv7_ln(ptr(o0[0]), ptr(o0[1]), ptr(dw[0]), ptr(dw[1]), blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(),
-                                                                      blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), n, H, H, stream()), "dw"))
+                                                                      blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), n, 64, H, H, stream()), "dw"))
     parts["block.pw1+pw2"] = timed(lambda: P.run(refine.slots["block"], n))
     parts["spatial_gru1"] = timed(lambda: refine._run_gru(1, pl))
     names = [s.name for s in refine.g["deeplab"]]

@@ -32,9 +32,11 @@ def _bn_fold_w(w: torch.Tensor, sd, norm: str):
 class LevelPlan:
     """One sf_plan at a fixed resolution with its own NHWC activation buffers and conv stages."""
 
-    def __init__(self, lib, H, W, max_images, x3, device):
+    def __init__(self, lib, H, W, max_images, x3, device, C_hidden: int = 64):
+        """C_hidden: the hidden width the gates / propose epilogues are instantiated for (64 or 128); the bias_act / residual
+        epilogues are width-generic (<= 128 output channels per launch)."""
         self.lib, self.H, self.W, self.n, self.x3, self.device = lib, H, W, max_images, x3, device
-        geo = L.Geometry(max_images, H, W, 64, L.PREC_BF16X3 if x3 else L.PREC_BF16, device.index)
+        geo = L.Geometry(max_images, H, W, C_hidden, L.PREC_BF16X3 if x3 else L.PREC_BF16, device.index)
         h = C.c_void_p()
         with torch.cuda.device(device):
             L.check(lib.sf_plan_create(C.byref(geo), C.byref(h)), "sf_plan_create")
@@ -106,65 +108,81 @@ def _act_flags(act: int, out32: bool = False) -> int:
     return (act << 1) | (L.FLAG_OUT32 if out32 else 0)
 
 
-def _conv_bn_act(name, sd, p, src, dst, act=L.ACT_LRELU, halves=1, w=None):
-    """ConvBlock (conv3x3 + BN + activation) as 1 or 2 launches of 128 (or fewer) output channels."""
+def _conv_bn_act(name, sd, p, src, dst, act=L.ACT_LRELU, w=None):
+    """ConvBlock (conv3x3 + BN + activation) as launches of 128 (or fewer) output channels."""
     if w is None:
         w = sd[p + ".conv.weight"].float()
     w, b = _bn_fold_w(w, sd, p + ".norm")
-    n = w.shape[0] // halves
+    n = min(w.shape[0], 128)
     out = []
-    for h in range(halves):
+    for h in range(w.shape[0] // n):
         r = slice(n * h, n * h + n)
-        out.append(StageDef(f"{name}{'ab'[h] if halves > 1 else ''}", L.EPI_BIAS_LRELU, b[r], [dst], [n * h], flags=_act_flags(act)).add(src, w[r], 0, 1))
+        out.append(StageDef(f"{name}{'abcd'[h] if w.shape[0] > n else ''}", L.EPI_BIAS_LRELU, b[r], [dst], [n * h], flags=_act_flags(act)).add(src, w[r], 0, 1))
     return out
 
 
 def _res_block(name, sd, p, src, tmp, dst, cin, cout):
-    """ResBlock(cin -> cout): conv_1 (cin -> cin), conv_2 (cin -> cout), identity or 1x1-projected skip (res_models.py:52-79)."""
-    stages = _conv_bn_act(name + ".c1", sd, p + ".layers.conv_1", src, tmp, halves=max(1, cin // 128))
+    """ResBlock(cin -> cout): conv_1 (cin -> cin), conv_2 (cin -> cout), identity or 1x1-projected skip (res_models.py:52-79);
+    every launch owns <= 128 output channels."""
+    stages = _conv_bn_act(name + ".c1", sd, p + ".layers.conv_1", src, tmp)
     w2, b2 = _bn_fold_w(sd[p + ".layers.conv_2.conv.weight"].float(), sd, p + ".layers.conv_2.norm")
-    if cin == cout:
-        assert cout <= 128
-        stages.append(StageDef(name + ".c2", L.EPI_RES_ID, b2, [src, dst]).add(tmp, w2, 0, 1))
-    else:
-        wp, bp = sd[p + ".projection.weight"].float(), sd[p + ".projection.bias"].float()
-        n = min(cout, 128)
-        for h in range(cout // n):
-            r = slice(n * h, n * h + n)
-            stages.append(StageDef(f"{name}.c2{'ab'[h] if cout > n else ''}", L.EPI_RES_PROJ, torch.cat([b2[r], bp[r]]), [dst], [n * h])
+    n = min(cout, 128)
+    for h in range(cout // n):
+        r, tag = slice(n * h, n * h + n), ('abcd'[h] if cout > n else '')
+        if cin == cout:
+            stages.append(StageDef(f"{name}.c2{tag}", L.EPI_RES_ID, b2[r], [src, dst], [n * h, n * h]).add(tmp, w2[r], 0, 1))
+        else:
+            wp, bp = sd[p + ".projection.weight"].float(), sd[p + ".projection.bias"].float()
+            stages.append(StageDef(f"{name}.c2{tag}", L.EPI_RES_PROJ, torch.cat([b2[r], bp[r]]), [dst], [n * h])
                           .add(tmp, w2[r], 0, 1).add(src, wp[r], n, 1))
     return stages
 
 
-ENC_BUFS = {"A": {0: 64, 1: 64, 2: 64}, "B": {0: 64, 1: 64, 2: 128}, "C": {0: 128, 1: 128, 2: 128, 3: 128, 4: 256, 5: 64}}
-DEC_BUFS = {"C": {0: 64, 1: 256, 2: 256, 3: 128, 4: 128, 5: 128, 6: 128}, "B": {0: 128, 1: 128, 2: 64}, "A": {0: 64, 1: 64, 2: 64, 3: 64, 4: 64}}
+def codec_widths(sd, e="srvp_encoder."):
+    """(nc, nf): input = latent width (MODEL.ENCODER.OUT_CHANNELS) and filter size (MODEL.SMALL_ENCODER.FILTER_SIZE)."""
+    return sd[e + "blocks.0.layers.conv_1.conv.weight"].shape[0], sd[e + "blocks.0.layers.conv_2.conv.weight"].shape[0]
+
+
+def enc_bufs(nc: int, nf: int = 64):
+    """Channel counts of the encoder's activation buffers per level (A: H, B: H/2, C: H/4)."""
+    return {"A": {0: nc, 1: nc, 2: nf}, "B": {0: nf, 1: nf, 2: 2 * nf}, "C": {0: 2 * nf, 1: 2 * nf, 2: 2 * nf, 3: 2 * nf, 4: 4 * nf, 5: nc}}
+
+
+def dec_bufs(nc: int, nf: int = 64):
+    return {"C": {0: nc, 1: 4 * nf, 2: 4 * nf, 3: 2 * nf, 4: 2 * nf, 5: 2 * nf, 6: 2 * nf}, "B": {0: 2 * nf, 1: 2 * nf, 2: nf},
+            "A": {0: nf, 1: nf, 2: nf, 3: nf, 4: nc}}
+
+
+ENC_BUFS, DEC_BUFS = enc_bufs(64), dec_bufs(64)
 ENC_IN, ENC_OUT = ("A", 0), ("C", 5)
 DEC_IN, DEC_OUT = ("C", 0), ("A", 4)
 
 
 def encoder_graph(sd, e="srvp_encoder."):
     """SmallEncoder.forward (res_models.py:96-109) as a list of ops over three resolution levels A (H), B (H/2), C (H/4):
-    ("stage", level, StageDef) | ("pool", (level, buf), (level, buf), channels)."""
-    g = [("stage", "A", s) for s in _res_block("enc0", sd, e + "blocks.0", 0, 1, 2, 64, 64)]
-    g.append(("pool", ("A", 2), ("B", 0), 64))
-    g += [("stage", "B", s) for s in _res_block("enc1", sd, e + "blocks.1", 0, 1, 2, 64, 128)]
-    g.append(("pool", ("B", 2), ("C", 0), 128))
-    st = _res_block("enc2", sd, e + "blocks.2", 0, 1, 2, 128, 128) + _res_block("enc3", sd, e + "blocks.3", 2, 1, 3, 128, 128)
-    st += _res_block("enc4", sd, e + "blocks.4", 3, 1, 4, 128, 256)
+    ("stage", level, StageDef) | ("pool", (level, buf), (level, buf), channels).  SmallEncoder(nc, nh = nc, nf)."""
+    nc, nf = codec_widths(sd, e)
+    g = [("stage", "A", s) for s in _res_block("enc0", sd, e + "blocks.0", 0, 1, 2, nc, nf)]
+    g.append(("pool", ("A", 2), ("B", 0), nf))
+    g += [("stage", "B", s) for s in _res_block("enc1", sd, e + "blocks.1", 0, 1, 2, nf, 2 * nf)]
+    g.append(("pool", ("B", 2), ("C", 0), 2 * nf))
+    st = _res_block("enc2", sd, e + "blocks.2", 0, 1, 2, 2 * nf, 2 * nf) + _res_block("enc3", sd, e + "blocks.3", 2, 1, 3, 2 * nf, 2 * nf)
+    st += _res_block("enc4", sd, e + "blocks.4", 3, 1, 4, 2 * nf, 4 * nf)
     st += _conv_bn_act("enc_last", sd, e + "last_conv.0", 4, 5, act=L.ACT_TANH)
     return g + [("stage", "C", s) for s in st]
 
 
 def decoder_graph(sd, d="srvp_decoder."):
     """SmallDecoder.forward (res_models.py:134-147, skip=None): ("stage", ...) | ("up", (level, buf), (level, buf), channels)."""
-    st = _conv_bn_act("dec_first", sd, d + "first_upconv", 0, 1, halves=2, w=_convT_as_conv(sd[d + "first_upconv.conv.weight"].float()))
-    st += _res_block("dec0", sd, d + "blocks.0", 1, 2, 3, 256, 128)
-    st += _res_block("dec1", sd, d + "blocks.1", 3, 4, 5, 128, 128) + _res_block("dec2", sd, d + "blocks.2", 5, 4, 6, 128, 128)
+    nf = sd[d + "blocks.4.layers.conv_2.conv.weight"].shape[0]
+    st = _conv_bn_act("dec_first", sd, d + "first_upconv", 0, 1, w=_convT_as_conv(sd[d + "first_upconv.conv.weight"].float()))
+    st += _res_block("dec0", sd, d + "blocks.0", 1, 2, 3, 4 * nf, 2 * nf)
+    st += _res_block("dec1", sd, d + "blocks.1", 3, 4, 5, 2 * nf, 2 * nf) + _res_block("dec2", sd, d + "blocks.2", 5, 4, 6, 2 * nf, 2 * nf)
     g = [("stage", "C", s) for s in st]
-    g.append(("up", ("C", 6), ("B", 0), 128))
-    g += [("stage", "B", s) for s in _res_block("dec3", sd, d + "blocks.3", 0, 1, 2, 128, 64)]
-    g.append(("up", ("B", 2), ("A", 0), 64))
-    st = _res_block("dec4", sd, d + "blocks.4", 0, 1, 2, 64, 64) + _conv_bn_act("dec_last0", sd, d + "last_conv.0", 2, 3)
+    g.append(("up", ("C", 6), ("B", 0), 2 * nf))
+    g += [("stage", "B", s) for s in _res_block("dec3", sd, d + "blocks.3", 0, 1, 2, 2 * nf, nf)]
+    g.append(("up", ("B", 2), ("A", 0), nf))
+    st = _res_block("dec4", sd, d + "blocks.4", 0, 1, 2, nf, nf) + _conv_bn_act("dec_last0", sd, d + "last_conv.0", 2, 3)
     wl = _convT_as_conv(sd[d + "last_conv.1.conv.weight"].float())
     st.append(StageDef("dec_last1", L.EPI_BIAS_LRELU, sd[d + "last_conv.1.conv.bias"].float(), [4], flags=_act_flags(L.ACT_LRELU, out32=True))
               .add(3, wl, 0, 1))
@@ -172,7 +190,10 @@ def decoder_graph(sd, d="srvp_decoder."):
 
 
 class CodecEngine:
-    """SmallEncoder + SmallDecoder of one NNFOwithBayesianJumps (nc = nh = nf = 64, SKIPCO False) for a fixed BEV size."""
+    """SmallEncoder + SmallDecoder of one NNFOwithBayesianJumps for a fixed BEV size: input = latent width nc = nh =
+    MODEL.ENCODER.OUT_CHANNELS = 64 or 128 (BASELINE config 5), filter size nf = 64 (the reference's default, config.py:115) or 128.
+    SKIPCO = True cannot run in the reference either (SmallDecoder.forward asserts on skip=None, which is what
+    temporal_ode_bayes.py:624 passes; with skips its last_conv would see nf instead of 2 nf channels), so there is nothing to mirror."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], H: int, W: int, n_enc: int, n_dec: int, precision: str, device):
         if H % 4 or W % 4:
@@ -187,14 +208,18 @@ class CodecEngine:
         self.x3 = precision == "bf16x3"
         self.n_enc, self.n_dec = n_enc, n_dec
         sd = {k: v.detach().to(device) for k, v in sd.items() if k.startswith(("srvp_encoder", "srvp_decoder"))}
-        if sd["srvp_encoder.blocks.0.layers.conv_1.conv.weight"].shape[0] != 64 or sd["srvp_encoder.last_conv.0.conv.weight"].shape[0] != 64:
-            raise L.SfError("fused encoder / decoder is built for 64 channels (nc = nh = nf = 64)")
+        nc, nf = codec_widths(sd)
+        self.nc, self.nf = nc, nf
+        if (nc not in (64, 128) or nf not in (64, 128) or sd["srvp_encoder.last_conv.0.conv.weight"].shape[0] != nc
+                or sd["srvp_decoder.first_upconv.conv.weight"].shape[0] != nc
+                or sd["srvp_decoder.blocks.0.layers.conv_1.conv.weight"].shape[0] != 4 * nf):
+            raise L.SfError("fused encoder / decoder is built for nc = nh in (64, 128), nf in (64, 128), SKIPCO off")
         self.launches = 0
         dims = {"A": (H, W), "B": (H // 2, W // 2), "C": (H // 4, W // 4)}
         self.dims = dims
-        self.enc, self.enc_ops = self._build(encoder_graph(sd), ENC_BUFS, n_enc, dims, self.enc_x3)
-        self.dec, self.dec_ops = self._build(decoder_graph(sd), DEC_BUFS, n_dec, dims, self.x3)
-        self.dec_out32 = torch.empty((n_dec, H, W, 64), dtype=torch.float32, device=device)
+        self.enc, self.enc_ops = self._build(encoder_graph(sd), enc_bufs(nc, nf), n_enc, dims, self.enc_x3)
+        self.dec, self.dec_ops = self._build(decoder_graph(sd), dec_bufs(nc, nf), n_dec, dims, self.x3)
+        self.dec_out32 = torch.empty((n_dec, H, W, nc), dtype=torch.float32, device=device)
         self.dec["A"].bind_out32(self.dec_out32)
 
     def _build(self, graph, bufs, n, dims, x3):
@@ -241,13 +266,13 @@ class CodecEngine:
         return k
 
     def encode(self, frames_nchw: torch.Tensor):
-        """frames [n, 64, H, W] fp32 NCHW -> encoded latents as NHWC bf16 planes (hi, lo) [n, h, w, 64] (views of the engine's
+        """frames [n, nc, H, W] fp32 NCHW -> encoded latents as NHWC bf16 planes (hi, lo) [n, h, w, nc] (views of the engine's
         output buffer: valid until the next encode)."""
         n = frames_nchw.shape[0]
-        assert n <= self.n_enc and tuple(frames_nchw.shape[1:]) == (64, self.H, self.W)
+        assert n <= self.n_enc and tuple(frames_nchw.shape[1:]) == (self.nc, self.H, self.W)
         src = frames_nchw.contiguous().float()
         a_in = self.enc[ENC_IN[0]].bufs[ENC_IN[1]]
-        L.check(self.lib.sf_pack_nchw_f32(src.data_ptr(), a_in[0].data_ptr(), a_in[1].data_ptr() if a_in[1] is not None else None, n, 64,
+        L.check(self.lib.sf_pack_nchw_f32(src.data_ptr(), a_in[0].data_ptr(), a_in[1].data_ptr() if a_in[1] is not None else None, n, self.nc,
                                           self.H, self.W, self._stream()), "pack")
         self.launches += 1 + self._run(self.enc, self.enc_ops, n)
         hi, lo = self.enc[ENC_OUT[0]].bufs[ENC_OUT[1]]
@@ -255,19 +280,19 @@ class CodecEngine:
 
     def decode(self, path_nhwc_f32: torch.Tensor, slots_dev: torch.Tensor, unpack: bool = True):
         """Recorded latent states (the ODE engine's fp32 NHWC path buffer), gathered by slot -> decoded frames
-        [n, 64, H, W] fp32 NCHW; with unpack=False the engine-layout result instead: ((hi, lo) NHWC bf16 planes, fp32 NHWC),
+        [n, nc, H, W] fp32 NCHW; with unpack=False the engine-layout result instead: ((hi, lo) NHWC bf16 planes, fp32 NHWC),
         views of the decoder's output buffers for the fused refinement."""
         n = slots_dev.numel()
         assert n <= self.n_dec
         z = self.dec[DEC_IN[0]].bufs[DEC_IN[1]]
         L.check(self.lib.sf_cast_nhwc_f32(path_nhwc_f32.data_ptr(), slots_dev.data_ptr(), z[0].data_ptr(), z[1].data_ptr() if z[1] is not None else None,
-                                          n, 64, self.h, self.w, self._stream()), "cast")
+                                          n, self.nc, self.h, self.w, self._stream()), "cast")
         k = self._run(self.dec, self.dec_ops, n)
         if not unpack:
             self.launches += k + 1
             hi, lo = self.dec[DEC_OUT[0]].bufs[DEC_OUT[1]]
             return (hi[:n], lo[:n] if lo is not None else None), self.dec_out32[:n]
-        out = torch.empty((n, 64, self.H, self.W), dtype=torch.float32, device=self.device)
-        L.check(self.lib.sf_unpack_nhwc_f32(self.dec_out32.data_ptr(), out.data_ptr(), None, n, 64, self.H, self.W, self._stream()), "unpack")
+        out = torch.empty((n, self.nc, self.H, self.W), dtype=torch.float32, device=self.device)
+        L.check(self.lib.sf_unpack_nhwc_f32(self.dec_out32.data_ptr(), out.data_ptr(), None, n, self.nc, self.H, self.W, self._stream()), "unpack")
         self.launches += k + 2
         return out

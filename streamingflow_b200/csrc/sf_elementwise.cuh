@@ -523,16 +523,86 @@ __global__ void __launch_bounds__(256, 1) dwconv7_ln_kernel(const __nv_bfloat16*
   }
 }
 
+// The same operator at any width CH (a multiple of 32; used for CH = 128, BASELINE config 5 at the module level): one warp per output
+// pixel, lane = CH / 32 consecutive channels, the 49 taps read through L1 (a tap of a warp is CH * 2 contiguous bytes), the filter
+// transposed in shared memory, LayerNorm by warp shuffles.  No halo tile: it would not fit shared memory at 128 channels.
+template <int CH, bool X3>
+__global__ void __launch_bounds__(256) dwconv7_ln_wide_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
+                                                              __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl,
+                                                              const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w, const float* __restrict__ ln_b, int H, int W,
+                                                              long long total) {
+  static_assert(CH % 64 == 0 && CH <= 256, "2 or 4 ... channels per lane, loaded as 32-bit pairs");
+  constexpr int PER = CH / 32;
+  __shared__ float wsm[49 * CH];                  // [tap][channel]
+  __shared__ float vsm[3 * CH];                   // conv bias | LN weight | LN bias
+  for (int i = threadIdx.x; i < 49 * CH; i += 256) { const int c = i / 49, t = i % 49; wsm[t * CH + c] = dw_w[c * 49 + t]; }
+  for (int i = threadIdx.x; i < CH; i += 256) { vsm[i] = dw_b[i]; vsm[CH + i] = ln_w[i]; vsm[2 * CH + i] = ln_b[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c0 = lane * PER;
+  const long long hw = (long long)H * W;
+  for (long long p = (long long)blockIdx.x * 8 + warp; p < total; p += (long long)gridDim.x * 8) {
+    const long long img = p / hw;
+    const int rem = (int)(p - img * hw), y = rem / W, x = rem - y * W;
+    float acc[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) acc[j] = vsm[c0 + j];
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xx = x + kx - 3;
+        if (xx < 0 || xx >= W) continue;
+        const size_t off = ((size_t)(img * H + yy) * W + xx) * CH + c0;
+        const float* wt = wsm + (ky * 7 + kx) * CH + c0;
+#pragma unroll
+        for (int j = 0; j < PER; j += 2) {
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(sh + off + j));
+          float f0 = bf16_lo_f(v), f1 = bf16_hi_f(v);
+          if (X3) {
+            const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(sl + off + j));
+            f0 += bf16_lo_f(u); f1 += bf16_hi_f(u);
+          }
+          acc[j] = fmaf(wt[j], f0, acc[j]);
+          acc[j + 1] = fmaf(wt[j + 1], f1, acc[j + 1]);
+        }
+      }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) s += acc[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    const float mean = s * (1.0f / CH);
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { const float dlt = acc[j] - mean; q = fmaf(dlt, dlt, q); }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+    const float rstd = rsqrtf(q * (1.0f / CH) + 1e-6f);
+    const size_t o = (size_t)p * CH + c0;
+#pragma unroll
+    for (int j = 0; j < PER; j += 2) {
+      const float o0 = fmaf(vsm[CH + c0 + j], (acc[j] - mean) * rstd, vsm[2 * CH + c0 + j]);
+      const float o1 = fmaf(vsm[CH + c0 + j + 1], (acc[j + 1] - mean) * rstd, vsm[2 * CH + c0 + j + 1]);
+      const uint32_t h = pack_bf16x2(o0, o1);
+      *reinterpret_cast<uint32_t*>(dh + o + j) = h;
+      if (X3) *reinterpret_cast<uint32_t*>(dl + o + j) = pack_bf16x2(o0 - bf16_lo_f(h), o1 - bf16_hi_f(h));
+    }
+  }
+}
+
 // ---- ASPP image pooling: per-image channel means of a 64-channel NHWC tensor (two deterministic levels), then
 // bias[img] = proj_w . relu(pool_w . mean + pool_b) + proj_b  (BatchNorms folded on the host) -------------------------------
 constexpr int POOL_PARTS = 32;
-template <bool X3>
+template <int CH, bool X3>
 __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* __restrict__ sh, const __nv_bfloat16* __restrict__ sl,
-                                                           float* __restrict__ partial, int hw) {   // partial [img][POOL_PARTS][64]
-  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3, img = blockIdx.y;
+                                                           float* __restrict__ partial, int hw) {   // partial [img][POOL_PARTS][CH]
+  constexpr int GROUPS = CH / 8, LANES = 256 / GROUPS;          // 8 channels per thread, LANES pixels per block iteration
+  const int g = threadIdx.x % GROUPS, pl = threadIdx.x / GROUPS, img = blockIdx.y;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int px = blockIdx.x * 32 + pl; px < hw; px += POOL_PARTS * 32) {
-    const size_t off = ((size_t)img * hw + px) * 64 + g * 8;
+  for (int px = blockIdx.x * LANES + pl; px < hw; px += POOL_PARTS * LANES) {
+    const size_t off = ((size_t)img * hw + px) * CH + g * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(sh + off);
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -544,30 +614,31 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* 
       for (int i = 0; i < 4; ++i) { acc[2 * i] += bf16_lo_f(x4[i]); acc[2 * i + 1] += bf16_hi_f(x4[i]); }
     }
   }
-  __shared__ float red[32][65];
+  __shared__ float red[LANES][CH + 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[pl][g * 8 + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < CH) {
     float t = 0.0f;
 #pragma unroll
-    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
-    partial[((size_t)img * POOL_PARTS + blockIdx.x) * 64 + threadIdx.x] = t;
+    for (int l = 0; l < LANES; ++l) t += red[l][threadIdx.x];
+    partial[((size_t)img * POOL_PARTS + blockIdx.x) * CH + threadIdx.x] = t;
   }
 }
+template <int CH>
 __global__ void __launch_bounds__(128) pool_bias_kernel(const float* __restrict__ partial, float inv_n, const float* __restrict__ pool_w,
                                                         const float* __restrict__ pool_b, const float* __restrict__ proj_w,
                                                         const float* __restrict__ proj_b, float* __restrict__ out) {
-  __shared__ float mean_s[64], v_s[128];
+  __shared__ float mean_s[CH], v_s[128];
   const int img = blockIdx.x, t = threadIdx.x;
-  if (t < 64) {
+  for (int c = t; c < CH; c += 128) {
     float a = 0.0f;
-    for (int k = 0; k < POOL_PARTS; ++k) a += partial[((size_t)img * POOL_PARTS + k) * 64 + t];
-    mean_s[t] = a * inv_n;
+    for (int k = 0; k < POOL_PARTS; ++k) a += partial[((size_t)img * POOL_PARTS + k) * CH + c];
+    mean_s[c] = a * inv_n;
   }
   __syncthreads();
   float a = pool_b[t];
-  for (int c = 0; c < 64; ++c) a = fmaf(pool_w[t * 64 + c], mean_s[c], a);
+  for (int c = 0; c < CH; ++c) a = fmaf(pool_w[t * CH + c], mean_s[c], a);
   v_s[t] = fmaxf(a, 0.0f);
   __syncthreads();
   float b = proj_b[t];

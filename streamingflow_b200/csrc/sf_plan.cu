@@ -968,12 +968,21 @@ int sf_cast_nhwc_f32(const float* src, const int32_t* slots, void* dst_hi, void*
 }
 
 int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* dst_lo, const float* dw_w, const float* dw_b,
-                  const float* ln_w, const float* ln_b, int n_images, int H, int W, void* stream) {
+                  const float* ln_w, const float* ln_b, int n_images, int C, int H, int W, void* stream) {
   if (!src_hi || !dst_hi || !dw_w || !dw_b || !ln_w || !ln_b || n_images <= 0) return fail(SF_ERR_INVALID, "bad dwconv arguments");
-  dim3 grid((W + DW_TILE_W - 1) / DW_TILE_W, (H + DW_TILE_H - 1) / DW_TILE_H, n_images);
+  if (C != 64 && C != 128) return fail(SF_ERR_INVALID, "depthwise 7x7 + LayerNorm is built for 64 or 128 channels");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
   auto dh = reinterpret_cast<__nv_bfloat16*>(dst_hi); auto dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
+  if (C == 128) {       // generic-width kernel: one warp per pixel
+    const long long total = (long long)n_images * H * W;
+    const int grid = (int)std::min<long long>((total + 7) / 8, 148 * 32);
+    if (src_lo && dst_lo) dwconv7_ln_wide_kernel<128, true><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W, total);
+    else dwconv7_ln_wide_kernel<128, false><<<grid, 256, 0, s>>>(sh, sl, dh, dl, dw_w, dw_b, ln_w, ln_b, H, W, total);
+    SF_CUDA(cudaGetLastError());
+    return SF_OK;
+  }
+  dim3 grid((W + DW_TILE_W - 1) / DW_TILE_W, (H + DW_TILE_H - 1) / DW_TILE_H, n_images);
   // 146 KB of dynamic shared memory (fp32 halo tile + filter): opt in per call (a per-device attribute; the call is cheap)
   SF_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(src_lo && dst_lo ? dwconv7_ln_kernel<true> : dwconv7_ln_kernel<false>),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
@@ -984,14 +993,22 @@ int sf_dwconv7_ln(const void* src_hi, const void* src_lo, void* dst_hi, void* ds
 }
 
 int sf_aspp_pool_bias(const void* src_hi, const void* src_lo, const float* pool_w, const float* pool_b, const float* proj_w,
-                      const float* proj_b, float* scratch, float* out, int n_images, int H, int W, void* stream) {
+                      const float* proj_b, float* scratch, float* out, int n_images, int C, int H, int W, void* stream) {
   if (!src_hi || !pool_w || !pool_b || !proj_w || !proj_b || !scratch || !out || n_images <= 0) return fail(SF_ERR_INVALID, "bad pool arguments");
+  if (C != 64 && C != 128) return fail(SF_ERR_INVALID, "ASPP pooling is built for 64 or 128 input channels");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   auto sh = reinterpret_cast<const __nv_bfloat16*>(src_hi); auto sl = reinterpret_cast<const __nv_bfloat16*>(src_lo);
   dim3 grid(POOL_PARTS, n_images);
-  if (src_lo) pool_partial_kernel<true><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
-  else pool_partial_kernel<false><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
-  pool_bias_kernel<<<n_images, 128, 0, s>>>(scratch, 1.0f / (float)(H * W), pool_w, pool_b, proj_w, proj_b, out);
+  const float inv_n = 1.0f / (float)(H * W);
+  if (C == 64) {
+    if (src_lo) pool_partial_kernel<64, true><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+    else pool_partial_kernel<64, false><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+    pool_bias_kernel<64><<<n_images, 128, 0, s>>>(scratch, inv_n, pool_w, pool_b, proj_w, proj_b, out);
+  } else {
+    if (src_lo) pool_partial_kernel<128, true><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+    else pool_partial_kernel<128, false><<<grid, 256, 0, s>>>(sh, sl, scratch, H * W);
+    pool_bias_kernel<128><<<n_images, 128, 0, s>>>(scratch, inv_n, pool_w, pool_b, proj_w, proj_b, out);
+  }
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

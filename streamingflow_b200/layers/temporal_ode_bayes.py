@@ -427,11 +427,12 @@ class NNFOwithBayesianJumps(nn.Module):
 
     # ------------------------------------------------------------------ the rollout
     def codec_available(self, H, W, device) -> bool:
-        """The fused encoder / decoder covers the shipped configuration: 64 channels everywhere, no skip connections."""
+        """The fused encoder / decoder covers filter sizes 64 / 128 with 64 or 128 (BASELINE config 5) input = latent channels; skip
+        connections are off (the reference's SKIPCO = True path asserts in SmallDecoder.forward, res_models.py:135)."""
         return (self.fused_codec and device.type == "cuda" and not self.training and not self.skipco and self._engine_factory is None
-                and self.hidden_size == 64 and self.input_size == 64 and H % 4 == 0 and W % 4 == 0
-                and self.srvp_encoder.blocks[0].layers.conv_1.conv.weight.shape[0] == 64
-                and self.srvp_encoder.blocks[0].layers.conv_2.conv.weight.shape[0] == 64)
+                and self.hidden_size == self.input_size and self.hidden_size in (64, 128) and H % 4 == 0 and W % 4 == 0
+                and self.srvp_encoder.blocks[0].layers.conv_1.conv.weight.shape[0] == self.hidden_size
+                and self.srvp_encoder.blocks[0].layers.conv_2.conv.weight.shape[0] in (64, 128))
 
     def _codec_for(self, H, W, n_enc, n_dec, device):
         from ..codec_engine import CodecEngine

@@ -92,7 +92,7 @@ class FuturePredictionODE(nn.Module):
         stacked = torch.stack(frames, dim=0)
         H, W = stacked.shape[2], stacked.shape[3]
         fused = ode.codec_available(H, W, stacked.device)
-        if fused and self.fused_refine and self.n_spatial_gru == 2 and self.n_res_layers == 1 and self.in_channels == 64:
+        if fused and self.fused_refine and self.n_spatial_gru == 2 and self.n_res_layers == 1 and self.in_channels in (64, 128):
             # encoder -> ODE loop -> decoder -> SpatialGRU / Block / SpatialGRU / DeepLabHead, all on the CUDA engine
             T = len(tgt_t[0])
             _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True, stamp_dtypes=dtypes)

@@ -1,7 +1,7 @@
 """Post-ODE refinement on the conv-stage kernels ("next" row 2 of SURVEY.md 8f): the two SpatialGRUs, the ConvNeXt Block
 and the DeepLabHead that FuturePredictionODE.forward applies to the decoded frames (future_prediction_ode.py:56-62).
 
-  SpatialGRU (layers/temporal.py:26-57)  T sequential ConvGRU cells on [B, 64, H, W]: per step the `gates` stage (one u|r pair,
+  SpatialGRU (layers/temporal.py:26-57)  T sequential ConvGRU cells on [B, C, H, W]: per step the `gates` stage (one u|r pair,
         flag SINGLE) and the `propose` stage of the ODE cell's kernels (the new state overwrites the fp32 / bf16 state in
         place), then the 1x1 `conv_decoder` as a bias_act stage whose A operand is the state and whose output image is
         frame (b, t).  The per-sample image indirection of the event table (sample id vs x image) does the (b, t) addressing.
@@ -26,9 +26,16 @@ from .codec_engine import LevelPlan, _act_flags
 from .engine import StageDef
 
 (R_X, R_S, R_U, R_G, R_O0, R_DW, R_P1, R_BK, R_O1, R_A0, R_A1, R_A2, R_A3, R_PR, R_H, R_OUT) = range(16)
-FRAME_BUFS = {R_X: 64, R_O0: 64, R_DW: 64, R_P1: 256, R_BK: 64, R_O1: 64, R_A0: 128, R_A1: 128, R_A2: 128, R_A3: 128, R_PR: 128,
-              R_H: 128, R_OUT: 64}
-STATE_BUFS = {R_S: 64, R_U: 64, R_G: 64}
+def frame_bufs(Cc: int):
+    """Channel counts of the per-frame buffers; Cc = FuturePredictionODE's in_channels (64, or 128 for BASELINE config 5)."""
+    return {R_X: Cc, R_O0: Cc, R_DW: Cc, R_P1: 4 * Cc, R_BK: Cc, R_O1: Cc, R_A0: 128, R_A1: 128, R_A2: 128, R_A3: 128, R_PR: 128, R_H: 128, R_OUT: Cc}
+
+
+def state_bufs(Cc: int):
+    return {R_S: Cc, R_U: Cc, R_G: Cc}
+
+
+FRAME_BUFS, STATE_BUFS = frame_bufs(64), state_bufs(64)
 ASPP_RATES = (12, 24, 36)
 
 
@@ -41,26 +48,27 @@ def refine_graph(sd: Dict[str, torch.Tensor]):
     """Stage definitions and kernel parameters of the refinement, from FuturePredictionODE's state_dict (keys spatial_grus.*,
     res_blocks.*).  Returns a dict consumed by RefineEngine and by the CPU interpreter in tests/."""
     g = {}
+    Cc = g["C"] = sd["spatial_grus.0.conv_update.weight"].shape[0]          # SpatialGRU(in_channels, in_channels): weights [Cc, 2 Cc, 3, 3]
     for i, (src, dst) in enumerate(((R_X, R_O0), (R_BK, R_O1))):
         p = f"spatial_grus.{i}."
         wu, wr, wt = (sd[p + k + ".weight"].float() for k in ("conv_update", "conv_reset", "conv_state_tilde"))
         gates = StageDef(f"gru{i}.gates", L.EPI_GATES, torch.cat([sd[p + "conv_update.bias"].float(), sd[p + "conv_reset.bias"].float()]),
                          [R_U, R_G], flags=L.FLAG_SINGLE)
-        gates.add(R_S, torch.cat([wu[:, 64:], wr[:, 64:]], 0), 0, 1).add(L.SRC_X, torch.cat([wu[:, :64], wr[:, :64]], 0), 0, 0)
+        gates.add(R_S, torch.cat([wu[:, Cc:], wr[:, Cc:]], 0), 0, 1).add(L.SRC_X, torch.cat([wu[:, :Cc], wr[:, :Cc]], 0), 0, 0)
         prop = StageDef(f"gru{i}.propose", L.EPI_PROPOSE, sd[p + "conv_state_tilde.bias"].float(), [R_U, R_S], flags=L.FLAG_SINGLE | L.FLAG_KEEP_A32)
-        prop.add(L.SRC_X, wt[:, :64], 0, 1).add(R_G, wt[:, 64:], 0, 0)
-        dec = StageDef(f"gru{i}.dec", L.EPI_BIAS_LRELU, torch.zeros(64, device=wu.device), [dst], flags=_act_flags(L.ACT_NONE))
+        prop.add(L.SRC_X, wt[:, :Cc], 0, 1).add(R_G, wt[:, Cc:], 0, 0)
+        dec = StageDef(f"gru{i}.dec", L.EPI_BIAS_LRELU, torch.zeros(Cc, device=wu.device), [dst], flags=_act_flags(L.ACT_NONE))
         dec.add(L.SRC_X, sd[p + "conv_decoder.weight"].float(), 0, 1)
         g[f"gru{i}"] = dict(src=src, dst=dst, gates=gates, propose=prop, dec=dec)
     b = "res_blocks.0.0."
-    w1, b1 = sd[b + "pwconv1.weight"].float(), sd[b + "pwconv1.bias"].float()          # Linear [256, 64]
-    w2, b2 = sd[b + "pwconv2.weight"].float(), sd[b + "pwconv2.bias"].float()          # Linear [64, 256]
+    w1, b1 = sd[b + "pwconv1.weight"].float(), sd[b + "pwconv1.bias"].float()          # Linear [4 Cc, Cc]
+    w2, b2 = sd[b + "pwconv2.weight"].float(), sd[b + "pwconv2.bias"].float()          # Linear [Cc, 4 Cc]
     gamma = sd[b + "gamma"].float() if (b + "gamma") in sd else torch.ones_like(b2)
     blk = dict(dw_w=sd[b + "dwconv.weight"].float().contiguous(), dw_b=sd[b + "dwconv.bias"].float().contiguous(),
                ln_w=sd[b + "norm.weight"].float().contiguous(), ln_b=sd[b + "norm.bias"].float().contiguous(), stages=[])
-    for h in range(2):
+    for h in range(4 * Cc // 128):
         r = slice(128 * h, 128 * h + 128)
-        blk["stages"].append(StageDef(f"block.pw1{'ab'[h]}", L.EPI_BIAS_LRELU, b1[r], [R_P1], [128 * h], flags=_act_flags(L.ACT_GELU))
+        blk["stages"].append(StageDef(f"block.pw1{'abcd'[h]}", L.EPI_BIAS_LRELU, b1[r], [R_P1], [128 * h], flags=_act_flags(L.ACT_GELU))
                              .add(R_DW, w1[r][:, :, None, None], 0, 1))
     blk["stages"].append(StageDef("block.pw2", L.EPI_RES_ID, gamma * b2, [R_O0, R_BK], flags=_act_flags(L.ACT_NONE))
                          .add(R_P1, (gamma[:, None] * w2)[:, :, None, None], 0, 1))
@@ -76,7 +84,7 @@ def refine_graph(sd: Dict[str, torch.Tensor]):
     wpool, bpool = _fold(sd[a + "convs.4.1.weight"], sd, a + "convs.4.2")
     wproj, bproj = _fold(sd[a + "project.0.weight"], sd, a + "project.1")              # [128, 640, 1, 1]
     g["pool"] = dict(pool_w=wpool[:, :, 0, 0].contiguous(), pool_b=bpool.contiguous(), proj_w=wproj[:, 512:640, 0, 0].contiguous(),
-                     proj_b=bproj.contiguous())
+                     proj_b=bproj.contiguous())          # pool_w [128, Cc]
     proj = StageDef("aspp.project", L.EPI_BIAS_LRELU, torch.zeros(128, device=wproj.device), [R_PR], flags=_act_flags(L.ACT_RELU) | L.FLAG_IMG_BIAS)
     for k in range(4):
         proj.add(R_A0 + k, wproj[:, 128 * k:128 * k + 128], 0, k == 0)
@@ -96,25 +104,27 @@ class RefineEngine:
         self.x3 = precision == "bf16x3"
         n = B * T
         sd = {k: v.detach().to(device) for k, v in sd.items() if k.startswith(("spatial_grus", "res_blocks"))}
-        if sd["spatial_grus.0.conv_update.weight"].shape[:2] != (64, 128) or "res_blocks.0.1.dwconv.weight" in sd:
-            raise L.SfError("fused refinement is built for 64 channels and one ConvNeXt block")
+        Cc = self.C = sd["spatial_grus.0.conv_update.weight"].shape[0]
+        if Cc not in (64, 128) or sd["spatial_grus.0.conv_update.weight"].shape[1] != 2 * Cc or "res_blocks.0.1.dwconv.weight" in sd \
+                or sd["res_blocks.1.0.convs.0.0.weight"].shape[0] != 128:
+            raise L.SfError("fused refinement is built for 64 or 128 channels, one ConvNeXt block and DeepLabHead(C, C, 128)")
         self.g = refine_graph(sd)
-        P = self.plan = LevelPlan(self.lib, H, W, n, self.x3, device)
-        for b, ch in FRAME_BUFS.items():
+        P = self.plan = LevelPlan(self.lib, H, W, n, self.x3, device, C_hidden=Cc)
+        for b, ch in frame_bufs(Cc).items():
             if b != R_X:
                 P.buf(b, ch)
-        for b, ch in STATE_BUFS.items():
+        for b, ch in state_bufs(Cc).items():
             shape = (B, H, W, ch)
             P.buf(b, ch, planes=(torch.zeros(shape, dtype=torch.bfloat16, device=device),
                                  torch.zeros(shape, dtype=torch.bfloat16, device=device) if self.x3 else None))
-        self.state32 = torch.zeros((B, H, W, 64), dtype=torch.float32, device=device)
+        self.state32 = torch.zeros((B, H, W, Cc), dtype=torch.float32, device=device)
         for slot in (L.F32_STATE0, L.F32_A):
             L.check(self.lib.sf_plan_bind_f32(P.plan, slot, self.state32.data_ptr()), "bind state")
-        self.out32 = torch.empty((n, H, W, 64), dtype=torch.float32, device=device)
+        self.out32 = torch.empty((n, H, W, Cc), dtype=torch.float32, device=device)
         P.bind_out32(self.out32)
         self.img_bias = torch.zeros((n, 128), dtype=torch.float32, device=device)
         L.check(self.lib.sf_plan_bind_f32(P.plan, L.F32_IMG_BIAS, self.img_bias.data_ptr()), "bind img bias")
-        self.pool_scratch = torch.zeros((n, 32, 64), dtype=torch.float32, device=device)
+        self.pool_scratch = torch.zeros((n, 32, Cc), dtype=torch.float32, device=device)
         self.slots = {}
         for i in range(2):
             gi = self.g[f"gru{i}"]
@@ -155,20 +165,20 @@ class RefineEngine:
     def _init_state(self, x_planes, x32):
         B, T = self.B, self.T
         idx = torch.arange(B, device=self.device) * T            # hidden_state = x[:, 0] (future_prediction_ode.py:56)
-        self.state32.copy_(x32.view(B * T, self.H, self.W, 64)[idx])
+        self.state32.copy_(x32.view(B * T, self.H, self.W, self.C)[idx])
         for dst, src in zip(self.plan.bufs[R_S], x_planes):
             if dst is not None:
                 dst.copy_(src[idx])
 
     def output_planes(self):
-        """The refined frames in engine layout: (hi, lo) NHWC bf16 [B*T, H, W, 64] (image index b*T + t)."""
+        """The refined frames in engine layout: (hi, lo) NHWC bf16 [B*T, H, W, C] (image index b*T + t)."""
         return self.plan.bufs[R_OUT]
 
     def run(self, x_planes, x32: torch.Tensor) -> torch.Tensor:
-        """x_planes: (hi, lo) NHWC bf16 [B*T, H, W, 64] decoded frames, image index b*T + t; x32: the same frames in fp32 NHWC.
-        Returns the refined frames [B, T, 64, H, W] fp32 NCHW."""
+        """x_planes: (hi, lo) NHWC bf16 [B*T, H, W, C] decoded frames, image index b*T + t; x32: the same frames in fp32 NHWC.
+        Returns the refined frames [B, T, C, H, W] fp32 NCHW."""
         P, lib, n = self.plan, self.lib, self.B * self.T
-        P.buf(R_X, 64, planes=(x_planes[0][:n], x_planes[1][:n] if x_planes[1] is not None else None))
+        P.buf(R_X, self.C, planes=(x_planes[0][:n], x_planes[1][:n] if x_planes[1] is not None else None))
         stream = self._stream()
         self._init_state(x_planes, x32)
         self._run_gru(0, x_planes)
@@ -176,16 +186,16 @@ class RefineEngine:
         o0, dw = P.bufs[R_O0], P.bufs[R_DW]
         L.check(lib.sf_dwconv7_ln(o0[0].data_ptr(), o0[1].data_ptr() if o0[1] is not None else None, dw[0].data_ptr(),
                                   dw[1].data_ptr() if dw[1] is not None else None, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(),
-                                  blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), n, self.H, self.W, stream), "dwconv7_ln")
+                                  blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), n, self.C, self.H, self.W, stream), "dwconv7_ln")
         self.launches += 1 + P.run(self.slots["block"], n)
         self._init_state(x_planes, x32)
         self._run_gru(1, x_planes)
         pl, o1 = self.g["pool"], P.bufs[R_O1]
         L.check(lib.sf_aspp_pool_bias(o1[0].data_ptr(), o1[1].data_ptr() if o1[1] is not None else None, pl["pool_w"].data_ptr(),
                                       pl["pool_b"].data_ptr(), pl["proj_w"].data_ptr(), pl["proj_b"].data_ptr(), self.pool_scratch.data_ptr(),
-                                      self.img_bias.data_ptr(), n, self.H, self.W, stream), "aspp_pool_bias")
+                                      self.img_bias.data_ptr(), n, self.C, self.H, self.W, stream), "aspp_pool_bias")
         self.launches += 2 + P.run(self.slots["deeplab"], n)
-        out = torch.empty((n, 64, self.H, self.W), dtype=torch.float32, device=self.device)
-        L.check(lib.sf_unpack_nhwc_f32(self.out32.data_ptr(), out.data_ptr(), None, n, 64, self.H, self.W, stream), "unpack")
+        out = torch.empty((n, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
+        L.check(lib.sf_unpack_nhwc_f32(self.out32.data_ptr(), out.data_ptr(), None, n, self.C, self.H, self.W, stream), "unpack")
         self.launches += 1
-        return out.view(self.B, self.T, 64, self.H, self.W)
+        return out.view(self.B, self.T, self.C, self.H, self.W)

@@ -372,28 +372,30 @@ def test_config5_module_level_latent_event_matches_oracle(precision):
         assert r["contract"]["state"] < contract and r["contract"]["x"] < 2 * contract, (i, r["contract"], precision)
 
 
+@pytest.mark.parametrize("Cc", [64, 128])
 @pytest.mark.parametrize("x3", [False, True])
 @pytest.mark.parametrize("H,W", [(200, 200), (37, 45), (8, 5)])
-def test_depthwise7_layernorm_kernel_matches_torch(H, W, x3):
-    """sf_dwconv7_ln (ConvNeXt Block front end, convolutions.py:320-331): depthwise 7x7 + bias, LayerNorm over the 64 channels --
-    the shared-memory-tile kernel vs fp64 torch, incl. ragged 32 x 8 tiles and images smaller than a tile."""
+def test_depthwise7_layernorm_kernel_matches_torch(H, W, x3, Cc):
+    """sf_dwconv7_ln (ConvNeXt Block front end, convolutions.py:320-331): depthwise 7x7 + bias, LayerNorm over the channels -- the
+    shared-memory-tile kernel (64 channels) and the warp-per-pixel kernel (128) vs fp64 torch, incl. ragged 32 x 8 tiles and images
+    smaller than a tile."""
     L, lib = _lib()
-    n = 3
+    n = 3 if Cc == 64 else 2
     g = torch.Generator().manual_seed(7)
-    x = torch.randn(n, 64, H, W, generator=g)
-    w = 0.2 * torch.randn(64, 1, 7, 7, generator=g)
-    b, lw, lb = 0.1 * torch.randn(64, generator=g), 1 + 0.2 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    x = torch.randn(n, Cc, H, W, generator=g)
+    w = 0.2 * torch.randn(Cc, 1, 7, 7, generator=g)
+    b, lw, lb = 0.1 * torch.randn(Cc, generator=g), 1 + 0.2 * torch.randn(Cc, generator=g), 0.1 * torch.randn(Cc, generator=g)
     nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     hi = nhwc.to(torch.bfloat16)
     lo = (nhwc - hi.float()).to(torch.bfloat16) if x3 else None
     oh, ol = torch.zeros_like(hi), (torch.zeros_like(hi) if x3 else None)
     ptr = lambda t: t.data_ptr() if t is not None else None
     wd, bd, lwd, lbd = (t.cuda().contiguous() for t in (w, b, lw, lb))
-    L.check(lib.sf_dwconv7_ln(ptr(hi), ptr(lo), ptr(oh), ptr(ol), wd.data_ptr(), bd.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), n, H, W, _stream()), "dwconv")
+    L.check(lib.sf_dwconv7_ln(ptr(hi), ptr(lo), ptr(oh), ptr(ol), wd.data_ptr(), bd.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), n, Cc, H, W, _stream()), "dwconv")
     torch.cuda.synchronize()
     xin = (hi.float() + (lo.float() if x3 else 0)).permute(0, 3, 1, 2).double().cpu()         # what the kernel read
-    y = F.conv2d(xin, w.double(), b.double(), padding=3, groups=64).permute(0, 2, 3, 1)
-    want = F.layer_norm(y, (64,), lw.double(), lb.double(), 1e-6)
+    y = F.conv2d(xin, w.double(), b.double(), padding=3, groups=Cc).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (Cc,), lw.double(), lb.double(), 1e-6)
     got = (oh.float() + (ol.float() if x3 else 0)).double().cpu()
     err = (got - want).abs().max().item() / want.abs().max().item()
     assert err < (1e-5 if x3 else 5e-3), err            # output rounding: bf16 (2^-9) or split bf16 (2^-17)

@@ -338,23 +338,57 @@ def test_cuda_graph_rollout_equals_eager_including_the_noise_stream():
     assert not torch.equal(outs[True][1], outs[True][5])                      # a and c saw different noise
 
 
+@pytest.mark.parametrize("precision,nf", [("bf16", 64), ("bf16x3", 128)])
+def test_module_forward_at_128_channels_runs_on_the_engine_and_matches_oracle(precision, nf):
+    """BASELINE config 5 at the MODULE level: FuturePredictionODE(128, 128) -- encoder, ODE loop, decoder, SpatialGRU x2, ConvNeXt
+    Block (depthwise 7x7 + LN, 128 -> 512 -> 128) and DeepLabHead all on the conv-stage kernels (no cuDNN fall-back) vs the fp64
+    oracle; BEV 96 x 80 -> 24 x 20 latent, jittered schedules of two samples."""
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+
+    C, H, W, B, seed = 128, 96, 80, 2, 31
+    m = FuturePredictionODE(C, C, 4, make_cfg(C, filter_size=nf)).eval()
+    sd32 = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed, 1.0)
+    m.load_state_dict(sd32, strict=True)
+    m = m.cuda()
+    m.gru_ode.precision = precision
+    ct = torch.tensor([[-1.0, -0.5, 0.0], [-1.013, -0.492, -0.004]], dtype=torch.float64)
+    lt = torch.tensor([[-0.8, -0.6, -0.4, -0.2, 0.0], [-0.81, -0.6, -0.418, -0.2, 0.011]], dtype=torch.float64)
+    tt = torch.tensor([[-1.0, 0.0, 1.0, 2.0], [-1.0, 0.0, 0.99, 2.0]], dtype=torch.float64)
+    cam = so.recipe_array("cam", (B, 3, C, H, W), seed).cuda()
+    lid = so.recipe_array("lidar", (B, 5, C, H, W), seed).cuda()
+    tape = torch.stack([so.recipe_array(f"eps{i}", (C, H // 4, W // 4), seed) for i in range(48)]).cuda()
+    m.gru_ode._draw_noise = lambda n, h, w, device: tape[:n].contiguous()
+    with torch.no_grad():
+        x, aux = m(torch.zeros(B, 1, C, H, W, device="cuda"), cam, lid, ct, lt, tt)
+    torch.cuda.synchronize()
+    assert m.last_output_planes is not None, "the 128-channel module fell back to the PyTorch modules"
+    sd64 = {k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd32.items()}
+    with torch.no_grad():
+        xo = so.future_prediction_forward(sd64, cam.double(), lid.double(), ct, lt, tt, 0.05, iter(tape.double()[:, None]))
+    assert aux == 0 and x.shape == xo.shape == (B, 4, C, H, W)
+    err = _rel(x, xo)
+    assert err < 5 * TOL[precision], f"refined output error {err:.3e}"
+
+
+@pytest.mark.parametrize("C,nf", [(64, 64), (128, 64), (128, 128)])
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
-def test_fused_encoder_and_decoder_match_oracle(precision):
-    """SmallEncoder / SmallDecoder on the conv-stage kernels (codec_engine.py) vs the fp64 oracle, ragged BEV size 72x56."""
+def test_fused_encoder_and_decoder_match_oracle(precision, C, nf):
+    """SmallEncoder / SmallDecoder on the conv-stage kernels (codec_engine.py) vs the fp64 oracle, ragged BEV size 72x56; input =
+    latent width 64, and 128 (BASELINE config 5: MODEL.ENCODER.OUT_CHANNELS = 128) with filter size 64 (the reference's default) or 128."""
     from streamingflow_b200.codec_engine import CodecEngine
 
     seed, H, W, n = 23, 72, 56, 3
-    sd32 = so.recipe_state_dict(nnfo_shapes(64), seed, 1.0)
+    sd32 = so.recipe_state_dict(nnfo_shapes(C, nf), seed, 1.0)
     sd64 = {"g." + k: (v.double().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd32.items()}
     codec = CodecEngine({k: v.cuda() for k, v in sd32.items()}, H, W, n, n, precision, torch.device("cuda", torch.cuda.current_device()))
-    frames = so.recipe_array("frames", (n, 64, H, W), seed).cuda()
+    frames = so.recipe_array("frames", (n, C, H, W), seed).cuda()
     hi, lo = codec.encode(frames)
     got = hi.float() + (lo.float() if lo is not None else 0)
     with torch.no_grad():
         want = so.small_encoder(sd64, "g.srvp_encoder", frames.double())
     tol = 2e-2 if precision == "bf16" else 1e-4
-    assert _rel(got.permute(0, 3, 1, 2), want) < 5e-4          # the encoder always runs in the accurate mode (11 convs deep)
-    z = torch.tanh(so.recipe_array("z", (5, H // 4, W // 4, 64), seed)).cuda().contiguous()     # a "path buffer" with 5 slots
+    assert got.shape[-1] == C and _rel(got.permute(0, 3, 1, 2), want) < 5e-4          # the encoder always runs in the accurate mode (11 convs deep)
+    z = torch.tanh(so.recipe_array("z", (5, H // 4, W // 4, C), seed)).cuda().contiguous()     # a "path buffer" with 5 slots
     slots = torch.tensor([4, 0, 2], dtype=torch.int32, device="cuda")
     out = codec.decode(z, slots)
     with torch.no_grad():

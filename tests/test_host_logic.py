@@ -396,43 +396,45 @@ def _interpret_codec_graph(graph, bufs_spec, x_in, in_key, out_key, dims):
     return bufs[out_key[0]][out_key[1]]
 
 
-def test_codec_stage_graphs_reproduce_encoder_and_decoder():
+@pytest.mark.parametrize("C,nf", [(64, 64), (128, 64), (128, 128)])
+def test_codec_stage_graphs_reproduce_encoder_and_decoder(C, nf):
     """SmallEncoder / SmallDecoder as conv-stage graphs (BatchNorm folded, ConvTranspose as flipped conv, 128-channel output
-    groups, residual / projection epilogues) == the oracle's encoder / decoder."""
+    groups, residual / projection epilogues) == the oracle's encoder / decoder; input = latent width 64 and 128 (config 5)."""
     from streamingflow_b200 import codec_engine as ce
 
-    sd = so.recipe_state_dict(nnfo_shapes(64), 9, 1.0, torch.float32)
+    sd = so.recipe_state_dict(nnfo_shapes(C, nf), 9, 1.0, torch.float32)
     H, W = 16, 24
     dims = {"A": (H, W), "B": (H // 2, W // 2), "C": (H // 4, W // 4)}
-    x = so.recipe_array("bev", (1, 64, H, W), 9, torch.float32)
+    x = so.recipe_array("bev", (1, C, H, W), 9, torch.float32)
     sd64 = {"g." + k: v.double() for k, v in sd.items()}
     with torch.no_grad():
         want = so.small_encoder(sd64, "g.srvp_encoder", x.double())
-        got = _interpret_codec_graph(ce.encoder_graph(sd), ce.ENC_BUFS, x, ce.ENC_IN, ce.ENC_OUT, dims)
+        got = _interpret_codec_graph(ce.encoder_graph(sd), ce.enc_bufs(C, nf), x, ce.ENC_IN, ce.ENC_OUT, dims)
     assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
-    z = torch.tanh(so.recipe_array("lat", (1, 64, H // 4, W // 4), 9, torch.float32))
+    z = torch.tanh(so.recipe_array("lat", (1, C, H // 4, W // 4), 9, torch.float32))
     with torch.no_grad():
         want = so.small_decoder(sd64, "g.srvp_decoder", z.double())
-        got = _interpret_codec_graph(ce.decoder_graph(sd), ce.DEC_BUFS, z, ce.DEC_IN, ce.DEC_OUT, dims)
+        got = _interpret_codec_graph(ce.decoder_graph(sd), ce.dec_bufs(C, nf), z, ce.DEC_IN, ce.DEC_OUT, dims)
     assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
 
 
-def test_refinement_stage_graph_reproduces_reference_refinement():
+@pytest.mark.parametrize("C", [64, 128])
+def test_refinement_stage_graph_reproduces_reference_refinement(C):
     """SpatialGRU x2 + ConvNeXt Block + DeepLabHead as conv-stage graphs (refine_engine.refine_graph), interpreted on the host,
-    == the oracle's refinement (future_prediction_ode.py:56-62)."""
+    == the oracle's refinement (future_prediction_ode.py:56-62); in_channels 64 and 128."""
     from streamingflow_b200 import _lib as L, engine as en, refine_engine as rf
     from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
     import torch.nn.functional as F
 
-    m = FuturePredictionODE(64, 64, 4, make_cfg(64)).eval()
+    m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval()
     sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 12, 1.0)
     g = rf.refine_graph(sd)
-    B, T, H, W = 1, 2, 48, 40
-    x = so.recipe_array("x", (B, T, 64, H, W), 12)
+    B, T, H, W = (1, 2, 48, 40) if C == 64 else (1, 2, 40, 24)
+    x = so.recipe_array("x", (B, T, C, H, W), 12)
     emu = lambda sdef, src: en.emulate_stage(sdef, True, {k: v.float() for k, v in src.items()})
     sig = torch.sigmoid
 
-    def run_gru(i, frames):          # frames [T, 64, H, W]
+    def run_gru(i, frames):          # frames [T, C, H, W]
         gi = g[f"gru{i}"]
         state = x[0, 0].double()
         outs = []
@@ -440,11 +442,11 @@ def test_refinement_stage_graph_reproduces_reference_refinement():
             xt = frames[t][None].double()
             acc = emu(gi["gates"], {rf.R_S: state[None], -1: xt})
             vec = gi["gates"].vec.double()
-            u = sig(acc[:64] + vec[:64, None, None])
-            r = sig(acc[64:128] + vec[64:, None, None])
+            u = sig(acc[:C] + vec[:C, None, None])
+            r = sig(acc[C:2 * C] + vec[C:, None, None])
             acc = emu(gi["propose"], {-1: xt, rf.R_G: ((1 - r) * state)[None]})
-            state = (1 - u) * state + u * (acc[:64] + gi["propose"].vec.double()[:, None, None])
-            outs.append(emu(gi["dec"], {-1: state[None]})[:64])
+            state = (1 - u) * state + u * (acc[:C] + gi["propose"].vec.double()[:, None, None])
+            outs.append(emu(gi["dec"], {-1: state[None]})[:C])
         return torch.stack(outs)
 
     def run_stage(sdef, bufs, img_bias=None):
@@ -465,9 +467,9 @@ def test_refinement_stage_graph_reproduces_reference_refinement():
     out_frames = []
     o1_in = []
     for t in range(T):
-        dw = F.conv2d(o0[t][None], blk["dw_w"].double(), blk["dw_b"].double(), padding=3, groups=64)[0]
-        dw = F.layer_norm(dw.permute(1, 2, 0), (64,), blk["ln_w"].double(), blk["ln_b"].double(), 1e-6).permute(2, 0, 1)
-        bufs = {rf.R_O0: o0[t], rf.R_DW: dw, rf.R_P1: torch.zeros(256, H, W, dtype=torch.float64)}
+        dw = F.conv2d(o0[t][None], blk["dw_w"].double(), blk["dw_b"].double(), padding=3, groups=C)[0]
+        dw = F.layer_norm(dw.permute(1, 2, 0), (C,), blk["ln_w"].double(), blk["ln_b"].double(), 1e-6).permute(2, 0, 1)
+        bufs = {rf.R_O0: o0[t], rf.R_DW: dw, rf.R_P1: torch.zeros(4 * C, H, W, dtype=torch.float64)}
         for sdef in blk["stages"]:
             dst, off, v = run_stage(sdef, bufs)
             if dst == rf.R_P1:
@@ -490,9 +492,9 @@ def test_refinement_stage_graph_reproduces_reference_refinement():
     sd64 = {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}
     with torch.no_grad():
         y = so.spatial_gru(sd64, "spatial_grus.0", x.double(), x[:, 0].double())
-        y = so.convnext_block(sd64, "res_blocks.0.0", y.reshape(B * T, 64, H, W)).view(B, T, 64, H, W)
+        y = so.convnext_block(sd64, "res_blocks.0.0", y.reshape(B * T, C, H, W)).view(B, T, C, H, W)
         y = so.spatial_gru(sd64, "spatial_grus.1", y, x[:, 0].double())
-        want = so.deeplab_head(sd64, "res_blocks.1", y.reshape(B * T, 64, H, W)).view(B, T, 64, H, W)
+        want = so.deeplab_head(sd64, "res_blocks.1", y.reshape(B * T, C, H, W)).view(B, T, C, H, W)
     assert got.shape == want.shape
     assert ((got - want).abs().max() / want.abs().max()).item() < 5e-4
 
