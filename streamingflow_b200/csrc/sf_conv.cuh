@@ -666,11 +666,25 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   // item w < n_whole: tile w, all M-tiles; else tile n_whole + (w - n_whole) / MT, M-tile (w - n_whole) % MT only.
   const int n_whole = (MT > 1 && 2 * (ntiles % (int)gridDim.x) <= (int)gridDim.x) ? ntiles - ntiles % (int)gridDim.x : ntiles;
   const int nwork = n_whole + (ntiles - n_whole) * MT;
+  // An M-tile that lies entirely to the right of the image (W = 200: the second M-tile of the 13th tile column; 50 x 50 latents:
+  // of every 4th column) is masked out: no MMAs are issued for it and its epilogue warpgroup only hands the accumulator back.
   auto work_tile = [&](int w, uint32_t& mtmask) -> int {
-    if (w < n_whole) { mtmask = (1u << MT) - 1u; return w; }
-    const int h = w - n_whole;
-    mtmask = 1u << (h % MT);
-    return n_whole + h / MT;
+    int tile;
+    if (w < n_whole) {
+      mtmask = (1u << MT) - 1u;
+      tile = w;
+    } else {
+      const int h = w - n_whole;
+      mtmask = 1u << (h % MT);
+      tile = n_whole + h / MT;
+    }
+    if (MT > 1) {
+      const int tx = (tile % tpi) % p.tiles_x;
+#pragma unroll
+      for (int mt = 1; mt < MT; ++mt)
+        if ((tx * MT + mt) * TILE_W >= p.W) mtmask &= ~(1u << mt);
+    }
+    return tile;
   };
   const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
   const uint32_t a_smem0 = smem_u32(a_base), b_smem0 = smem_u32(b_base);
