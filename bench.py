@@ -481,6 +481,7 @@ def e2e_forward_host(c, model, B, steps, decoder=None):
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     bufs = [(torch.empty_like(cam_h, device=dev), torch.empty_like(lid_h, device=dev)) for _ in range(2)]
+    marks = []                 # (forward start, forward end) events of every step on the main stream
     up = [None, None]          # H2D-done events per buffer
     free = [None, None]        # forward-has-consumed events per buffer
     out_done = [None]
@@ -501,13 +502,16 @@ def e2e_forward_host(c, model, B, steps, decoder=None):
         if not last:
             upload(i + 1)
         main.wait_event(up[k])
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record(main)
         with torch.no_grad():
             x, _ = model(fpi, bufs[k][0], bufs[k][1], ct, lt, tt)
             if decoder is not None:      # the step after the head: BEV Decoder + arg-max on the engine, frames handed over in engine layout
                 x = decoder(x, planes=model.last_output_planes)["segmentation_argmax"].view(B, len(TARGETS), H, H)
-        e = torch.cuda.Event()
+        e = torch.cuda.Event(enable_timing=True)
         e.record(main)
         free[k] = e
+        marks.append((t0, e))
         if out_done[0] is not None:
             s_out.wait_event(out_done[0])
         s_out.wait_event(e)
@@ -526,21 +530,25 @@ def e2e_forward_host(c, model, B, steps, decoder=None):
 
     run(2)      # warm-up: builds the codec / engine / refinement plans
     c.barrier()
+    marks.clear()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     run(steps)
     b.record()
     c.barrier()
     ms = max_over_ranks(a.elapsed_time(b), dev, c.world)
+    # where a step's time goes on the main stream: the forward itself, and the wait for the step's H2D copy in front of it
+    fwd_ms = statistics.mean(s0.elapsed_time(s1) for s0, s1 in marks)
+    stall_ms = statistics.mean(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1)) if len(marks) > 1 else 0.0
     n_steps = model.gru_ode.last_rollout.n_state_steps
     if decoder is not None:
         return dict(value=c.world * n_steps * steps / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=(cam_h.numel() + lid_h.numel()) * 4,
-                    d2h_bytes_per_step=out_h.numel(), ms_per_step=ms / steps, steps=steps,
+                    d2h_bytes_per_step=out_h.numel(), ms_per_step=ms / steps, steps=steps, forward_ms_in_pipeline=fwd_ms, wait_for_h2d_ms=stall_ms,
                     api="FuturePredictionODE.forward -> Decoder.forward(x, planes=...) -> segmentation arg-max (trainer.py:230-231), all on the "
                         "engine; H2D of the BEV states and D2H of the uint8 occupancy masks [B, 7, 200, 200] inside the timed region")
     return dict(value=c.world * n_steps * steps / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=(cam_h.numel() + lid_h.numel()) * 4,
                 d2h_bytes_per_step=out_h.numel() * 4, ms_per_step=ms / steps, steps=steps,
-                launches_per_step=model.gru_ode.last_rollout.launches,
+                launches_per_step=model.gru_ode.last_rollout.launches, forward_ms_in_pipeline=fwd_ms, wait_for_h2d_ms=stall_ms,
                 api="FuturePredictionODE.forward(future_prediction_input, camera_states, lidar_states, camera_timestamp, lidar_timestamp, "
                     f"target_timestamp), B = {B}/GPU, BEV 200x200x64 (-> 50x50x64 latent), camera/LiDAR states in pinned host memory, output "
                     "read back to pinned host memory; all copies of every timed step inside the timed region (double-buffered copy streams)")

@@ -205,7 +205,7 @@ class NNFOwithBayesianJumps(nn.Module):
         self.last_rollout = None
 
     # ------------------------------------------------------------------ copy / pickle (EMA copies, torch.save of the whole module)
-    _RUNTIME_CACHES = ("_engines", "_codecs", "_graphs", "_stream_plans", "_copy_streams", "_stage_bufs", "download_done")
+    _RUNTIME_CACHES = ("_engines", "_codecs", "_graphs", "_stream_plans", "_copy_streams", "_stage_bufs", "download_done", "_fused_preps")
 
     def _wire_cells(self):
         from .. import ops
@@ -686,6 +686,42 @@ class NNFOwithBayesianJumps(nn.Module):
         x = self.srvp_decode(sel)
         return state, 0, x
 
+    def fused_prep(self, n, H, W, obs_counts, times, targets, delta_t, stamp_dtypes, device):
+        """Host-side preparation of encoder -> jump / integrate loop -> decoder for one schedule, cached: the engines, the compiled
+        rollout, the event table and the path-slot list ALREADY ON THE DEVICE.  With it a forward issues no host<->device copy of
+        its own and never waits for the device (the pageable uploads of a fresh table would)."""
+        key = (str(device), n, H, W, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
+               tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), tuple(stamp_dtypes), self.precision, self.solver,
+               bool(self.use_variable_ode_step), bool(self.impute), self.event_group)
+        B, T = len(obs_counts), len(targets[0])
+        codec = self._codec_for(H, W, n, B * T, device)
+        eng = self._engine_for(H // 4, W // 4, B, device)
+        cache = self.__dict__.setdefault("_fused_preps", {})
+        ent = cache.get(key)
+        if ent is not None and ent["codec"] is codec and ent["eng"] is eng:
+            return ent
+        if len(cache) >= 8:
+            cache.clear()
+        plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
+        base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), max_group=self.event_group)
+        table, evs = eng.build_table(ro.events)
+        flat = [s for slots in ro.out_slots for s in slots]
+        ent = cache[key] = dict(codec=codec, eng=eng, ro=ro, evs=evs, tdev=eng.upload_table(table),
+                                slots=torch.tensor(flat, dtype=torch.int32).to(device), B=B, T=T, eps=None)
+        return ent
+
+    def fused_run(self, prep, frames, eps):
+        """The device work of encoder -> loop -> decoder on prepared state: launches only (capturable into a CUDA graph when
+        ``frames`` and ``eps`` are static buffers).  Returns the decoded frames in engine layout."""
+        codec, eng, ro = prep["codec"], prep["eng"], prep["ro"]
+        planes = codec.encode(frames)
+        eng.bind_observation_planes(*planes)
+        eng.bind_eps(eps)
+        eng.zero_state(0)
+        ro.launches = eng.run_events(prep["evs"], prep["tdev"])
+        return codec.decode(eng.path, prep["slots"], unpack=False)
+
     def encode_integrate_decode(self, frames, obs_counts, times, targets, delta_t, raw: bool = False, stamp_dtypes=("float64", "float64")):
         """SmallEncoder -> jump / integrate loop -> SmallDecoder entirely on the conv-stage kernels: frames [n, C, H, W] (all
         samples' observation frames, sample-major, processing order) -> (final latent states, decoded frames [B, T, C, H, W]).
@@ -693,12 +729,25 @@ class NNFOwithBayesianJumps(nn.Module):
         self._guard_no_grad(frames, *self.srvp_encoder.parameters(), *self.srvp_decoder.parameters())
         n, c, H, W = frames.shape
         B, T = len(obs_counts), len(targets[0])
-        codec = self._codec_for(H, W, n, B * T, frames.device)
-        planes = codec.encode(frames)
-        state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True,
-                                                     stamp_dtypes=stamp_dtypes)
-        slots = torch.tensor(flat, dtype=torch.int32).to(frames.device)
-        x = codec.decode(eng.path, slots, unpack=not raw)
+        if self.record_all:            # debug path: per-event trace through the general rollout
+            codec = self._codec_for(H, W, n, B * T, frames.device)
+            planes = codec.encode(frames)
+            state, (eng, flat) = self.integrate_latents(None, obs_counts, times, targets, delta_t, obs_planes=planes, return_slots=True,
+                                                         stamp_dtypes=stamp_dtypes)
+            slots = torch.tensor(flat, dtype=torch.int32).to(frames.device)
+            x = codec.decode(eng.path, slots, unpack=not raw)
+        else:
+            prep = self.fused_prep(n, H, W, obs_counts, times, targets, delta_t, stamp_dtypes, frames.device)
+            codec, eng, ro = prep["codec"], prep["eng"], prep["ro"]
+            eng.ensure_path_slots(ro.n_path)
+            x = self.fused_run(prep, frames, self._draw_noise(ro.n_eps, H // 4, W // 4, frames.device))
+            self.last_rollout = ro
+            state = eng.unpack_f32(eng.state32[0], B)
+            if not raw:
+                out = torch.empty((B * T, c, H, W), dtype=torch.float32, device=frames.device)
+                L.check(codec.lib.sf_unpack_nhwc_f32(x[1].data_ptr(), out.data_ptr(), None, B * T, c, H, W, codec._stream()), "unpack")
+                codec.launches += 1
+                x = out
         if not raw:
             x = x.view(B, T, c, H, W)
         self.last_rollout.launches += codec.launches

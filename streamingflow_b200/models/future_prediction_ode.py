@@ -18,6 +18,14 @@ from ..layers.temporal_ode_bayes import NNFOwithBayesianJumps
 from ..schedule import merge_observations
 
 
+class _StackSpec:
+    """Shape and device of ``torch.stack(frames)`` without the copy."""
+
+    def __init__(self, frames):
+        self.shape = (len(frames),) + tuple(frames[0].shape)
+        self.device = frames[0].device
+
+
 class FuturePredictionODE(nn.Module):
     def __init__(self, in_channels, latent_dim, n_future, cfg, mixture=True, n_gru_blocks=2, n_res_layers=1, delta_t=0.05):
         super().__init__()
@@ -34,7 +42,11 @@ class FuturePredictionODE(nn.Module):
         self.res_blocks = nn.ModuleList(blocks)
         self.in_channels, self.n_res_layers = in_channels, n_res_layers
         self.fused_refine = os.environ.get("SF_B200_FUSED_REFINE", "1") == "1"   # SpatialGRU / Block / DeepLabHead on the CUDA engine
+        # the whole forward (layout pack, encoder, step loop, decoder, refinement: ~340 launches) captured once per schedule and
+        # replayed as ONE CUDA graph; the noise draw, the gather of the caller's frames and the final layout unpack stay eager
+        self.forward_graph = os.environ.get("SF_B200_FORWARD_GRAPH", "1") == "1"
         self.__dict__["_refiners"] = {}
+        self.__dict__["_fwd_graphs"] = {}
 
     def _refine_for(self, H, W, B, T, device):
         from ..refine_engine import RefineEngine
@@ -51,9 +63,53 @@ class FuturePredictionODE(nn.Module):
             self._refiners[key] = ent
         return ent["engine"]
 
+    def _forward_graphed(self, frames, shape, counts, times, targets, dtypes, refine):
+        """Encoder -> ODE loop -> decoder -> refinement as ONE captured CUDA graph per (shapes, schedule, weights version).
+        Eager around the replay: the gather of the caller's frames into the graph's static input, the rollout's noise (one launch
+        on torch's Philox stream, exactly the draws the eager path makes) and the unpack of the result into a fresh tensor."""
+        ode = self.gru_ode
+        n, C, H, W = shape
+        dev = frames[0].device
+        prep = ode.fused_prep(n, H, W, counts, times, targets, self.delta_t, dtypes, dev)
+        eng, codec, ro = prep["eng"], prep["codec"], prep["ro"]
+        eng.ensure_path_slots(ro.n_path)
+        key = (id(prep), id(refine))
+        ent = self._fwd_graphs.get(key)
+        if ent is not None and (ent["prep"] is not prep or ent["refine"] is not refine or ent["gen"] != eng.alloc_gen):
+            ent = None
+        if ent is None:
+            if len(self._fwd_graphs) >= 4:
+                self._fwd_graphs.clear()
+            static_in = torch.empty((n, C, H, W), dtype=torch.float32, device=dev)
+            eps = torch.empty((max(ro.n_eps, 1), C, H // 4, W // 4), dtype=torch.float32, device=dev)
+            torch.stack(frames, dim=0, out=static_in)
+            eps.zero_()
+            # one eager pass on the static buffers: builds every per-size table, binds every buffer (nothing of it is kept)
+            planes, x32 = ode.fused_run(prep, static_in, eps)
+            refine.run_core(planes, x32)
+            torch.cuda.synchronize(dev)
+            gen0 = eng.alloc_gen
+            codec.launches = refine.launches = 0
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                planes, x32 = ode.fused_run(prep, static_in, eps)
+                refine.run_core(planes, x32)
+            if eng.alloc_gen != gen0:
+                raise RuntimeError("a buffer moved during the capture of the forward graph")
+            ent = self._fwd_graphs[key] = dict(graph=graph, static_in=static_in, eps=eps, prep=prep, refine=refine, gen=eng.alloc_gen,
+                                               launches=ro.launches + codec.launches + refine.launches)
+            codec.launches = refine.launches = 0
+        torch.stack(frames, dim=0, out=ent["static_in"])
+        ode._noise_into(ent["eps"], ro.n_eps, H // 4, W // 4, dev)
+        ent["graph"].replay()
+        ro.launches = ent["launches"]
+        ode.last_rollout = ro
+        refine.launches = 0
+        return refine.unpack_output()
+
     def __getstate__(self):
         d = dict(self.__dict__)          # the refinement engines hold ctypes plan handles: per-instance, rebuilt on first use
-        d["_refiners"] = {}
+        d["_refiners"], d["_fwd_graphs"] = {}, {}
         d.pop("last_output_planes", None)
         return d
 
@@ -89,15 +145,19 @@ class FuturePredictionODE(nn.Module):
             counts.append(len(order))
             times.append([t for t, _, _ in order])
         ode = self.gru_ode
-        stacked = torch.stack(frames, dim=0)
+        stacked = _StackSpec(frames)                  # shape / device of torch.stack(frames); the copy itself happens where it is consumed
         H, W = stacked.shape[2], stacked.shape[3]
         fused = ode.codec_available(H, W, stacked.device)
         if fused and self.fused_refine and self.n_spatial_gru == 2 and self.n_res_layers == 1 and self.in_channels in (64, 128):
             # encoder -> ODE loop -> decoder -> SpatialGRU / Block / SpatialGRU / DeepLabHead, all on the CUDA engine
             T = len(tgt_t[0])
-            _, (planes, x32) = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, raw=True, stamp_dtypes=dtypes)
             refine = self._refine_for(H, W, B, T, stacked.device)
-            x = refine.run(planes, x32)
+            if self.forward_graph and not ode.record_all:
+                x = self._forward_graphed(frames, stacked.shape, counts, times, tgt_t, dtypes, refine)
+            else:
+                _, (planes, x32) = ode.encode_integrate_decode(torch.stack(frames, dim=0), counts, times, tgt_t, self.delta_t, raw=True,
+                                                               stamp_dtypes=dtypes)
+                x = refine.run(planes, x32)
             # the same frames in engine layout ((hi, lo) NHWC bf16 [B*T, H, W, C], views of the refinement's output buffer, valid
             # until the next forward): streamingflow_b200.models.decoder.Decoder.forward(x, planes=...) consumes them directly
             self.__dict__["last_output_planes"] = refine.output_planes()
@@ -106,9 +166,9 @@ class FuturePredictionODE(nn.Module):
             return x, 0
         self.__dict__["last_output_planes"] = None
         if fused:
-            _, x = ode.encode_integrate_decode(stacked, counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)      # encoder / loop / decoder on the CUDA engine
+            _, x = ode.encode_integrate_decode(torch.stack(frames, dim=0), counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)      # encoder / loop / decoder on the CUDA engine
         else:
-            hx = ode.srvp_encoder(stacked)
+            hx = ode.srvp_encoder(torch.stack(frames, dim=0))
             _, sel = ode.integrate_latents(hx, counts, times, tgt_t, self.delta_t, stamp_dtypes=dtypes)
             x = ode.srvp_decode(sel)                                   # [B, T, C, H, W]
         hidden_state = x[:, 0]

@@ -143,6 +143,7 @@ class RefineEngine:
                 (self.ev_gru if name == "gru" else self.ev_dec)[t] = off
                 off += 5 * B
         self.table = torch.from_numpy(np.concatenate(rows)).to(device)
+        self._first_frames = torch.arange(B, device=device) * T
         self.launches = 0
 
     def _stream(self):
@@ -164,7 +165,7 @@ class RefineEngine:
 
     def _init_state(self, x_planes, x32):
         B, T = self.B, self.T
-        idx = torch.arange(B, device=self.device) * T            # hidden_state = x[:, 0] (future_prediction_ode.py:56)
+        idx = self._first_frames                                  # hidden_state = x[:, 0] (future_prediction_ode.py:56)
         self.state32.copy_(x32.view(B * T, self.H, self.W, self.C)[idx])
         for dst, src in zip(self.plan.bufs[R_S], x_planes):
             if dst is not None:
@@ -177,6 +178,12 @@ class RefineEngine:
     def run(self, x_planes, x32: torch.Tensor) -> torch.Tensor:
         """x_planes: (hi, lo) NHWC bf16 [B*T, H, W, C] decoded frames, image index b*T + t; x32: the same frames in fp32 NHWC.
         Returns the refined frames [B, T, C, H, W] fp32 NCHW."""
+        self.run_core(x_planes, x32)
+        return self.unpack_output()
+
+    def run_core(self, x_planes, x32: torch.Tensor):
+        """Everything up to the head's fp32 NHWC output buffer (``out32``) and the bf16 output planes: static buffers in, static
+        buffers out, no allocation the caller keeps -- the part a CUDA graph of the whole forward captures."""
         P, lib, n = self.plan, self.lib, self.B * self.T
         P.buf(R_X, self.C, planes=(x_planes[0][:n], x_planes[1][:n] if x_planes[1] is not None else None))
         stream = self._stream()
@@ -195,7 +202,11 @@ class RefineEngine:
                                       pl["pool_b"].data_ptr(), pl["proj_w"].data_ptr(), pl["proj_b"].data_ptr(), self.pool_scratch.data_ptr(),
                                       self.img_bias.data_ptr(), n, self.C, self.H, self.W, stream), "aspp_pool_bias")
         self.launches += 2 + P.run(self.slots["deeplab"], n)
+
+    def unpack_output(self) -> torch.Tensor:
+        """out32 (NHWC fp32) -> a fresh [B, T, C, H, W] fp32 NCHW tensor."""
+        n = self.B * self.T
         out = torch.empty((n, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
-        L.check(lib.sf_unpack_nhwc_f32(self.out32.data_ptr(), out.data_ptr(), None, n, self.C, self.H, self.W, stream), "unpack")
+        L.check(self.lib.sf_unpack_nhwc_f32(self.out32.data_ptr(), out.data_ptr(), None, n, self.C, self.H, self.W, self._stream()), "unpack")
         self.launches += 1
         return out.view(self.B, self.T, self.C, self.H, self.W)

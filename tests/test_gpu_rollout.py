@@ -338,6 +338,42 @@ def test_cuda_graph_rollout_equals_eager_including_the_noise_stream():
     assert not torch.equal(outs[True][1], outs[True][5])                      # a and c saw different noise
 
 
+def test_forward_graph_equals_eager_forward_including_the_noise_stream():
+    """FuturePredictionODE.forward replayed as ONE CUDA graph (encoder, step loop, decoder, refinement) == the eager launch
+    sequence bit for bit: two consecutive calls on torch's own Philox stream, new inputs through the same graph, and a recapture
+    after an in-place weight update (the graph must not keep serving folded weights of the old version)."""
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+
+    C, H, W, B, seed = 64, 96, 80, 2, 41
+    m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval()
+    m.load_state_dict(so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed, 1.0), strict=True)
+    m = m.cuda()
+    ct = torch.tensor([[-1.0, -0.5, 0.0], [-1.013, -0.492, -0.004]], dtype=torch.float64)
+    lt = torch.tensor([[-0.8, -0.6, -0.4, -0.2, 0.0], [-0.81, -0.6, -0.418, -0.2, 0.011]], dtype=torch.float64)
+    tt = torch.tensor([[-1.0, 0.0, 1.0, 2.0], [-1.0, 0.0, 0.99, 2.0]], dtype=torch.float64)
+    fpi = torch.zeros(B, 1, C, H, W, device="cuda")
+    ins = [(so.recipe_array(f"cam{k}", (B, 3, C, H, W), seed).cuda(), so.recipe_array(f"lidar{k}", (B, 5, C, H, W), seed).cuda()) for k in range(2)]
+
+    def run(graph):
+        m.forward_graph = graph
+        torch.manual_seed(7)
+        with torch.no_grad():
+            outs = [m(fpi, *ins[0], ct, lt, tt)[0].clone(), m(fpi, *ins[0], ct, lt, tt)[0].clone(), m(fpi, *ins[1], ct, lt, tt)[0].clone()]
+        return outs, torch.cuda.default_generators[torch.cuda.current_device()].get_offset(), m.gru_ode.last_rollout.launches
+
+    eager, off_e, n_e = run(False)
+    graphed, off_g, n_g = run(True)
+    assert len(m._fwd_graphs) == 1 and off_e == off_g and n_e == n_g, (off_e, off_g, n_e, n_g)
+    assert all(torch.equal(a, b) for a, b in zip(eager, graphed))
+    assert not torch.equal(eager[0], eager[1]) and not torch.equal(eager[1], eager[2])      # later noise, other inputs
+    with torch.no_grad():
+        m.spatial_grus[0].conv_update.bias.add_(0.05)
+        m.gru_ode.gru_c.conv_update_1.bias.add_(0.05)
+    eager2, _, _ = run(False)
+    graphed2, _, _ = run(True)
+    assert all(torch.equal(a, b) for a, b in zip(eager2, graphed2)) and not torch.equal(eager2[0], eager[0])
+
+
 @pytest.mark.parametrize("precision,nf", [("bf16", 64), ("bf16x3", 128)])
 def test_module_forward_at_128_channels_runs_on_the_engine_and_matches_oracle(precision, nf):
     """BASELINE config 5 at the MODULE level: FuturePredictionODE(128, 128) -- encoder, ODE loop, decoder, SpatialGRU x2, ConvNeXt
