@@ -53,6 +53,12 @@ def flops_per_state_step_px(C):
     return 2 * (364 * C * C + 2 * C)
 
 
+def rollout_flops_px(ro, C):
+    """Algorithmic FLOPs per pixel of the work a compiled rollout EXECUTES: every op runs the cell (227 C^2 + 2 C MACs); the prior
+    net (137 C^2 MACs) runs only where its sample is read (rollout.py: not before a jump, not after the last op)."""
+    return ro.n_cell_evals * 2 * (227 * C * C + 2 * C) + ro.n_prior_evals * 2 * 137 * C * C
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -181,6 +187,9 @@ def workload_config(args, hw, batch):
                          f"observations (8 jumps + 10 variable Euler state-steps per sample), ODE grid {hw}x{hw}x64 "
                          f"({'cell-level: the literal 200x200x64 state' if args.grid == 'cell' else 'module-level latent of a 200x200x64 BEV'})",
                 grid=args.grid, batch_per_gpu=batch, precision=args.precision, solver="euler", variable_step=True, impute=True,
+                prior_net="evaluated where its sample is read (before each ode_step): 10 of the 18 ops of a sample; the reference also evaluates it "
+                          "before a jump and after the last op, where nothing reads the result (GRUObservationCell ignores p) -- outputs are "
+                          "bit-identical either way; 'all_prior_evaluated' in this line times the rollout with all 18",
                 launch="eager" if getattr(args, "no_graph", False) else "one CUDA graph per rollout (all stage launches); layout pack, one-launch noise draw and gathers eager around it",
                 l2="inputs + workspace (>1 GB at 200x200, B=8) exceed the 126 MB L2; no explicit flush" if hw >= 200 else
                    "working set fits L2 (module-level latent): L2 flushed by a 256 MB memset between steps",
@@ -412,6 +421,16 @@ def main():
     ms_total = max_over_ranks(ms, dev, world)
     value = world * steps_per_rollout * args.steps / (ms_total * 1e-3)
 
+    # the same rollout with the prior net evaluated after EVERY op, as the reference does (the dead evaluations included)
+    ode.skip_dead_prior = False
+    for _ in range(warm):
+        rollout()
+    ro_all = ode.last_rollout
+    ms_all = max_over_ranks(timed_rollouts(rollout, min(args.steps, 5), 0, barrier, flush), dev, world)
+    all_prior = dict(value=world * steps_per_rollout * min(args.steps, 5) / (ms_all * 1e-3), unit=UNIT, ms_per_step=ms_all / min(args.steps, 5),
+                     prior_evaluations_per_sample=ro_all.n_prior_evals // B, live_prior_evaluations_per_sample=ro.n_prior_evals // B)
+    ode.skip_dead_prior = True
+
     # ---------------- end to end through FuturePredictionODE.forward with host buffers (e2e)
     e2e = e2e_forward_host(c, model, B, args.steps)
     if args.workload == "config2" and args.grid == "cell" and not args.quick:
@@ -451,7 +470,7 @@ def main():
                     dtype="bf16" if args.precision == "bf16" else "bf16x3 (split-bf16 operands, 3 products, fp32 accumulate)",
                     data="synthetic", config=workload_config(args, hw, B), clocks=clocks.summary(), e2e=e2e,
                     gpu_launches=launches_per_rollout * args.steps, gpu_launches_per_step=launches_per_rollout,
-                    roofline=roof, cpu_baseline=cpu, parity=parity, modes=modes, configs=configs, config5_row_sharded=config5,
+                    roofline=roof, cpu_baseline=cpu, parity=parity, all_prior_evaluated=all_prior, modes=modes, configs=configs, config5_row_sharded=config5,
                     host_dma_probe=dma, host_affinity=affinity, gpu_eager_baseline=gpu_eager, module_level=module_level, stages=stages,
                     events_per_sec=world * (ro.n_state_steps + ro.n_jumps) * args.steps / (ms_total * 1e-3),
                     tflops=world * (ro.n_cell_evals * 2 * (227 * 4096 + 128) + ro.n_prior_evals * 2 * 137 * 4096) * hw * hw * args.steps
@@ -651,7 +670,7 @@ def accurate_mode(c, model, hx_dev, B, n_obs, times, hw, peaks):
         n = ode.last_rollout.n_state_steps
         out = dict(value=c.world * n * steps / (ms * 1e-3), unit=UNIT, ms_per_step=ms / steps, steps=steps,
                    dtype="bf16x3: x*w ~ xh*wh + xh*wl + xl*wh, fp32 accumulate (kind::tf32 operands measure 5e-4 on this rollout, outside 1e-4)",
-                   tflops_algorithmic=c.world * flops_per_state_step_px(64) * hw * hw * (n + ode.last_rollout.n_jumps) * steps / (ms * 1e-3) / 1e12)
+                   tflops_algorithmic=c.world * rollout_flops_px(ode.last_rollout, 64) * hw * hw * steps / (ms * 1e-3) / 1e12)
         if c.rank == 0 and not c.args.no_stage_timing:
             eng = ode._engines[(str(c.dev), hw, hw, "bf16x3")]["engine"]
             st = time_stages(eng, B, hw, peaks, reps=5)
@@ -687,7 +706,7 @@ def other_config(c, model, name, total_batch, targets):
     return dict(workload=f"{name}: batch {total_batch} total = {b}/GPU x {c.world} GPU, {len(targets)} targets, "
                          f"{ro.n_state_steps // b} state-steps + {ro.n_jumps // b} jumps per sample, 200x200x64 state, bf16",
                 value=c.world * ro.n_state_steps * steps / (ms * 1e-3), unit=UNIT, ms_per_step=ms / steps, steps=steps, scaling="strong",
-                tflops_algorithmic=c.world * flops_per_state_step_px(64) * hw * hw * (ro.n_state_steps + ro.n_jumps) * steps / (ms * 1e-3) / 1e12)
+                tflops_algorithmic=c.world * rollout_flops_px(ro, 64) * hw * hw * steps / (ms * 1e-3) / 1e12)
 
 
 def config5_row_sharded(c, steps=3, full_line=False):
@@ -729,7 +748,7 @@ def config5_row_sharded(c, steps=3, full_line=False):
     ms = max_over_ranks(a.elapsed_time(b), c.dev, c.world)
     n = ro.n_state_steps
     value = n * steps / (ms * 1e-3)
-    flops = flops_per_state_step_px(C) * H * H * (n + ro.n_jumps)
+    flops = rollout_flops_px(ro, C) * H * H
     out = dict(workload=f"config5: 400x400x128 ODE state, B = 1, row-sharded over {c.world} GPU(s) ({sh.own_hi - sh.own_lo} rows + 12-row halos per rank), "
                         "per event one halo push / pull per neighbour + two [B,2C] all-reduces (NVLink peer-memory kernels, or NCCL calls: see transport), "
                         "replayed as CUDA graph(s)",

@@ -194,6 +194,9 @@ class NNFOwithBayesianJumps(nn.Module):
         self.noise = "reference"
         self.event_group = int(os.environ.get("SF_EVENT_GROUP", "0"))   # > 0: at most this many samples per batched event
         self.noise_skip = 0                             # draws to discard first (batch sharding: samples of earlier ranks)
+        # the prior net is evaluated only where its sample is read (before an ode_step); the reference also evaluates it before
+        # a jump and after the last op, where nothing reads it (rollout.py).  SF_B200_ALL_PRIOR=1 evaluates it everywhere.
+        self.skip_dead_prior = os.environ.get("SF_B200_ALL_PRIOR", "0") != "1"
         self.cuda_graph = os.environ.get("SF_B200_CUDA_GRAPH", "0") == "1"   # capture / replay the whole rollout as one CUDA graph
         self.fused_codec = os.environ.get("SF_B200_FUSED_CODEC", "1") == "1"  # SmallEncoder / SmallDecoder on the conv-stage kernels
         self.__dict__["_codecs"] = {}
@@ -475,7 +478,8 @@ class NNFOwithBayesianJumps(nn.Module):
             dev = hx_obs.device
         plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-        ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all, max_group=self.event_group)
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), record_all=self.record_all, max_group=self.event_group,
+                             skip_dead_prior=self.skip_dead_prior)
         eng = self._engine_for(h, w, B, dev)
         T = len(targets[0])
         flat = [s for slots in ro.out_slots for s in slots]
@@ -555,14 +559,15 @@ class NNFOwithBayesianJumps(nn.Module):
         T = len(targets[0])
         cache = self.__dict__.setdefault("_stream_plans", {})
         sig = (id(eng), tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times), tuple(tuple(float(x) for x in t) for t in targets),
-               float(delta_t), self.use_variable_ode_step, self.solver, bool(self.impute), tuple(stamp_dtypes))
+               float(delta_t), self.use_variable_ode_step, self.solver, bool(self.impute), tuple(stamp_dtypes), bool(self.skip_dead_prior))
         plan = cache.get(sig)
         if plan is None:
             if len(cache) >= 8:
                 cache.clear()
             plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
             base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-            ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b)
+            ro = compile_rollout(plans, base, self.solver, bool(self.impute), obs_index=lambda b, k: k * B + b,
+                                 skip_dead_prior=self.skip_dead_prior)
             table, evs = eng.build_table(ro.events)
             tdev = eng.upload_table(table)
             slots_dev = torch.tensor([[ro.out_slots[b][t] for b in range(B)] for t in range(T)], dtype=torch.int32).to(dev)
@@ -692,7 +697,7 @@ class NNFOwithBayesianJumps(nn.Module):
         its own and never waits for the device (the pageable uploads of a fresh table would)."""
         key = (str(device), n, H, W, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
                tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), tuple(stamp_dtypes), self.precision, self.solver,
-               bool(self.use_variable_ode_step), bool(self.impute), self.event_group)
+               bool(self.use_variable_ode_step), bool(self.impute), self.event_group, bool(self.skip_dead_prior))
         B, T = len(obs_counts), len(targets[0])
         codec = self._codec_for(H, W, n, B * T, device)
         eng = self._engine_for(H // 4, W // 4, B, device)
@@ -704,7 +709,7 @@ class NNFOwithBayesianJumps(nn.Module):
             cache.clear()
         plans = [plan_sample(times[b], targets[b], delta_t, self.use_variable_ode_step, self.solver, *stamp_dtypes) for b in range(B)]
         base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-        ro = compile_rollout(plans, base, self.solver, bool(self.impute), max_group=self.event_group)
+        ro = compile_rollout(plans, base, self.solver, bool(self.impute), max_group=self.event_group, skip_dead_prior=self.skip_dead_prior)
         table, evs = eng.build_table(ro.events)
         flat = [s for slots in ro.out_slots for s in slots]
         ent = cache[key] = dict(codec=codec, eng=eng, ro=ro, evs=evs, tdev=eng.upload_table(table),

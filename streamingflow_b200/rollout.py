@@ -9,6 +9,14 @@ step would redraw the sampled input (SURVEY 7.3 'Schedule parity').
 
 Noise slots follow the reference's consumption order exactly: sample-major, then event order, one
 standard-normal tensor per infer_state call (two per midpoint step).
+
+Dead prior-net evaluations.  The reference calls ``infer_state`` (p_model + rsample) after EVERY op, but the sampled input it
+produces is read only by a following ``ode_step``: an observation jump feeds the cell the observation itself
+(``GRUObservationCell.forward(state, p, X_obs)`` ignores ``p``, temporal_ode_bayes.py:327-344) and nothing reads the input after
+the last op (:606-624 select and decode STATES).  ``skip_dead_prior`` (default) therefore runs the prior net only where its
+sample is consumed -- before a step, and inside a midpoint step -- which leaves every state, hence every output, bit-identical
+(the parity fixtures compare per-event states).  The noise slots are still numbered as if every call drew: the RNG stream of
+live draws is the reference's.
 """
 from __future__ import annotations
 
@@ -35,9 +43,12 @@ class Rollout:
 
 
 def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool,
-                    record_all: bool = False, obs_index=None, max_group: int = 0) -> Rollout:
+                    record_all: bool = False, obs_index=None, max_group: int = 0, skip_dead_prior: bool = True,
+                    keep_last_input: bool = False) -> Rollout:
     """record_all additionally records the state after EVERY op (debug / parity traces).  obs_index(b, k) overrides the
-    image index of sample b's k-th observation in the OBS buffer (default: sample-major obs_base[b] + k)."""
+    image index of sample b's k-th observation in the OBS buffer (default: sample-major obs_base[b] + k).
+    skip_dead_prior: do not evaluate the prior net after an op whose sampled input nothing reads (module docstring);
+    keep_last_input: the input sampled after the LAST op is live (a streaming session continues from it later)."""
     ro = Rollout()
     if obs_index is None:
         obs_index = lambda b, k: obs_base[b] + k
@@ -59,25 +70,29 @@ def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver
                     ro.n_path += 1
             ro.trace_slots.append([picked[i] for i in range(len(plan.ops))])
         evs: List[dict] = []
+        n_ops = len(plan.ops)
         for i, op in enumerate(plan.ops):
             rec = picked.get(i, -1)
+            # is the input sampled after this op read by anything?  only by a following ode_step
+            live = (plan.ops[i + 1].kind == STEP) if i + 1 < n_ops else keep_last_input
+            prior = bool(impute) and (live or not skip_dead_prior)
             if op.kind == JUMP:
                 evs.append(dict(kind=JUMP, x_buf=BUF_OBS, x_img=obs_index(b, op.obs), s_in=0, s_base=0, s_out=0, dt=0.0, eps=eps,
-                                rec=rec, run_prior=impute))
+                                rec=rec, run_prior=prior))
                 eps += 1
                 ro.n_jumps += 1
             else:
                 xb, xi = (BUF_X, b) if impute else (BUF_ZERO, 0)
                 if solver == "euler":
                     evs.append(dict(kind=STEP, x_buf=xb, x_img=xi, s_in=0, s_base=0, s_out=0, dt=op.dt, eps=eps, rec=rec,
-                                    run_prior=impute))
+                                    run_prior=prior))
                     eps += 1
                 elif solver == "midpoint":
                     # k = s + dt/2 f(x, s); pk = infer(k)   |   s = s + dt f(pk, k); x = infer(s)      (tob:449-454)
                     evs.append(dict(kind=STEP, x_buf=xb, x_img=xi, s_in=0, s_base=0, s_out=1, dt=op.dt / 2, eps=eps, rec=-1,
                                     run_prior=True))
                     evs.append(dict(kind=STEP, x_buf=BUF_X, x_img=b, s_in=1, s_base=0, s_out=0, dt=op.dt, eps=eps + 1, rec=rec,
-                                    run_prior=impute))
+                                    run_prior=prior))
                     eps += 2
                 else:
                     raise ValueError(f"Unknown solver '{solver}'.")

@@ -390,14 +390,15 @@ class RowShardedOde:
             self.arena = PeerArena(eng.lib, self.rank, self.world, self.group, self._halo_bytes_max(), self.B * 2 * eng.C)
             eng.alloc_gen += 1
         key = (B, tuple(obs_counts), tuple(tuple(float(x) for x in t) for t in times),
-               tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), ode.solver, bool(ode.impute), eng.precision)
+               tuple(tuple(float(x) for x in t) for t in targets), float(delta_t), ode.solver, bool(ode.impute), eng.precision,
+               bool(ode.skip_dead_prior))
         sched = self.__dict__.setdefault("_schedules", {}).get(key)
         if sched is None:
             if len(self._schedules) >= 8:
                 self._schedules.clear()
             plans = [plan_sample(times[b], targets[b], delta_t, ode.use_variable_ode_step, ode.solver) for b in range(B)]
             base = np.concatenate([[0], np.cumsum(obs_counts)[:-1]]).astype(int).tolist()
-            ro = compile_rollout(plans, base, ode.solver, bool(ode.impute))
+            ro = compile_rollout(plans, base, ode.solver, bool(ode.impute), skip_dead_prior=ode.skip_dead_prior)
             flat = torch.tensor([s for slots in ro.out_slots for s in slots], dtype=torch.int32, device=self.device)
             sched = self._schedules[key] = (ro, flat)
         ro, flat = sched

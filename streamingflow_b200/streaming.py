@@ -111,7 +111,10 @@ class StreamingOdeSession:
 
     def _run(self, plans: List[SamplePlan], latents: Optional[torch.Tensor]):
         ode, eng = self.ode, self.eng
-        ro = compile_rollout(plans, list(range(self.B)), ode.solver, bool(ode.impute))     # observation image of sample b = b
+        # observation image of sample b = b.  A push leaves the session's sampled input behind for whatever comes next (keep the
+        # last op's prior evaluation); a look-ahead is rolled back afterwards, its last input is dead
+        ro = compile_rollout(plans, list(range(self.B)), ode.solver, bool(ode.impute), skip_dead_prior=ode.skip_dead_prior,
+                             keep_last_input=latents is not None)
         if latents is not None:
             eng.bind_observations(latents)
         eng.ensure_path_slots(max(ro.n_path, 1))

@@ -82,6 +82,45 @@ def test_rollout_grouping_and_noise_order():
     assert steps[0]["x_buf"] == 4 and steps[0]["run_prior"] == 1 and steps[1]["x_buf"] == 2 and steps[1]["run_prior"] == 0
 
 
+def test_prior_net_runs_only_where_its_sample_is_read(golden_dir):
+    """compile_rollout evaluates the prior net (infer_state) only after ops whose sampled input a following ode_step reads: not
+    before a jump (GRUObservationCell ignores p, temporal_ode_bayes.py:327-344), not after the last op; noise slots keep the
+    reference's numbering; a streaming push keeps its last input alive; and the module's output (reference fixture) does not
+    depend on the switch."""
+    times = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
+    tg = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+    p = sc.plan_sample(times, tg, 0.05, True)
+    kinds = [o.kind for o in p.ops]
+    live = [i + 1 < len(kinds) and kinds[i + 1] == sc.STEP for i in range(len(kinds))]
+    ro = compile_rollout([p], [0], "euler", True)
+    full = compile_rollout([p], [0], "euler", True, skip_dead_prior=False)
+    assert [e["run_prior"] for e in ro.events] == [int(v) for v in live] and all(e["run_prior"] == 1 for e in full.events)
+    assert ro.n_prior_evals == sum(live) < full.n_prior_evals == len(kinds) == 18
+    assert [e["eps"] for e in ro.events] == [e["eps"] for e in full.events] and ro.n_eps == full.n_eps == 18
+    assert compile_rollout([p], [0], "euler", True, keep_last_input=True).events[-1]["run_prior"] == 1
+    mid = compile_rollout([p], [0], "midpoint", True)
+    firsts = [e for e in mid.events if e["kind"] == sc.STEP and e["s_out"] == 1]
+    assert firsts and all(e["run_prior"] == 1 for e in firsts)                    # pk = infer_state(k) feeds the second half step
+    assert compile_rollout([p], [0], "euler", False).n_prior_evals == 0
+    # the module on the reference's fixture, both settings: identical output
+    z = np.load(os.path.join(golden_dir, "tiny_full_c8.npz"))
+    C, H, B, seed = int(z["C"]), int(z["H"]), int(z["B"]), int(z["seed"])
+    outs = []
+    for skip in (True, False):
+        m = _tiny_module(z, torch.float64)
+        m.gru_ode.skip_dead_prior = skip
+        m.gru_ode._draw_noise = lambda n, h, w, device: torch.stack(
+            [so.recipe_array(f"eps{i}", (C, H // 4, H // 4), seed, torch.float64) for i in range(n)])
+        with torch.no_grad():
+            x, _ = m(torch.zeros(B, 1, C, H, H, dtype=torch.float64), so.recipe_array("cam", (B, 3, C, H, H), seed, torch.float64),
+                     so.recipe_array("lidar", (B, 5, C, H, H), seed, torch.float64), torch.from_numpy(z["camera_timestamp"]),
+                     torch.from_numpy(z["lidar_timestamp"]), torch.from_numpy(z["target_timestamp"]))
+        outs.append((x, m.gru_ode.last_rollout.n_prior_evals))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] < outs[1][1]
+    ref = torch.from_numpy(z["x_f64"])
+    assert ((outs[0][0] - ref).abs().max() / ref.abs().max()).item() < 1e-11
+
+
 @pytest.mark.parametrize("x3", [False, True])
 def test_packed_stage_plans_reproduce_the_convolutions(x3):
     """The chunk / tap / column plan + packed weight matrix the TMA ring streams, replayed on the host, equals F.conv2d."""
