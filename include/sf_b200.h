@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 2
+#define SF_ABI_VERSION 3
 
 typedef enum {
   SF_OK = 0,
@@ -275,6 +275,130 @@ int sf_head_1x1(const void* src_hi, const void* src_lo, const float* w, const fl
 /* bring-up of the back-to-back GEMM in the fused trunk epilogue: A [128 x 64] bf16 written to tensor memory by the threads
  * (tcgen05.st, two elements per column, at column a_col >= n), B [n x 64] from shared memory; d [128 x n] fp32 */
 int sf_diag_umma_ts(const void* a_bf16, const void* b_bf16, float* d, int n, int a_col, void* stream);
+
+/* =================================================================================================================
+ * The ODE head driven from this header alone (SURVEY 8b's proposed exports: sf_query_workspace, sf_pack_cell_weights,
+ * sf_pack_pmodel_weights, sf_event, sf_rollout -- the last two are sf_ode_event / sf_ode_rollout here because `sf_event` is the
+ * event struct).  streamingflow_b200/csrc/sf_ode.cu; pure host code on top of the sf_plan_* entry points above.
+ *
+ *   weights (host fp32, reference state_dict names)  --sf_pack_*-->  stage descriptions + packed bf16 matrices (host)
+ *   sf_ode_create: carves ONE caller-owned device allocation into the activation / fp32 / weight buffers, uploads the packed
+ *       weights, defines every stage, the two SE layers and the event graph on an sf_plan and finalises it
+ *   sf_rollout_plan_*: per-sample timestamps -> the batched event list + int32 event table (the host schedule of
+ *       temporal_ode_bayes.py:508,539-622, incl. the reference's float32 / float64 time arithmetic and its 1-ulp micro-steps)
+ *   sf_ode_rollout: enqueues every stage launch of the event list on `stream` (no sync, no allocation: graph-capturable)
+ * ================================================================================================================= */
+
+/* activation buffer ids of the ODE head's plan (the stage descriptions produced by sf_pack_* refer to them) */
+enum {
+  SF_BUF_S0 = 0, SF_BUF_S1, SF_BUF_X, SF_BUF_OBS, SF_BUF_ZERO, SF_BUF_U1, SF_BUF_U2, SF_BUF_G1, SF_BUF_G2, SF_BUF_A, SF_BUF_B,
+  SF_BUF_HH, SF_BUF_T1, SF_BUF_T2, SF_BUF_Q1, SF_BUF_Z1, SF_BUF_Y1, SF_BUF_Q3, SF_BUF_Z2, SF_BUF_Y2, SF_BUF_COUNT
+};
+/* chunk sources resolved per event: the event's x buffer, the bf16 mirror of the state buffer the cell reads / writes */
+#define SF_SRC_X (-1)
+#define SF_SRC_STATE_IN (-2)
+#define SF_SRC_STATE_OUT (-3)
+
+/* one named fp32 tensor in HOST memory, contiguous, in torch's own layout (conv weights [out][in][ky][kx]); `name` is the
+   reference's state_dict key below the ODE module, e.g. "gru_c.conv_update_1.weight" (temporal_ode_bayes.py:357-393) */
+typedef struct {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} sf_tensor;
+
+/* read-only view of one item of a packed stage list.  se_layer >= 0: the item is not a conv stage but marks where squeeze-excite
+   layer se_layer (res_models.py:150-165) sits in the launch order; then only name / se_layer / fc1 / fc2 are meaningful. */
+typedef struct {
+  const char* name;
+  int32_t se_layer;
+  int32_t epilogue, flags;
+  int32_t n_chunks;
+  const sf_chunk* chunks;
+  const void* w;            /* bf16 [w_rows][64], the matrix sf_plan_define_stage streams                              */
+  int32_t w_rows;
+  const float* vec;         /* per-stage constants (biases / LayerNorm / gate weights)                                 */
+  int32_t n_vec;
+  int32_t n_io;
+  const int32_t* io;
+  const int32_t* io_off;
+  int32_t fold_se;          /* >= 0: this stage consumes SE layer fold_se folded into its weights: w32 / row_meta are the
+                               arguments of sf_plan_define_stage_fold                                                  */
+  const float* w32;
+  const int32_t* row_meta;
+  const float* fc1;         /* SE marker: fc.0.weight [2C/8][2C], fc.2.weight [2C][2C/8], n_fc elements each           */
+  const float* fc2;
+  int32_t n_fc;
+} sf_stage_desc;
+
+typedef struct sf_packed sf_packed;
+#define SF_PACK_PAIR_ROWS 1   /* C = 64: row-paired taps in the 7x7 trunk (stage flag bit 9)                           */
+#define SF_PACK_B2B 2         /* C = 64: 7x7 + LN + GELU + 1x1 + LN + GELU as ONE stage (stage flag bit 10)            */
+#define SF_PACK_FOLD_SE 4     /* prior net: SE layers folded into their consumers' weights                             */
+/* One dual-GRU cell (prefix "gru_c." = derivative, temporal_ode_bayes.py:92-161; "gru_obs.gru_d." = observation jump, :239-305):
+   gates / propose / decode / trunk / mix stages with cat[state, state] of GRU-2 folded; channel width from the weights. */
+int sf_pack_cell_weights(const sf_tensor* tensors, int n_tensors, const char* prefix, int precision, int options, sf_packed** out);
+/* p_model = ConvNet(C, 2C) with eval-mode BatchNorm folded (prefix "p_model.", res_models.py:168-180): q1..q5 + the two SE markers */
+int sf_pack_pmodel_weights(const sf_tensor* tensors, int n_tensors, const char* prefix, int precision, int options, sf_packed** out);
+int sf_packed_count(const sf_packed* p);
+int sf_packed_get(const sf_packed* p, int i, sf_stage_desc* out);
+int sf_packed_free(sf_packed* p);
+
+typedef struct {
+  int32_t path_slots;     /* recorded states the PATH tensor holds                                                    */
+  int32_t obs_images;     /* encoded observation frames the OBS buffer holds                                          */
+  int32_t eps_slots;      /* noise tensors the EPS tensor holds                                                       */
+  int32_t pack_options;   /* SF_PACK_* (default: all three)                                                           */
+} sf_ode_options;
+
+typedef enum {            /* device tensors inside the workspace (sf_ode_tensor)                                      */
+  SF_ODE_OBS_HI = 0,      /* bf16 NHWC [obs_images][H][W][C]; fill with sf_pack_nchw_f32 or sf_ode_set_observations    */
+  SF_ODE_OBS_LO = 1,      /* its residual plane (BF16X3), else NULL                                                   */
+  SF_ODE_EPS = 2,         /* fp32 NCHW [eps_slots][C][H][W]; fill with sf_normal_fill_slots                           */
+  SF_ODE_PATH = 3,        /* fp32 NHWC [path_slots][H][W][C]; read with sf_unpack_nhwc_f32 or sf_ode_read_path        */
+  SF_ODE_STATE0 = 4,      /* fp32 NHWC [max_images][H][W][C]                                                          */
+  SF_ODE_STATE1 = 5,
+  SF_ODE_X32 = 6,         /* fp32 copy of the sampled input (events with want_f32)                                    */
+  SF_ODE_PARAMS32 = 7,    /* fp32 p_model output [max_images][H][W][2C] (events with want_f32)                        */
+  SF_ODE_ERRFLAG = 8      /* int32 word: non-zero after a device-side pipeline timeout                                */
+} sf_ode_tensor_id;
+
+typedef struct sf_ode sf_ode;
+/* bytes of the single device allocation sf_ode_create carves up (the library allocates no device memory itself) */
+int sf_ode_query_workspace(const sf_geometry* g, const sf_ode_options* o, size_t* bytes);
+/* tensors: the ODE module's parameters (gru_c.*, gru_obs.gru_d.*, p_model.*; others are ignored) with `prefix` stripped from
+   the front of each name (e.g. "gru_ode." when they come from FuturePredictionODE's state_dict).  Synchronous (uploads). */
+int sf_ode_create(const sf_geometry* g, const sf_ode_options* o, const sf_tensor* tensors, int n_tensors, const char* prefix,
+                  void* workspace, size_t workspace_bytes, sf_ode** out);
+int sf_ode_destroy(sf_ode* ode);
+int sf_ode_plan(sf_ode* ode, sf_plan** plan);                /* the underlying plan (stage-level access)              */
+int sf_ode_tensor(sf_ode* ode, int which, void** ptr, size_t* bytes);
+/* encoded observations, fp32 NCHW on the device -> images [first_image, first_image + n_images) of the OBS buffer */
+int sf_ode_set_observations(sf_ode* ode, const float* obs_nchw, int first_image, int n_images, void* stream);
+/* state buffers (fp32 masters and bf16 mirrors) of the first n_images samples back to zero (temporal_ode_bayes.py:505)  */
+int sf_ode_reset_state(sf_ode* ode, void* stream);
+/* ONE event (cell + state update + prior net + sampling) / a whole event list; `table` is the device copy of the event table */
+int sf_ode_event(sf_ode* ode, const sf_event* ev, const int32_t* table, void* stream);
+int sf_ode_rollout(sf_ode* ode, const sf_event* evs, int n_events, const int32_t* table, void* stream);
+/* recorded states `slots` (device int32 [n]) -> fp32 NCHW [n][C][H][W] on the device */
+int sf_ode_read_path(sf_ode* ode, const int32_t* slots, int n, float* out_nchw, void* stream);
+
+/* Host schedule: B samples, each with n_obs observation times (already in processing order, future_prediction_ode.py:37-45) and
+   n_targets target times.  obs_f32 / target_f32: the caller's timestamp tensors were float32 (the reference then compares and
+   steps in float32, see schedule.py).  solver: 0 euler, 1 midpoint.  flags: bit 0 keep the dead prior-net evaluations (the
+   reference's literal schedule), bit 1 keep the input sampled after the last op alive (streaming).
+   obs image index of sample b's k-th observation = b * n_obs + k. */
+typedef struct sf_rollout_plan sf_rollout_plan;
+typedef struct {
+  int32_t n_events, n_table, n_eps, n_path, n_state_steps, n_jumps, n_cell_evals, n_prior_evals;
+} sf_rollout_info;
+int sf_rollout_plan_create(const double* obs_times, int n_obs, const double* targets, int n_targets, int B, double delta_t,
+                           int variable_step, int solver, int impute, int obs_f32, int target_f32, int flags, sf_rollout_plan** out);
+int sf_rollout_plan_info(const sf_rollout_plan* r, sf_rollout_info* info);
+const sf_event* sf_rollout_plan_events(const sf_rollout_plan* r);
+const int32_t* sf_rollout_plan_table(const sf_rollout_plan* r);          /* host int32 [n_table]: upload before sf_ode_rollout */
+const int32_t* sf_rollout_plan_out_slots(const sf_rollout_plan* r);      /* [B][n_targets] path slot of every output frame     */
+int sf_rollout_plan_free(sf_rollout_plan* r);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsf_b200.so")
 
-SF_ABI_VERSION = 2
+SF_ABI_VERSION = 3
 PREC_BF16, PREC_BF16X3 = 0, 1
 (EPI_GATES, EPI_PROPOSE, EPI_DECODE, EPI_LNGELU, EPI_MIX, EPI_BIAS_LRELU, EPI_RES_PROJ, EPI_RES_ID, EPI_SAMPLE) = range(9)
 (F32_STATE0, F32_STATE1, F32_A, F32_B, F32_PATH, F32_SE_SUMS, F32_EPS, F32_X, F32_PARAMS, F32_ERRFLAG, F32_OUT, F32_IMG_BIAS) = range(12)
@@ -37,6 +37,30 @@ class Event(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("kind", "n_active", "x_buf", "s_in", "s_base", "s_out", "run_cell", "run_prior",
                                          "want_f32", "table_off")]
 
+
+class Tensor(C.Structure):
+    """sf_tensor: a named fp32 tensor in host memory (reference state_dict key, torch layout)."""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
+class StageDesc(C.Structure):
+    """sf_stage_desc: read-only view of one item of a packed stage list (sf_packed_get)."""
+    _fields_ = [("name", C.c_char_p), ("se_layer", C.c_int32), ("epilogue", C.c_int32), ("flags", C.c_int32), ("n_chunks", C.c_int32),
+                ("chunks", C.POINTER(Chunk)), ("w", C.c_void_p), ("w_rows", C.c_int32), ("vec", C.POINTER(C.c_float)), ("n_vec", C.c_int32),
+                ("n_io", C.c_int32), ("io", C.POINTER(C.c_int32)), ("io_off", C.POINTER(C.c_int32)), ("fold_se", C.c_int32),
+                ("w32", C.POINTER(C.c_float)), ("row_meta", C.POINTER(C.c_int32)), ("fc1", C.POINTER(C.c_float)), ("fc2", C.POINTER(C.c_float)), ("n_fc", C.c_int32)]
+
+
+class OdeOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("path_slots", "obs_images", "eps_slots", "pack_options")]
+
+
+class RolloutInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_events", "n_table", "n_eps", "n_path", "n_state_steps", "n_jumps", "n_cell_evals", "n_prior_evals")]
+
+
+PACK_PAIR_ROWS, PACK_B2B, PACK_FOLD_SE = 1, 2, 4
+(ODE_OBS_HI, ODE_OBS_LO, ODE_EPS, ODE_PATH, ODE_STATE0, ODE_STATE1, ODE_X32, ODE_PARAMS32, ODE_ERRFLAG) = range(9)
 
 EXPORTS = {
     "sf_abi_version": (C.c_int, []),
@@ -87,6 +111,29 @@ EXPORTS = {
                               C.c_void_p]),
     "sf_dwconv7_ln": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_aspp_pool_bias": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sf_pack_cell_weights": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sf_pack_pmodel_weights": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sf_packed_count": (C.c_int, [C.c_void_p]),
+    "sf_packed_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(StageDesc)]),
+    "sf_packed_free": (C.c_int, [C.c_void_p]),
+    "sf_ode_query_workspace": (C.c_int, [C.POINTER(Geometry), C.POINTER(OdeOptions), C.POINTER(C.c_size_t)]),
+    "sf_ode_create": (C.c_int, [C.POINTER(Geometry), C.POINTER(OdeOptions), C.POINTER(Tensor), C.c_int, C.c_char_p, C.c_void_p, C.c_size_t,
+                                C.POINTER(C.c_void_p)]),
+    "sf_ode_destroy": (C.c_int, [C.c_void_p]),
+    "sf_ode_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sf_ode_tensor": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "sf_ode_set_observations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "sf_ode_reset_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sf_ode_event": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_void_p, C.c_void_p]),
+    "sf_ode_rollout": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_ode_read_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_rollout_plan_create": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sf_rollout_plan_info": (C.c_int, [C.c_void_p, C.POINTER(RolloutInfo)]),
+    "sf_rollout_plan_events": (C.POINTER(Event), [C.c_void_p]),
+    "sf_rollout_plan_table": (C.POINTER(C.c_int32), [C.c_void_p]),
+    "sf_rollout_plan_out_slots": (C.POINTER(C.c_int32), [C.c_void_p]),
+    "sf_rollout_plan_free": (C.c_int, [C.c_void_p]),
     "sf_diag_tma_dump": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "sf_diag_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_diag_umma_ts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsf_b200.so")
 STAMP = OUT + ".stamp"
-SOURCES = ["sf_plan.cu", "sf_diag.cu"]
+SOURCES = ["sf_plan.cu", "sf_diag.cu", "sf_ode.cu"]
 HEADERS = ["sf_ptx.cuh", "sf_conv.cuh", "sf_elementwise.cuh", "sf_peer.cuh", os.path.join("..", "..", "include", "sf_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

@@ -470,6 +470,8 @@ extern "C" {
 
 int sf_abi_version(void) { return SF_ABI_VERSION; }
 const char* sf_last_error(void) { return g_err.c_str(); }
+// the other translation units of the library (sf_ode.cu) report their failures through the same thread-local string
+void sf_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 int sf_device_supported(int device) {
   cudaDeviceProp prop;

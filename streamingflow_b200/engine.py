@@ -418,57 +418,60 @@ class OdeEngine:
     def load_weights(self, sd: Dict[str, torch.Tensor], prefix: str):
         """(Re)packs every stage from reference-named parameters ``{prefix}gru_c.*``, ``{prefix}gru_obs.gru_d.*``,
         ``{prefix}p_model.*``."""
-        sd = {k: v.detach().to(self.device) for k, v in sd.items() if k.startswith(prefix)}
+        from . import cpack
+
+        sd = {k: v.detach() for k, v in sd.items() if k.startswith(prefix)}
         pre = prefix
         # captured CUDA graphs hold the addresses of the packed weights / vectors released below: retire them
         self.alloc_gen = getattr(self, "alloc_gen", 0) + 1
         self._keep = []
-        self.stage_defs: Dict[int, StageDef] = {}
+        self.stage_defs: Dict[int, object] = {}          # slot -> cpack.PackedItem (name, epilogue, chunks, flags, ...)
         self.stage_names: Dict[int, str] = {}
         pair = os.environ.get("SF_PAIR_ROWS", "1") != "0"
         b2b = os.environ.get("SF_B2B", "1") != "0"
-        cells = [cell_stage_defs(sd, pre + "gru_c", pair, b2b), cell_stage_defs(sd, pre + "gru_obs.gru_d", pair, b2b)]
+        # BatchNorm / cat[state, state] folding, tap order and the hi / lo split happen in the library (sf_pack_cell_weights,
+        # sf_pack_pmodel_weights: csrc/sf_ode.cu) -- the same bytes a C host gets; cell_stage_defs / prior_stage_defs / pack_stage
+        # above restate them in torch and are pinned to the library's output by tests/test_c_host.py
+        cells = [cpack.pack_cell(sd, pre + "gru_c.", self.x3, pair, b2b), cpack.pack_cell(sd, pre + "gru_obs.gru_d.", self.x3, pair, b2b)]
         n_cell = len(cells[0])
         cell_slots = [list(range(ws * n_cell, (ws + 1) * n_cell)) for ws in range(2)]
         for ws in range(2):
-            for slot, sdef in zip(cell_slots[ws], cells[ws]):
-                self.stage_defs[slot] = sdef
+            for slot, item in zip(cell_slots[ws], cells[ws]):
+                self.stage_defs[slot] = item
                 if ws == 0:
-                    self.stage_names[slot] = sdef.name
-        prior_items, slot = [], 2 * n_cell
-        for it in prior_stage_defs(sd, pre + "p_model", fold_se=self.se_fold):
-            if isinstance(it, str):
-                prior_items.append((L.SE_FOLD_ITEM_BASE if self.se_fold else L.SE_ITEM_BASE) + int(it[2]))
-                self.stage_names[prior_items[-1]] = "se" + str(int(it[2]) + 1)
+                    self.stage_names[slot] = item.name
+        prior_items, slot, se_items = [], 2 * n_cell, []
+        for it in cpack.pack_pmodel(sd, pre + "p_model.", self.x3, self.se_fold):
+            if it.se_layer >= 0:
+                prior_items.append((L.SE_FOLD_ITEM_BASE if self.se_fold else L.SE_ITEM_BASE) + it.se_layer)
+                self.stage_names[prior_items[-1]] = "se" + str(it.se_layer + 1)
+                se_items.append(it)
             else:
                 self.stage_defs[slot] = it
                 self.stage_names[slot] = it.name
                 prior_items.append(slot)
                 slot += 1
         self.cell_slots, self.prior_items = cell_slots, prior_items
-        for slot, sdef in self.stage_defs.items():
-            chunks, wp = pack_stage(sdef, self.x3)
-            vec = sdef.vec.to(torch.float32).contiguous()
-            arr = (L.Chunk * len(chunks))(*[L.Chunk(**c) for c in chunks])
-            io = (C.c_int32 * max(1, len(sdef.io)))(*sdef.io)
-            io_off = (C.c_int32 * max(1, len(sdef.io)))(*sdef.io_off)
+        for slot, item in self.stage_defs.items():
+            wp = item.w.to(self.device)
+            vec = item.vec.to(self.device, torch.float32).contiguous()
+            arr = (L.Chunk * len(item.chunks))(*[L.Chunk(**c) for c in item.chunks])
+            io = (C.c_int32 * max(1, len(item.io)))(*item.io)
+            io_off = (C.c_int32 * max(1, len(item.io)))(*item.io_off)
             self._keep += [wp, vec]
-            L.check(self.lib.sf_plan_define_stage(self.plan, slot, sdef.epilogue, len(chunks), arr, wp.data_ptr(), wp.shape[0],
-                                                  vec.data_ptr(), vec.numel(), io, io_off, len(sdef.io), sdef.flags),
-                    f"sf_plan_define_stage({slot}:{sdef.name})")
-            if sdef.fold_se is not None:
-                w32, meta = pack_stage_master(sdef, self.x3)
-                assert w32.shape[0] == wp.shape[0]
-                w32, meta = w32.to(self.device), meta.to(self.device)
+            L.check(self.lib.sf_plan_define_stage(self.plan, slot, item.epilogue, len(item.chunks), arr, wp.data_ptr(), wp.shape[0],
+                                                  vec.data_ptr(), vec.numel(), io, io_off, len(item.io), item.flags),
+                    f"sf_plan_define_stage({slot}:{item.name})")
+            if item.fold_se is not None:
+                w32, meta = item.w32.to(self.device), item.row_meta.to(self.device)
                 scaled = torch.zeros((self.max_images, wp.shape[0], 64), dtype=torch.bfloat16, device=self.device)
                 self._keep += [w32, meta, scaled]
-                L.check(self.lib.sf_plan_define_stage_fold(self.plan, slot, sdef.fold_se, w32.data_ptr(), meta.data_ptr(), scaled.data_ptr()),
-                        f"sf_plan_define_stage_fold({slot}:{sdef.name})")
-        for which, (idx, zin, yout) in enumerate(((1, BUF_Z1, BUF_Y1), (3, BUF_Z2, BUF_Y2))):
-            fc1 = sd[f"{pre}p_model.model.{idx}.fc.0.weight"].float().contiguous()
-            fc2 = sd[f"{pre}p_model.model.{idx}.fc.2.weight"].float().contiguous()
+                L.check(self.lib.sf_plan_define_stage_fold(self.plan, slot, item.fold_se, w32.data_ptr(), meta.data_ptr(), scaled.data_ptr()),
+                        f"sf_plan_define_stage_fold({slot}:{item.name})")
+        for it, (zin, yout) in zip(se_items, ((BUF_Z1, BUF_Y1), (BUF_Z2, BUF_Y2))):
+            fc1, fc2 = it.fc1.to(self.device), it.fc2.to(self.device)
             self._keep += [fc1, fc2]
-            L.check(self.lib.sf_plan_define_se(self.plan, which, fc1.data_ptr(), fc2.data_ptr(), zin, yout), "sf_plan_define_se")
+            L.check(self.lib.sf_plan_define_se(self.plan, it.se_layer, fc1.data_ptr(), fc2.data_ptr(), zin, yout), "sf_plan_define_se")
         i32 = lambda v: (C.c_int32 * len(v))(*v)
         L.check(self.lib.sf_plan_define_event_graph(self.plan, i32(cell_slots[0]), i32(cell_slots[1]), n_cell,
                                                     i32(prior_items), len(prior_items)), "sf_plan_define_event_graph")

@@ -350,7 +350,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     from streamingflow_b200 import _lib
 
     header = open(os.path.join(ROOT, "include", "sf_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(sf_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|const char\*|const sf_event\*|const int32_t\*)\s+(sf_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     assert os.path.exists(_lib.LIB_PATH), "libsf_b200.so not built: run __graft_entry__.build()"
     lib = ctypes.CDLL(_lib.LIB_PATH)
