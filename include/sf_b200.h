@@ -238,6 +238,12 @@ int sf_unpack_nhwc_f32(const float* src, float* dst, const int32_t* slots, int n
 int sf_normal_policy(long long numel, int device, int* grid, int* offset_per_slot);
 int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long long seed, unsigned long long offset0, int grid,
                          int offset_per_slot, void* stream);
+/* The same for a subset: only the slots listed in slot_list (device int32 [n_list], indices into the same slot numbering) are filled,
+   each exactly as sf_normal_fill_slots would fill it.  A rollout that skips the prior-net evaluations nothing reads (the reference
+   draws for them too, temporal_ode_bayes.py:463-477 after every op) leaves those slots untouched; the caller still advances the
+   generator by the full slot count, so the live draws are the reference's.                                                        */
+int sf_normal_fill_slot_list(float* out, const int32_t* slot_list, int n_list, long long numel, unsigned long long seed,
+                             unsigned long long offset0, int grid, int offset_per_slot, void* stream);
 
 /* SmallEncoder / SmallDecoder glue on NHWC bf16 planes: 2x2 max-pool (res_models.py:96-104), nearest x2 up-sampling
    (:134-147; call once per plane), fp32 NHWC (gathered by slot) -> bf16 hi [+ lo] */

@@ -102,6 +102,7 @@ EXPORTS = {
     "sf_unpack_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_normal_policy": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sf_normal_fill_slots": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]),
+    "sf_normal_fill_slot_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]),
     "sf_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_upsample2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sf_cast_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -217,13 +217,16 @@ __global__ void __launch_bounds__(256) se_fold_kernel(const float* __restrict__ 
 // curand_init(seed, idx, offset) followed by k curand_normal4 draws evaluates Philox at counter (offset / 4 + k) of subsequence
 // idx (offset is a multiple of 4 here: ATen advances it by 4 per loop iteration); curand itself evaluates two extra blocks per
 // thread (one in each skipahead, one look-ahead per draw), so the counters are formed directly.
+// slot_list (optional): only the listed slots are filled -- a rollout that skips dead prior-net evaluations never reads the others
 __global__ void __launch_bounds__(256) normal_slots_kernel(float* __restrict__ out, long long numel, unsigned long long seed,
-                                                           unsigned long long offset0, unsigned int per_slot, int n_slots) {
+                                                           unsigned long long offset0, unsigned int per_slot, int n_slots,
+                                                           const int* __restrict__ slot_list) {
   const unsigned int idx = blockIdx.x * 256u + threadIdx.x;
   const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
   const long long T = (long long)gridDim.x * 256;
   const long long rounded = ((numel - 1) / (T * 4) + 1) * T * 4;
-  for (int slot = blockIdx.y; slot < n_slots; slot += gridDim.y) {      // a block walks several slots: fewer, longer-lived blocks
+  for (int si = blockIdx.y; si < n_slots; si += gridDim.y) {      // a block walks several slots: fewer, longer-lived blocks
+    const int slot = slot_list ? slot_list[si] : si;
     unsigned long long ctr = (offset0 + (unsigned long long)slot * per_slot) >> 2;
     float* o = out + (long long)slot * numel;
     for (long long li = idx; li < rounded && li < numel; li += T * 4, ++ctr) {      // li >= numel: none of the 4 outputs is stored

@@ -891,7 +891,20 @@ int sf_normal_fill_slots(float* out, int n_slots, long long numel, unsigned long
   // about 8 waves of resident blocks in total; each block row walks n_slots / grid.y slots
   int rows = (8 * 148 * 8 + grid - 1) / grid;
   if (rows > n_slots) rows = n_slots;
-  normal_slots_kernel<<<dim3(grid, rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot, n_slots);
+  normal_slots_kernel<<<dim3(grid, rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot, n_slots,
+                                                                                            nullptr);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+int sf_normal_fill_slot_list(float* out, const int32_t* slot_list, int n_list, long long numel, unsigned long long seed, unsigned long long offset0,
+                             int grid, int offset_per_slot, void* stream) {
+  if (!out || !slot_list || n_list <= 0 || numel <= 0 || grid <= 0 || offset_per_slot <= 0 || n_list > 65535) return fail(SF_ERR_INVALID, "bad normal fill arguments");
+  if ((offset0 & 3) || (offset_per_slot & 3)) return fail(SF_ERR_INVALID, "Philox offsets must be multiples of 4 (ATen's generator invariant)");
+  int rows = (8 * 148 * 8 + grid - 1) / grid;
+  if (rows > n_list) rows = n_list;
+  normal_slots_kernel<<<dim3(grid, rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, numel, seed, offset0, (unsigned int)offset_per_slot, n_list,
+                                                                                            slot_list);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -276,10 +276,13 @@ class NNFOwithBayesianJumps(nn.Module):
                 sd[f"{name}.{k}"] = v
         return sd
 
-    def _draw_noise(self, n, h, w, device, out=None):
+    def _draw_noise(self, n, h, w, device, out=None, live=None):
         """Standard-normal tensors in the reference's order: one ``torch.empty([1,C,h,w]).normal_()`` per infer_state call
         (torch.distributions.Normal.rsample -> _standard_normal), here drawn in place into one [n, C, h, w] buffer
-        (``out``: an existing buffer of at least that size, e.g. the static noise buffer of a captured graph)."""
+        (``out``: an existing buffer of at least that size, e.g. the static noise buffer of a captured graph).
+        ``live``: device int32 list of the slots the rollout reads (``Rollout.live_eps``); the others -- draws of prior-net
+        evaluations nothing consumes -- are not produced (their slots keep whatever they held), the generator still advances
+        over all n, so every live draw is the reference's."""
         eps = out if out is not None else torch.empty((max(n, 1), self.hidden_size, h, w), dtype=torch.float32, device=device)
         if device.type == "cuda" and self.noise != "bulk" and not torch.cuda.is_current_stream_capturing():
             # one launch for all n slots, bit-identical to n successive normal_() calls (sf_normal_fill_slots reproduces torch's
@@ -292,7 +295,12 @@ class NNFOwithBayesianJumps(nn.Module):
             L.check(lib.sf_normal_policy(numel, gen.device.index, ctypes.byref(grid), ctypes.byref(per)), "sf_normal_policy")
             seed, off = gen.initial_seed(), gen.get_offset() + self.noise_skip * per.value
             self.noise_skip = 0
-            if n > 0:
+            if n > 0 and live is not None:
+                if live.numel() > 0:
+                    with torch.cuda.device(device):
+                        L.check(lib.sf_normal_fill_slot_list(eps.data_ptr(), live.data_ptr(), live.numel(), numel, seed, off, grid.value, per.value,
+                                                             ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "sf_normal_fill_slot_list")
+            elif n > 0:
                 with torch.cuda.device(device):
                     L.check(lib.sf_normal_fill_slots(eps.data_ptr(), n, numel, seed, off, grid.value, per.value,
                                                      ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "sf_normal_fill_slots")
@@ -324,10 +332,19 @@ class NNFOwithBayesianJumps(nn.Module):
         for _ in range(n):
             buf.normal_()
 
-    def _noise_into(self, buf, n, h, w, device):
+    @staticmethod
+    def live_noise_slots(ro, device, cache: dict):
+        """Device list of the noise slots rollout ``ro`` reads, kept in ``cache`` (a per-schedule dict); None when it reads all."""
+        if len(ro.live_eps) >= ro.n_eps or os.environ.get("SF_B200_ALL_NOISE", "0") == "1":
+            return None
+        if cache.get("live_eps") is None:
+            cache["live_eps"] = torch.tensor(ro.live_eps, dtype=torch.int32).to(device)
+        return cache["live_eps"]
+
+    def _noise_into(self, buf, n, h, w, device, live=None):
         """Draws the rollout's noise into ``buf`` (the static noise buffer of captured graphs)."""
         try:
-            noise = self._draw_noise(n, h, w, device, out=buf)
+            noise = self._draw_noise(n, h, w, device, out=buf, live=live)
         except TypeError:                                  # a test double with the four-argument signature
             noise = self._draw_noise(n, h, w, device)
         if noise.data_ptr() != buf.data_ptr():
@@ -534,7 +551,7 @@ class NNFOwithBayesianJumps(nn.Module):
         eng.bind_eps(ent["eps"])
         # Around the replay, eagerly: the noise of the whole rollout (one launch, the reference's Philox stream), the layout pack
         # of the caller's observations and the gathers into fresh output tensors -- no staging copy, no clone of the results.
-        self._noise_into(ent["eps"], ro.n_eps, h, w, hx_obs.device)
+        self._noise_into(ent["eps"], ro.n_eps, h, w, hx_obs.device, live=self.live_noise_slots(ro, hx_obs.device, ent))
         eng.pack_into(3, hx_obs)
         ent["graph"].replay()
         ro.launches = ent["launches"]
@@ -598,7 +615,7 @@ class NNFOwithBayesianJumps(nn.Module):
         eng.zero_state(0)
         if graphs is not None:
             eng.bind_eps(plan["eps"])
-            self._noise_into(plan["eps"], ro.n_eps, h, w, dev)
+            self._noise_into(plan["eps"], ro.n_eps, h, w, dev, live=self.live_noise_slots(ro, dev, plan))
         else:
             eng.bind_eps(self._draw_noise(ro.n_eps, h, w, dev))
         if out_host is None:

@@ -100,7 +100,7 @@ class FuturePredictionODE(nn.Module):
                                                launches=ro.launches + codec.launches + refine.launches)
             codec.launches = refine.launches = 0
         torch.stack(frames, dim=0, out=ent["static_in"])
-        ode._noise_into(ent["eps"], ro.n_eps, H // 4, W // 4, dev)
+        ode._noise_into(ent["eps"], ro.n_eps, H // 4, W // 4, dev, live=ode.live_noise_slots(ro, dev, ent))
         ent["graph"].replay()
         ro.launches = ent["launches"]
         ode.last_rollout = ro

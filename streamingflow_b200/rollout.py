@@ -40,6 +40,7 @@ class Rollout:
     n_cell_evals: int = 0
     n_prior_evals: int = 0
     trace_slots: List[List[int]] = field(default_factory=list)  # record_all: per sample, per op: path slot
+    live_eps: List[int] = field(default_factory=list)      # noise slots some prior-net evaluation reads (all of them unless dead evaluations are skipped)
 
 
 def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver: str, impute: bool,
@@ -99,6 +100,7 @@ def compile_rollout(plans: Sequence[SamplePlan], obs_base: Sequence[int], solver
                 ro.n_state_steps += 1
         per_sample.append(evs)
     ro.n_eps = eps
+    ro.live_eps = sorted(e["eps"] for evs in per_sample for e in evs if e["run_prior"])
     depth = max((len(e) for e in per_sample), default=0)
     for r in range(depth):
         groups: Dict[Tuple, dict] = {}

@@ -338,6 +338,42 @@ def test_cuda_graph_rollout_equals_eager_including_the_noise_stream():
     assert not torch.equal(outs[True][1], outs[True][5])                      # a and c saw different noise
 
 
+def test_only_the_noise_slots_a_rollout_reads_are_drawn():
+    """With the dead prior-net evaluations skipped, sf_normal_fill_slot_list draws only the slots some evaluation reads: the live
+    slots hold exactly what the reference's successive normal_() calls put there, the dead ones are never written (they stay
+    NaN-poisoned here) and never read (no NaN reaches the output, which equals the run that draws everything), and the generator
+    ends where the reference's ends."""
+    m = _nnfo("euler", True, True, 5, 1.0, "bf16")
+    h = w = 24
+    times = [sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])] * 2
+    targets = [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]] * 2
+    hx = torch.tanh(so.recipe_array("hx1", (16, 64, h, w), 5)).cuda()
+    m.cuda_graph = True
+    with torch.no_grad():
+        m.integrate_latents(hx, [8, 8], times, targets, 0.05)                 # capture
+    (ent,) = m._graphs.values()
+    ro = m.last_rollout
+    assert 0 < len(ro.live_eps) < ro.n_eps and ro.n_prior_evals == len(ro.live_eps)
+    ent["eps"].fill_(float("nan"))
+    torch.manual_seed(91)
+    with torch.no_grad():
+        got = m.integrate_latents(hx, [8, 8], times, targets, 0.05)
+    tail = torch.randn(4, device="cuda")
+    eps = ent["eps"].clone()
+    torch.manual_seed(91)
+    ref = torch.stack([torch.empty(64, h, w, device="cuda").normal_() for _ in range(ro.n_eps)])
+    tail_ref = torch.randn(4, device="cuda")
+    live = torch.zeros(ro.n_eps, dtype=torch.bool)
+    live[ro.live_eps] = True
+    assert torch.equal(eps[live], ref[live]) and bool(torch.isnan(eps[~live]).all()) and torch.equal(tail, tail_ref)
+    m.cuda_graph = False                                                       # the eager path draws every slot
+    torch.manual_seed(91)
+    with torch.no_grad():
+        want = m.integrate_latents(hx, [8, 8], times, targets, 0.05)
+    for a, b in zip(got, want):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
 def test_forward_graph_equals_eager_forward_including_the_noise_stream():
     """FuturePredictionODE.forward replayed as ONE CUDA graph (encoder, step loop, decoder, refinement) == the eager launch
     sequence bit for bit: two consecutive calls on torch's own Philox stream, new inputs through the same graph, and a recapture
