@@ -144,6 +144,10 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
    bit 12 (propose) the output is the GRU-ODE derivative u (s~ - s) instead of the blend; with activation code 2 in bits 1-3 the
    proposal is ReLU(conv + bias) (the plain SpatialGRUODECell / SpatialGRUCell, temporal_ode_bayes.py:14-61, 165-208);
    bit 11 (res_id) the activation is applied after the residual add: out = act(conv + bias + residual) (ResNet BasicBlock);
+   bit 13 (res_id, C = 64, bf16) the ConvNeXt block's pointwise pair in ONE launch (convolutions.py:334-344): the stage's conv is
+   pwconv1 (one 1x1 chunk, n = 256), the epilogue applies GELU, keeps the 256-channel result in tensor memory as the A operand of
+   pwconv2 (its [64][256] weights -- layer scale folded -- appended to w_packed as four K-chunks of [64 n][64 k] rows) and adds the
+   residual: out = pwconv2(GELU(pwconv1(x) + b1)) + b2 + residual; vec = [b1 (256), b2 (64)];
    bit 10 (lngelu, C = 64) a 1x1 convolution + LayerNorm + GELU fused behind the stage (convolutions.py:356-361 in ONE launch):
    its [C][64] weights (hi rows, then lo rows in BF16X3) are the LAST rows of w_packed and vec = [LN1 w, LN1 b, LN2 w, LN2 b];
    the epilogue keeps the first LN+GELU result in tensor memory as the A operand of a back-to-back GEMM.                */

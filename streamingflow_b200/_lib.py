@@ -19,6 +19,7 @@ FLAG_PAIR_ROWS = 512          # lngelu stages at C = 64: vertically adjacent tap
 FLAG_ACT_AFTER_RES = 2048     # res_id: out = act(conv + bias + residual) (ResNet BasicBlock) instead of act(conv + bias) + residual
 FLAG_DERIV = 4096             # propose: output u (s~ - s) (GRU-ODE derivative) instead of the blended state
 FLAG_B2B = 1024               # lngelu stages at C = 64: a 1x1 conv + LN + GELU fused behind the stage (weights appended to w_packed)
+FLAG_PW_B2B = 8192            # res_id at C = 64 (bf16): pwconv1 -> GELU -> pwconv2 -> + residual of the ConvNeXt block in ONE launch
 SRC_X, SRC_STATE_IN, SRC_STATE_OUT = -1, -2, -3
 SE_MAX_PARTIALS = 160        # SF_SE_MAX_PARTIALS in include/sf_b200.h
 SE_ITEM_BASE = 1000          # event-graph item: SE reduce + apply (activation pass)

@@ -101,9 +101,12 @@ struct alignas(64) StageParams {
 
 // M-tiles per CTA tile: 256-column launches get 1, the rest 2 (accumulator slot = 256 / MT columns).  CG = hidden channels.
 __host__ __device__ constexpr int mtiles_for(int epi, int CG) {
-  return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ || (CG == 128 && (epi == SF_EPI_MIX || epi == SF_EPI_SAMPLE))) ? 1 : 2;
+  return (epi == SF_EPI_GATES || epi == SF_EPI_RES_PROJ || epi == 12 /* SF_EPI_PW_B2B */ || (CG == 128 && (epi == SF_EPI_MIX || epi == SF_EPI_SAMPLE))) ? 1 : 2;
 }
 constexpr int ACC_STAGES = 2;
+// epilogue warpgroups per accumulator slot: the fused pointwise pair (256 GELUs per pixel: ALU / MUFU bound) splits a slot's columns
+// between two warpgroups (warps with equal warp % 4 share a TMEM lane quadrant)
+__host__ __device__ constexpr int wgs_per_slot(int epi) { return epi == 12 /* SF_EPI_PW_B2B */ ? 2 : 1; }
 __host__ __device__ constexpr int a_box_bytes(int R, int MT) { return (TILE_H + R - 1) * (TILE_W * MT + R - 1) * ROW_BYTES; }
 
 // ------------------------------------------------------------------------------------------------
@@ -157,12 +160,17 @@ constexpr int SF_EPI_RES_ID_ACT = 10;
 // lngelu followed, inside the same epilogue, by a 1x1 convolution + LayerNorm + GELU (the Bottleblock's layers 0..5 in one
 // launch): a back-to-back GEMM whose A operand is written to tensor memory by the epilogue threads (stage flag 1024)
 constexpr int SF_EPI_LNGELU_B2B = 11;
-constexpr int SF_EPI_KERNELS = 12;
+// res_id whose conv is the ConvNeXt block's pwconv1 (1x1, C -> 4C): GELU and pwconv2 (4C -> C) run inside the epilogue as a
+// back-to-back GEMM on tensor-memory A operands, so the 4C-channel intermediate never leaves the SM (stage flag 8192)
+constexpr int SF_EPI_PW_B2B = 12;
+constexpr int SF_EPI_KERNELS = 13;
+__host__ __device__ constexpr bool epi_has_b2b(int epi) { return epi == SF_EPI_LNGELU_B2B || epi == SF_EPI_PW_B2B; }
 
 // per-warpgroup state of the back-to-back GEMM (shared-window addresses; phase = parity of the group's completion barrier)
 struct B2BCtx {
   uint32_t w_smem, w_full, done_bar, phase;
   bool w_ready;
+  uint32_t peer_done;      // the completion barrier of the slot's other warpgroup (stages with two warpgroups per slot)
 };
 
 // v = act(v + b) on a 16-channel slice; the activation code is uniform per launch, so the switch is taken once per slice
@@ -226,6 +234,7 @@ struct PixelCtx {
   bool valid;
   size_t pix;    // (sid*H + y)*W + x
   int wg, m;     // epilogue warpgroup index and the thread's index in it (= TMEM lane)
+  int sub;       // which of the slot's warpgroups this is (stages with wgs_per_slot > 1)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -567,6 +576,63 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
         store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
       }
     }
+  } else if constexpr (EPI == SF_EPI_PW_B2B) {
+    // ConvNeXt block, pointwise pair (convolutions.py:334-344): columns [0, 4C) = pwconv1 (1x1, C -> 4C) of this pixel.
+    // The slot's TWO warpgroups each own one half of 2C columns (sub = 0 / 1): GELU(acc + b1) goes back into the columns it came
+    // from as packed bf16 pairs (the first C of the half: a slice is read before the narrower slice that replaces it is written) --
+    // the A operand [128 pixels x 2C] of that half of pwconv2, whose [C x 4C] weights (layer scale folded, four K-chunks of
+    // [C rows x 64]) stay in shared memory for the whole launch.  One thread of the warpgroup issues the half's 2C/16 MMAs into the
+    // half's upper C columns (dead once the half has been read) and commits to the warpgroup's barrier; both warpgroups then wait for
+    // BOTH partial products and each finishes C/2 output channels: out = part0 + part1 + gamma b2 + residual (the block's input).
+    // vec = [b1 (4C) | gamma * b2 (C)]; b2b.peer_done = the other warpgroup's barrier.
+    static_assert(CG == 64 && !X3, "the fused pointwise pair is built for 64 channels, bf16 operands");
+    const size_t o0 = c.pix * e.out_cs[0] + e.out_co[0], i0 = c.pix * e.in_cs[0] + e.in_co[0];
+    constexpr uint32_t B_HI = 64u | (1u << 14) | (2u << 29);       // SBO = 1024 B, version 1, SWIZZLE_128B
+    const uint32_t idesc = make_idesc_bf16(128, CG);
+    const uint32_t w_lo = (b2b.w_smem & 0x3FFFFu) >> 4;
+    const uint32_t half = (uint32_t)c.sub;
+    const uint32_t base = taddr + half * 2 * CG;
+#pragma unroll 1
+    for (int j = 0; j < 2 * CG / 16; ++j) {
+      float v[16], b[16];
+      tmem_ld16(base + j * 16, v);
+      vec16(vec, (int)half * 2 * CG + j * 16, b);
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i] + b[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      tmem_st8(base + j * 8, h);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
+    if (c.m == 0) {
+      tc_fence_after();
+      if (!b2b.w_ready) mbar_wait(b2b.w_full, 0, p.err, 7);
+#pragma unroll
+      for (uint32_t k = 0; k < 2 * CG / 16; ++k)      // K-chunk 2 half + k / 4 (8 KB = 512 descriptor units apart), 16-wide step k % 4
+        umma_bf16_ts(base + CG, base + 8 * k, ((uint64_t)B_HI << 32) | (w_lo + (2 * half + (k >> 2)) * ((CG * ROW_BYTES) >> 4) + 2 * (k & 3)), idesc,
+                     k ? 1u : 0u);
+      umma_commit(b2b.done_bar);
+    }
+    b2b.w_ready = true;
+    mbar_wait(b2b.done_bar, b2b.phase, p.err, 8);
+    mbar_wait(b2b.peer_done, b2b.phase, p.err, 9);
+    b2b.phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = (int)half * (CG / 32); j < ((int)half + 1) * (CG / 32); ++j) {
+      float v[16], q[16], r[16], b[16];
+      if (c.valid) load_act16<X3>(e.in_h[0], e.in_l[0], i0 + j * 16, r); else zero16(r);
+      tmem_ld16x2(taddr + CG + j * 16, taddr + 3 * CG + j * 16, v, q);
+      vec16(vec, 4 * CG + j * 16, b);
+      if (c.valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ((v[i] + q[i]) + b[i]) + r[i];
+        store_act16<X3>(e.out_h[0], e.out_l[0], o0 + j * 16, v);
+      }
+    }
   } else if constexpr (EPI == SF_EPI_SAMPLE) {
     // columns: [0,CG) loc | [CG,2CG) raw scale ; vec = conv bias (2CG); eps is NCHW [slot][CG][H][W]
     const size_t hw = (size_t)p.H * p.W;
@@ -608,10 +674,11 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
 // the stage kernel
 // ------------------------------------------------------------------------------------------------
 template <int EPI, bool X3, int CG>
-__global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
+__global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) * wgs_per_slot(EPI), 1) conv_stage_kernel(const __grid_constant__ StageParams p) {
   constexpr int S = ACC_STAGES;
   constexpr int MT = mtiles_for(EPI, CG);
-  constexpr int NGROUPS = S * MT;                       // epilogue warpgroups = accumulator slots
+  constexpr int WGS = wgs_per_slot(EPI);                // epilogue warpgroups per accumulator slot
+  constexpr int NGROUPS = S * MT * WGS;                 // epilogue warpgroups
   constexpr uint32_t STAGE_COLS = TMEM_COLS / S;        // 256
   constexpr uint32_t SLOT_COLS = STAGE_COLS / MT;       // 256 or 128
   extern __shared__ uint8_t smem_raw[];
@@ -620,7 +687,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + (size_t)nA * p.a_slot_bytes;
   uint8_t* b2b_w = b_base + (size_t)nB * p.b_slot_bytes;                 // weights of the fused 1x1 follow-up conv (1024-aligned)
-  float* vec_s = reinterpret_cast<float*>(b2b_w + (EPI == SF_EPI_LNGELU_B2B ? p.b2b_bytes : 0));
+  float* vec_s = reinterpret_cast<float*>(b2b_w + (epi_has_b2b(EPI) ? p.b2b_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + VEC_MAX + p.wg_scratch * NGROUPS);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + nA;
@@ -639,8 +706,8 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nA; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
-    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128 * MT); }
-    if (EPI == SF_EPI_LNGELU_B2B) {
+    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(acc_full + i), 1); mbar_init(smem_u32(acc_empty + i), 128 * MT * WGS); }
+    if (epi_has_b2b(EPI)) {
       mbar_init(smem_u32(b2b_full), 1);
       for (int i = 0; i < NGROUPS; ++i) mbar_init(smem_u32(b2b_done + i), 1);
     }
@@ -697,7 +764,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       if (elect_one()) {
         for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
         tma_prefetch_desc(&p.wmap);
-        if (EPI == SF_EPI_LNGELU_B2B) {          // the follow-up conv's weights: resident for the whole launch
+        if (epi_has_b2b(EPI)) {          // the follow-up conv's weights: resident for the whole launch
           mbar_expect_tx(smem_u32(b2b_full), (uint32_t)p.b2b_bytes);
           for (int q = 0; q * 64 * ROW_BYTES < p.b2b_bytes; ++q)
             tma_load_2d(smem_u32(b2b_w) + q * 64 * ROW_BYTES, &p.wmap, smem_u32(b2b_full), 0, p.b2b_wrow + q * 64);
@@ -857,13 +924,13 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
   } else if (warp < 4 * NGROUPS) {
     // ===================== epilogue warpgroup g owns accumulator slot (stage g / MT, M-tile g % MT) =====================
     const int g = warp >> 2;
-    const int st = g / MT, mt = g % MT;
+    const int st = g / (MT * WGS), mt = (g / WGS) % MT, sub = g % WGS;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int r = m >> 3, cx = m & 7;
     const uint32_t taddr = tmem_base + (uint32_t)st * STAGE_COLS + (uint32_t)mt * SLOT_COLS + ((uint32_t)(q * 32) << 16);
     uint32_t aph = 0;
-    B2BCtx b2b{smem_u32(b2b_w), smem_u32(b2b_full), smem_u32(b2b_done + g), 0u, false};
+    B2BCtx b2b{smem_u32(b2b_w), smem_u32(b2b_full), smem_u32(b2b_done + g), 0u, false, smem_u32(b2b_done + (g ^ (WGS - 1)))};
     // pixel of this thread in tile t (index into per-sample NHWC tensors), or -1 outside the image / past the last tile
     auto pixel_of = [&](int w, PixelCtx* out) -> long long {
       if (w >= nwork) return -1;
@@ -876,7 +943,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG), 
       const int y = p.pair_rows ? ty * (TILE_H - 1) - 1 + r : ty * TILE_H + r, x = (tx * MT + mt) * TILE_W + cx;
       const bool valid = (y < p.H) && (x < p.W) && !(p.pair_rows && r == 0);
       const size_t pix = ((size_t)sid * p.H + y) * p.W + x;
-      if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; out->wg = g; out->m = m; }
+      if (out) { out->bi = bi; out->sid = sid; out->y = y; out->x = x; out->valid = valid; out->pix = pix; out->wg = g; out->m = m; out->sub = sub; }
       return valid ? (long long)pix : -1;
     };
     for (int w = blockIdx.x + st * gridDim.x; w < nwork; w += S * gridDim.x, aph ^= 1) {

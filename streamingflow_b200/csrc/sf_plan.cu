@@ -62,6 +62,7 @@ struct Stage {
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
   std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
   int b2b_wrow = 0, b2b_bytes = 0;   // fused 1x1 follow-up conv of a lngelu stage (flag 1024): its weights are the last rows of w
+  int mt_epi = 0;                    // epilogue id that decides the CTA tile shape (the fused pointwise pair, flag 8192, runs one M-tile)
   // SE layer folded into this stage's weights (sf_plan_define_stage_fold)
   int fold_se = -1;
   const float* w32 = nullptr;
@@ -158,6 +159,9 @@ StageKernel kernel_for(int epi) {
     case SF_EPI_LNGELU_B2B:
       if constexpr (CG == 64) return conv_stage_kernel<SF_EPI_LNGELU_B2B, X3, CG>;
       else return nullptr;
+    case SF_EPI_PW_B2B:
+      if constexpr (CG == 64 && !X3) return conv_stage_kernel<SF_EPI_PW_B2B, X3, CG>;
+      else return nullptr;
   }
   return nullptr;
 }
@@ -194,7 +198,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   for (int c = 0; c < sp.nchunk; ++c) {
     const sf_chunk& ck = st.chunks[c];
     const int buf = resolve_buf(ev, ck.buf);
-    int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.epi, p->g.C), &sp.amap[c]);
+    int rc = encode_act_map(p, buf, ck.plane, ck.R, sf::mtiles_for(st.mt_epi, p->g.C), &sp.amap[c]);
     if (rc) return rc;
     if (ck.c0 + KC > p->act[buf].channels) return fail(SF_ERR_INVALID, "chunk channel range exceeds buffer");
     sp.chunk[c] = ChunkK{ck.R, ck.n, ck.nrep, ck.col, ck.wrow, ck.init, ck.c0, ck.buf == -1 ? 1 : 0, st.tb[c], ck.ox, ck.oy};
@@ -202,7 +206,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.wmap = st.wmap;
   sp.H = p->g.H;
   sp.W = p->g.W;
-  const int MT = sf::mtiles_for(st.epi, p->g.C);
+  const int MT = sf::mtiles_for(st.mt_epi, p->g.C);
   sp.tiles_x = (p->g.W + TILE_W * MT - 1) / (TILE_W * MT);
   const bool pair = (st.flags & 512) != 0;
   const int tile_rows = pair ? TILE_H - 1 : TILE_H;          // row-paired taps: lane row 0 of a tile is the row above its 15 output rows
@@ -310,6 +314,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   int kepi = st.epi;
   const bool general = e.act != 0 || e.out32 || e.img_bias || e.act_after_res;
   if (kepi == SF_EPI_BIAS_LRELU && general) kepi = SF_EPI_BIAS_ACT;
+  if (kepi == SF_EPI_RES_ID && (st.flags & 8192)) kepi = SF_EPI_PW_B2B;
   if (kepi == SF_EPI_RES_ID && general) kepi = SF_EPI_RES_ID_ACT;
   if (kepi == SF_EPI_LNGELU && st.b2b_bytes) kepi = SF_EPI_LNGELU_B2B;
   StageKernel k = kernel_for(kepi, x3, p->g.C);
@@ -319,7 +324,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   // tail of the previous kernel in the stream; it executes griddepcontrol.wait before touching anything that kernel wrote
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(128 + 128 * sf::ACC_STAGES * MT);
+  cfg.blockDim = dim3(128 + 128 * sf::ACC_STAGES * MT * sf::wgs_per_slot(kepi));
   cfg.dynamicSmemBytes = (size_t)st.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -527,10 +532,17 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   Stage& st = p->stage[stage];
   st = Stage();
   st.epi = epilogue;
+  // flag 8192 (res_id, C = 64, bf16): the stage's conv is the ConvNeXt block's pwconv1 (ONE 1x1 chunk, n = 256); GELU and pwconv2 run
+  // in the epilogue as a back-to-back GEMM.  w_packed = [pwconv1 rows | pwconv2 as four K-chunks of [64 n][64 k] rows], vec = [b1 (256), b2 (64)]
+  const bool pw = epilogue == SF_EPI_RES_ID && (flags & 8192);
+  st.mt_epi = pw ? sf::SF_EPI_PW_B2B : epilogue;
+  if (pw && (p->g.C != 64 || p->g.precision != SF_PREC_BF16 || n_chunks != 1 || chunks[0].R != 1 || chunks[0].n != 256 || chunks[0].col != 0 ||
+             chunks[0].nrep != 1 || n_vec != 320 || w_rows < 512))
+    return fail(SF_ERR_INVALID, "the fused pointwise pair needs 64 channels, bf16 operands, one 1x1 chunk with n = 256, a [b1 (256), b2 (64)] vector and pwconv2's 256 rows appended");
   st.chunks.assign(chunks, chunks + n_chunks);
   for (const sf_chunk& c : st.chunks) {
     if (!(c.R == 1 || c.R == 3 || c.R == 7)) return fail(SF_ERR_INVALID, "filter size must be 1, 3 or 7");
-    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(epilogue, p->g.C)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
+    if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(st.mt_epi, p->g.C)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
     if ((flags & 512) && (epilogue != SF_EPI_LNGELU || p->g.C != 64 || c.n != 64 || c.col != 0 || c.R < 2))
@@ -540,11 +552,11 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   // flag 1024: a 1x1 convolution + LayerNorm + GELU fused behind a lngelu stage (back-to-back GEMM in the epilogue); its
   // [C x C] weights (hi, then lo in the split mode) are the last rows of the packed matrix and stay in shared memory
   const bool b2b = (flags & 1024) != 0;
-  const int b2b_rows = b2b ? p->g.C * (p->g.precision == SF_PREC_BF16X3 ? 2 : 1) : 0;
+  const int b2b_rows = b2b ? p->g.C * (p->g.precision == SF_PREC_BF16X3 ? 2 : 1) : pw ? 256 : 0;
   if (b2b && (epilogue != SF_EPI_LNGELU || p->g.C != 64 || n_vec != 4 * p->g.C || w_rows < b2b_rows))
     return fail(SF_ERR_INVALID, "the fused 1x1 follow-up needs the lngelu epilogue, 64 channels, a [LN1 w, LN1 b, LN2 w, LN2 b] vector and its weights appended");
   for (const sf_chunk& c : st.chunks)
-    if (b2b && c.wrow + c.R * c.R * c.nrep * c.n > w_rows - b2b_rows) return fail(SF_ERR_INVALID, "chunk weight rows overlap the follow-up conv's rows");
+    if ((b2b || pw) && c.wrow + c.R * c.R * c.nrep * c.n > w_rows - b2b_rows) return fail(SF_ERR_INVALID, "chunk weight rows overlap the follow-up conv's rows");
   const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA + b2b_rows * ROW_BYTES;
   // Weight tiles: as many taps of a dx column per tile as the cap allows (fewer producer <-> issuer barrier round trips per MMA;
   // measured: 48 KB tiles are worth 4 % of the rollout over 24 KB ones), shrunk until at least two weight slots fit next to
@@ -560,7 +572,7 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
       if (tb > c.R) tb = c.R;
       if (flags & 512) tb = tb < 2 ? 2 : (tb & ~1);          // row-paired taps: a B tile = whole pairs of vertically adjacent taps
       st.tb.push_back(tb);
-      const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(epilogue, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
+      const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(st.mt_epi, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
       a_slot = a > a_slot ? a : a_slot;
       b_slot = b > b_slot ? b : b_slot;
     }

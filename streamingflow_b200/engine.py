@@ -194,11 +194,11 @@ def pack_stage(sdef: StageDef, x3: bool):
     """Packs a stage's weights into the [rows, 64] bf16 matrix the TMA weight ring streams, in consumption order:
     chunk -> dx -> dy -> rep -> n rows (see sf_chunk.wrow in include/sf_b200.h).  Returns (chunks, w_packed).
     Row-paired stages (FLAG_PAIR_ROWS): chunk -> dx -> pair -> rep -> [tap_hi n rows | tap_lo n rows]."""
-    if sdef.flags & L.FLAG_B2B:
-        plain = StageDef(sdef.name, sdef.epilogue, sdef.vec, sdef.io, sdef.io_off, sdef.flags & ~L.FLAG_B2B)
+    if sdef.flags & (L.FLAG_B2B | L.FLAG_PW_B2B):
+        plain = StageDef(sdef.name, sdef.epilogue, sdef.vec, sdef.io, sdef.io_off, sdef.flags & ~(L.FLAG_B2B | L.FLAG_PW_B2B))
         plain.chunks = sdef.chunks
         chunks, wp = pack_stage(plain, x3)
-        w = sdef.b2b_w.float()                                       # [n, k] = the K-major B operand of the follow-up GEMM
+        w = sdef.b2b_w.float()                                       # [n, k] = the K-major B operand of the follow-up GEMM (64 k per row)
         hi = w.to(torch.bfloat16)
         tail = [hi] + ([(w - hi.float()).to(torch.bfloat16)] if x3 else [])
         return chunks, torch.cat([wp] + tail, 0).contiguous()

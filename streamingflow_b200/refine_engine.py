@@ -16,6 +16,7 @@ decoder's output buffer and the result leaves as NCHW fp32.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -44,9 +45,11 @@ def _fold(w, sd, bn):
     return w.float() * scale[:, None, None, None], sd[bn + ".bias"].float() - sd[bn + ".running_mean"].float() * scale
 
 
-def refine_graph(sd: Dict[str, torch.Tensor]):
+def refine_graph(sd: Dict[str, torch.Tensor], fuse_pw: bool = False):
     """Stage definitions and kernel parameters of the refinement, from FuturePredictionODE's state_dict (keys spatial_grus.*,
-    res_blocks.*).  Returns a dict consumed by RefineEngine and by the CPU interpreter in tests/."""
+    res_blocks.*).  Returns a dict consumed by RefineEngine and by the CPU interpreter in tests/.
+    fuse_pw (64 channels, bf16): the ConvNeXt block's pwconv1 -> GELU -> pwconv2 -> layer scale -> + residual as ONE stage whose
+    4C-channel intermediate stays in tensor memory (stage flag FLAG_PW_B2B) instead of three launches around a [n, H, W, 4C] buffer."""
     g = {}
     Cc = g["C"] = sd["spatial_grus.0.conv_update.weight"].shape[0]          # SpatialGRU(in_channels, in_channels): weights [Cc, 2 Cc, 3, 3]
     for i, (src, dst) in enumerate(((R_X, R_O0), (R_BK, R_O1))):
@@ -66,12 +69,20 @@ def refine_graph(sd: Dict[str, torch.Tensor]):
     gamma = sd[b + "gamma"].float() if (b + "gamma") in sd else torch.ones_like(b2)
     blk = dict(dw_w=sd[b + "dwconv.weight"].float().contiguous(), dw_b=sd[b + "dwconv.bias"].float().contiguous(),
                ln_w=sd[b + "norm.weight"].float().contiguous(), ln_b=sd[b + "norm.bias"].float().contiguous(), stages=[])
-    for h in range(4 * Cc // 128):
-        r = slice(128 * h, 128 * h + 128)
-        blk["stages"].append(StageDef(f"block.pw1{'abcd'[h]}", L.EPI_BIAS_LRELU, b1[r], [R_P1], [128 * h], flags=_act_flags(L.ACT_GELU))
-                             .add(R_DW, w1[r][:, :, None, None], 0, 1))
-    blk["stages"].append(StageDef("block.pw2", L.EPI_RES_ID, gamma * b2, [R_O0, R_BK], flags=_act_flags(L.ACT_NONE))
-                         .add(R_P1, (gamma[:, None] * w2)[:, :, None, None], 0, 1))
+    if fuse_pw:
+        assert Cc == 64, "the fused pointwise pair is built for 64 channels"
+        st = StageDef("block.pw", L.EPI_RES_ID, torch.cat([b1, gamma * b2]), [R_O0, R_BK], flags=_act_flags(L.ACT_NONE) | L.FLAG_PW_B2B)
+        st.add(R_DW, w1[:, :, None, None], 0, 1)
+        # pwconv2 [C n][4C k] as four K-chunks of [C n][64 k] rows: the B operand tiles of the back-to-back GEMM
+        st.b2b_w = (gamma[:, None] * w2).view(Cc, 4 * Cc // 64, 64).permute(1, 0, 2).reshape(4 * Cc, 64).contiguous()
+        blk["stages"].append(st)
+    else:
+        for h in range(4 * Cc // 128):
+            r = slice(128 * h, 128 * h + 128)
+            blk["stages"].append(StageDef(f"block.pw1{'abcd'[h]}", L.EPI_BIAS_LRELU, b1[r], [R_P1], [128 * h], flags=_act_flags(L.ACT_GELU))
+                                 .add(R_DW, w1[r][:, :, None, None], 0, 1))
+        blk["stages"].append(StageDef("block.pw2", L.EPI_RES_ID, gamma * b2, [R_O0, R_BK], flags=_act_flags(L.ACT_NONE))
+                             .add(R_P1, (gamma[:, None] * w2)[:, :, None, None], 0, 1))
     g["block"] = blk
     d = "res_blocks.1."
     a = d + "0."
@@ -108,10 +119,12 @@ class RefineEngine:
         if Cc not in (64, 128) or sd["spatial_grus.0.conv_update.weight"].shape[1] != 2 * Cc or "res_blocks.0.1.dwconv.weight" in sd \
                 or sd["res_blocks.1.0.convs.0.0.weight"].shape[0] != 128:
             raise L.SfError("fused refinement is built for 64 or 128 channels, one ConvNeXt block and DeepLabHead(C, C, 128)")
-        self.g = refine_graph(sd)
+        # 64 channels, bf16: the block's pointwise pair runs as one back-to-back GEMM stage (SF_PW_B2B=0: three launches)
+        self.fuse_pw = Cc == 64 and not self.x3 and os.environ.get("SF_PW_B2B", "1") != "0"
+        self.g = refine_graph(sd, fuse_pw=self.fuse_pw)
         P = self.plan = LevelPlan(self.lib, H, W, n, self.x3, device, C_hidden=Cc)
         for b, ch in frame_bufs(Cc).items():
-            if b != R_X:
+            if b != R_X and not (b == R_P1 and self.fuse_pw):          # the fused pair has no 4C-channel intermediate in HBM
                 P.buf(b, ch)
         for b, ch in state_bufs(Cc).items():
             shape = (B, H, W, ch)

@@ -671,3 +671,48 @@ def test_plain_convgru_cells_match_the_reference_formula(precision):
         scale = torch.maximum(want.abs().max(), s.double().abs().max())
         err = ((got.double() - want).abs().max() / scale).item()
         assert got.shape == want.shape and err < TOL[precision], f"{cls.__name__}: {err:.3e} ({precision})"
+
+
+def test_fused_pointwise_pair_of_the_convnext_block_matches_the_three_launch_form_and_the_oracle(monkeypatch):
+    """The ConvNeXt block's pwconv1 -> GELU -> pwconv2 -> + residual as ONE stage (back-to-back GEMM, the 4C-channel intermediate in
+    tensor memory; refine_engine fuse_pw) vs the three-launch form around a [n, H, W, 4C] HBM buffer (SF_PW_B2B=0), on ragged sizes
+    with energised layer scale, and the whole refinement vs the fp64 oracle."""
+    from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
+    from streamingflow_b200.refine_engine import RefineEngine
+
+    dev = torch.device("cuda", 0)
+    C, B, T, H, W = 64, 2, 3, 72, 52
+    m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval()
+    sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 21, 1.0)
+    sd["res_blocks.0.0.gamma"] = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(3))        # default init 1e-6 would hide the pair
+    rsd = {k: v for k, v in sd.items() if k.startswith(("spatial_grus", "res_blocks"))}
+    x = torch.tanh(so.recipe_array("x", (B, T, C, H, W), 21))
+    x32 = x.view(B * T, C, H, W).permute(0, 2, 3, 1).contiguous().to(dev)
+    planes = (x32.to(torch.bfloat16), None)
+    from streamingflow_b200 import refine_engine as rf
+
+    outs, blk = {}, {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("SF_PW_B2B", fuse)
+        eng = RefineEngine(rsd, H, W, B, T, "bf16", dev)
+        assert eng.fuse_pw == (fuse == "1") and len(eng.slots["block"]) == (1 if fuse == "1" else 3)
+        with torch.no_grad():
+            outs[fuse] = eng.run(planes, x32).clone()
+            blk[fuse] = eng.plan.bufs[rf.R_BK][0].float().clone()                      # the block's output planes (bf16)
+        torch.cuda.synchronize()
+        assert int(eng.plan.errflag.item()) == 0
+    # The block's output: same operand rounding in both forms (the 4C intermediate is bf16 either way); the fused form adds the two
+    # K-halves of pwconv2 from separate accumulators, so a value may differ in its last fp32 bit and then round to the neighbouring
+    # bf16: at most one bf16 ulp, on a small fraction of the elements (downstream, the SpatialGRU amplifies such flips to bf16 level).
+    d = (blk["1"] - blk["0"]).abs()
+    assert bool((d <= blk["0"].abs() * 2.0 ** -7 + 1e-6).all()) and float((d > 0).float().mean()) < 2e-3, (d.max().item(), (d > 0).float().mean().item())
+    sd64 = {k: v.double().to(dev) if v.is_floating_point() else v.to(dev) for k, v in sd.items()}
+    xb = planes[0].double().permute(0, 3, 1, 2).reshape(B, T, C, H, W)                 # the engine starts from the bf16 planes
+    with torch.no_grad():
+        y = so.spatial_gru(sd64, "spatial_grus.0", xb, x.double().to(dev)[:, 0])
+        y = so.convnext_block(sd64, "res_blocks.0.0", y.reshape(B * T, C, H, W)).view(B, T, C, H, W)
+        y = so.spatial_gru(sd64, "spatial_grus.1", y, x.double().to(dev)[:, 0])
+        want = so.deeplab_head(sd64, "res_blocks.1", y.reshape(B * T, C, H, W)).view(B, T, C, H, W)
+    assert _rel(outs["1"], want) < TOL["bf16"] and _rel(outs["0"], want) < TOL["bf16"], (_rel(outs["1"], want), _rel(outs["0"], want))
+    print("refinement vs fp64 oracle: fused %.3e, three launches %.3e; block outputs differing by one bf16 ulp: %.2e of the elements"
+          % (_rel(outs["1"], want), _rel(outs["0"], want), (d > 0).float().mean().item()))

@@ -457,17 +457,19 @@ def test_codec_stage_graphs_reproduce_encoder_and_decoder(C, nf):
     assert got.shape == want.shape and ((got - want).abs().max() / want.abs().max()).item() < 2e-4
 
 
-@pytest.mark.parametrize("C", [64, 128])
-def test_refinement_stage_graph_reproduces_reference_refinement(C):
+@pytest.mark.parametrize("C, fuse_pw", [(64, False), (64, True), (128, False)])
+def test_refinement_stage_graph_reproduces_reference_refinement(C, fuse_pw):
     """SpatialGRU x2 + ConvNeXt Block + DeepLabHead as conv-stage graphs (refine_engine.refine_graph), interpreted on the host,
-    == the oracle's refinement (future_prediction_ode.py:56-62); in_channels 64 and 128."""
+    == the oracle's refinement (future_prediction_ode.py:56-62); in_channels 64 and 128; fuse_pw: the block's pointwise pair as
+    ONE stage (pwconv2 read back from the K-chunked rows appended to the packed matrix, as the kernel's back-to-back GEMM reads them)."""
     from streamingflow_b200 import _lib as L, engine as en, refine_engine as rf
     from streamingflow_b200.models.future_prediction_ode import FuturePredictionODE
     import torch.nn.functional as F
 
     m = FuturePredictionODE(C, C, 4, make_cfg(C)).eval()
     sd = so.recipe_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 12, 1.0)
-    g = rf.refine_graph(sd)
+    g = rf.refine_graph(sd, fuse_pw=fuse_pw)
+    assert len(g["block"]["stages"]) == (1 if fuse_pw else 4 * C // 128 + 1)
     B, T, H, W = (1, 2, 48, 40) if C == 64 else (1, 2, 40, 24)
     x = so.recipe_array("x", (B, T, C, H, W), 12)
     emu = lambda sdef, src: en.emulate_stage(sdef, True, {k: v.float() for k, v in src.items()})
@@ -490,6 +492,13 @@ def test_refinement_stage_graph_reproduces_reference_refinement(C):
 
     def run_stage(sdef, bufs, img_bias=None):
         acc = emu(sdef, {k: v[None] for k, v in bufs.items()})
+        if sdef.flags & L.FLAG_PW_B2B:
+            vec = sdef.vec.double()
+            t = F.gelu(acc[:4 * C] + vec[:4 * C, None, None])
+            rows = en.pack_stage(sdef, True)[1][-2 * 4 * C:].double()                       # [hi rows | lo rows], each [kc][n][64 k]
+            w2 = (rows[:4 * C] + rows[4 * C:]).view(4 * C // 64, C, 64).permute(1, 0, 2).reshape(C, 4 * C)
+            v = torch.einsum("nk,khw->nhw", w2, t) + vec[4 * C:, None, None] + bufs[sdef.io[0]]
+            return sdef.io[1], 0, v
         n = max(ck[2].shape[0] for ck in sdef.chunks if ck[3] == 0)
         v = acc[:n] + sdef.vec.double()[:n, None, None]
         if img_bias is not None:
