@@ -136,7 +136,8 @@ int sf_plan_bind_f32(sf_plan* p, int slot, void* ptr);
    0 LeakyReLU(0.1), 1 tanh, 2 ReLU, 3 identity, 4 GELU(erf); bit 4 (bias_act) also write the output to SF_F32_OUT in fp32;
    bit 5 (gates / propose at C = 64) a single gate pair / proposal (plain ConvGRU of the refinement) instead of two;
    bit 6 (bias_act) add the per-image bias SF_F32_IMG_BIAS[image][n_out] (ASPP pooling branch);
-   bit 9 (lngelu, C = 64, n = 64 chunks) row-paired taps: the packed weights order each dx column as pairs of vertically
+   bit 9 (C = 64, n = 64 chunks at column 0; epilogues with one 64-column accumulator block: lngelu, decode, bias_lrelu / bias_act,
+   res_id) row-paired taps: the packed weights order each dx column as pairs of vertically
    adjacent taps [dy = 1 | 0], [3 | 2], ... (+ the last tap alone when R is odd), per rep [tap_hi rows | tap_lo rows]; the kernel
    issues one MMA of twice the width per pair and folds the second column block back one row in the epilogue;
    bit 7 (res_id) the residual input is multiplied by the per-sample channel scales of SE layer (flags >> 8) & 1 (the SE
@@ -345,6 +346,8 @@ typedef struct sf_packed sf_packed;
 #define SF_PACK_PAIR_ROWS 1   /* C = 64: row-paired taps in the 7x7 trunk (stage flag bit 9)                           */
 #define SF_PACK_B2B 2         /* C = 64: 7x7 + LN + GELU + 1x1 + LN + GELU as ONE stage (stage flag bit 10)            */
 #define SF_PACK_FOLD_SE 4     /* prior net: SE layers folded into their consumers' weights                             */
+#define SF_PACK_PAIR_3X3 8    /* C = 64: row-paired taps also in the 64 -> 64 3x3 stages (decode, q1); measured slower: not a default */
+#define SF_PACK_DEFAULT (SF_PACK_PAIR_ROWS | SF_PACK_B2B | SF_PACK_FOLD_SE)
 /* One dual-GRU cell (prefix "gru_c." = derivative, temporal_ode_bayes.py:92-161; "gru_obs.gru_d." = observation jump, :239-305):
    gates / propose / decode / trunk / mix stages with cat[state, state] of GRU-2 folded; channel width from the weights. */
 int sf_pack_cell_weights(const sf_tensor* tensors, int n_tensors, const char* prefix, int precision, int options, sf_packed** out);
@@ -358,7 +361,7 @@ typedef struct {
   int32_t path_slots;     /* recorded states the PATH tensor holds                                                    */
   int32_t obs_images;     /* encoded observation frames the OBS buffer holds                                          */
   int32_t eps_slots;      /* noise tensors the EPS tensor holds                                                       */
-  int32_t pack_options;   /* SF_PACK_* (default: all three)                                                           */
+  int32_t pack_options;   /* SF_PACK_* (NULL options: SF_PACK_DEFAULT)                                                 */
 } sf_ode_options;
 
 typedef enum {            /* device tensors inside the workspace (sf_ode_tensor)                                      */

@@ -60,7 +60,8 @@ class RolloutInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_events", "n_table", "n_eps", "n_path", "n_state_steps", "n_jumps", "n_cell_evals", "n_prior_evals")]
 
 
-PACK_PAIR_ROWS, PACK_B2B, PACK_FOLD_SE = 1, 2, 4
+PACK_PAIR_ROWS, PACK_B2B, PACK_FOLD_SE, PACK_PAIR_3X3 = 1, 2, 4, 8
+PACK_DEFAULT = PACK_PAIR_ROWS | PACK_B2B | PACK_FOLD_SE
 (ODE_OBS_HI, ODE_OBS_LO, ODE_EPS, ODE_PATH, ODE_STATE0, ODE_STATE1, ODE_X32, ODE_PARAMS32, ODE_ERRFLAG) = range(9)
 
 EXPORTS = {

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import StageDef, _bn_fold, pack_stage
+from .engine import StageDef, _bn_fold, pack_stage, pair_rows_if_eligible
 
 
 def _convT_as_conv(w_t: torch.Tensor) -> torch.Tensor:
@@ -36,6 +36,7 @@ class LevelPlan:
         """C_hidden: the hidden width the gates / propose epilogues are instantiated for (64 or 128); the bias_act / residual
         epilogues are width-generic (<= 128 output channels per launch)."""
         self.lib, self.H, self.W, self.n, self.x3, self.device = lib, H, W, max_images, x3, device
+        self.C_hidden = C_hidden
         geo = L.Geometry(max_images, H, W, C_hidden, L.PREC_BF16X3 if x3 else L.PREC_BF16, device.index)
         h = C.c_void_p()
         with torch.cuda.device(device):
@@ -67,6 +68,7 @@ class LevelPlan:
     def stage(self, sdef: StageDef) -> int:
         slot = self.n_stages
         self.n_stages += 1
+        pair_rows_if_eligible(sdef, self.C_hidden)
         chunks, wp = pack_stage(sdef, self.x3)
         vec = sdef.vec.to(torch.float32).contiguous()
         arr = (L.Chunk * len(chunks))(*[L.Chunk(**c) for c in chunks])

@@ -82,23 +82,24 @@ def _unpack(lib, handle) -> List[PackedItem]:
     return out
 
 
-def pack_cell(sd: Dict[str, torch.Tensor], prefix: str, x3: bool, pair_rows: bool = True, b2b: bool = True) -> List[PackedItem]:
+def pack_cell(sd: Dict[str, torch.Tensor], prefix: str, x3: bool, pair_rows: bool = True, b2b: bool = True, pair3: bool = False) -> List[PackedItem]:
     """One dual-GRU cell (``prefix`` = '...gru_c.' or '...gru_obs.gru_d.') packed by the library."""
     lib = L.load()
     arr, n, keep = tensor_table(sd, prefix)
     h = C.c_void_p()
-    opts = (L.PACK_PAIR_ROWS if pair_rows else 0) | (L.PACK_B2B if b2b else 0)
+    opts = (L.PACK_PAIR_ROWS if pair_rows else 0) | (L.PACK_B2B if b2b else 0) | (L.PACK_PAIR_3X3 if pair3 else 0)
     L.check(lib.sf_pack_cell_weights(arr, n, prefix.encode(), L.PREC_BF16X3 if x3 else L.PREC_BF16, opts, C.byref(h)), "sf_pack_cell_weights")
     del keep
     return _unpack(lib, h)
 
 
-def pack_pmodel(sd: Dict[str, torch.Tensor], prefix: str, x3: bool, fold_se: bool) -> List[PackedItem]:
+def pack_pmodel(sd: Dict[str, torch.Tensor], prefix: str, x3: bool, fold_se: bool, pair3: bool = False) -> List[PackedItem]:
     """p_model (``prefix`` = '...p_model.') packed by the library: q1 .. q5 with the two SE markers in launch order."""
     lib = L.load()
     arr, n, keep = tensor_table(sd, prefix)
     h = C.c_void_p()
-    L.check(lib.sf_pack_pmodel_weights(arr, n, prefix.encode(), L.PREC_BF16X3 if x3 else L.PREC_BF16, L.PACK_FOLD_SE if fold_se else 0, C.byref(h)),
+    L.check(lib.sf_pack_pmodel_weights(arr, n, prefix.encode(), L.PREC_BF16X3 if x3 else L.PREC_BF16,
+                                       (L.PACK_FOLD_SE if fold_se else 0) | (L.PACK_PAIR_3X3 if pair3 else 0), C.byref(h)),
             "sf_pack_pmodel_weights")
     del keep
     return _unpack(lib, h)

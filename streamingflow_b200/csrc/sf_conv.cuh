@@ -95,6 +95,8 @@ struct alignas(64) StageParams {
   int w_rows_per_sample;     // > 0: per-sample weights (SE layer folded in): active sample bi reads rows [bi * this, (bi+1) * this)
   int b2b_wrow;              // lngelu_b2b: first row of the 1x1 follow-up conv's weights [CG n x 64 k] (hi, then lo in the split mode)
   int b2b_bytes;             // ... and their size in shared memory (loaded once per CTA)
+  int resident_b;            // > 0: the stage's whole packed weight matrix (this many bytes) is loaded once per CTA into the (single) weight
+                             // slot and stays for the launch: no weight ring, the issuer addresses taps by their row in the matrix
   int* err;
   EpiArgs e;
 };
@@ -237,6 +239,47 @@ struct PixelCtx {
   int sub;       // which of the slot's warpgroups this is (stages with wgs_per_slot > 1)
 };
 
+// Row-paired taps (stage flag 512, 64-channel stages): column block 1 [64, 128) of lane m holds the partial sum that belongs to the
+// pixel ONE ROW BELOW (lane m + 8).  Fold it in: block0[m] += block1[m - 8].  Inside a warp that is a shuffle by 8 lanes; the first
+// row of a warp takes the last row of the warp above through the warpgroup's shared scratch (double-buffered per slice; one named
+// barrier per slice).  The tile's first row (lane row 0) is a scratch row: it only feeds row 1.  Afterwards block 0 holds the
+// complete accumulator and every epilogue runs unchanged.
+__device__ __forceinline__ void fold_paired_rows(const StageParams& p, uint32_t vec, uint32_t taddr, const PixelCtx& c) {
+  constexpr int N = 64;
+  const int lane = c.m & 31, q = c.m >> 5;
+  const uint32_t scratch = vec + (uint32_t)(VEC_MAX + c.wg * p.wg_scratch) * 4u;
+#pragma unroll 1
+  for (int j = 0; j < N / 16; ++j) {
+    float v0[16], v1[16];
+    tmem_ld16x2(taddr + j * 16, taddr + N + j * 16, v0, v1);
+    const uint32_t buf = scratch + (uint32_t)((j & 1) * 512 + q * 128) * 4u;
+    if (lane >= 24) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)((lane - 24) * 16 + 4 * i) * 4u), "f"(v1[4 * i]),
+                     "f"(v1[4 * i + 1]), "f"(v1[4 * i + 2]), "f"(v1[4 * i + 3]) : "memory");
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
+    float up[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) up[i] = __shfl_up_sync(0xffffffffu, v1[i], 8);
+    if (lane < 8) {
+      if (q > 0) vec16(buf - 128u * 4u, lane * 16, up); else zero16(up);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v0[i] += up[i];
+    tmem_st16(taddr + j * 16, v0);
+  }
+  tmem_st_wait();
+}
+// epilogues that accept row-paired taps: one 64-column accumulator block at column 0 (the register-bound propose / mix / sample
+// epilogues stay out: the extra code costs them spills)
+__host__ __device__ constexpr bool epi_can_pair(int epi) {
+  return epi == SF_EPI_LNGELU || epi == SF_EPI_LNGELU_B2B || epi == SF_EPI_DECODE || epi == SF_EPI_BIAS_LRELU || epi == SF_EPI_BIAS_ACT ||
+         epi == SF_EPI_RES_ID || epi == SF_EPI_RES_ID_ACT;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // fused epilogues.  taddr = TMEM address of this warp's lane quadrant, column 0 of the accumulator stage.
 // All tcgen05.ld are executed by every lane (they are warp-collective); global traffic is predicated.
@@ -249,6 +292,9 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
   const EpiArgs& e = p.e;
   constexpr int NJ = CG / 16;                      // 16-channel slices of one CG-channel tensor
   const size_t pc = c.pix * CG;                    // this pixel in a CG-channel NHWC tensor
+  if constexpr (CG == 64 && epi_can_pair(EPI)) {
+    if (p.pair_rows) fold_paired_rows(p, vec, taddr, c);
+  }
   if constexpr (EPI == SF_EPI_GATES) {
     // columns: pair g = [u_g (CG) | r_g (CG)]; CG = 64: two pairs (u1 r1 u2 r2) in one launch, CG = 128: one pair per launch.
     // vec = biases in column order; out[2g] = u_g, out[2g+1] = (1 - r_g) * s
@@ -336,37 +382,6 @@ __device__ __forceinline__ bool run_epilogue(const StageParams& p, uint32_t vec,
       }
     }
   } else if constexpr (EPI == SF_EPI_LNGELU || EPI == SF_EPI_LNGELU_B2B) {
-    if (p.pair_rows) {
-      // Row-paired taps: column block 1 [CG, 2CG) of lane m holds the partial sum that belongs to the pixel ONE ROW BELOW
-      // (lane m + 8).  Fold it in: block0[m] += block1[m - 8].  Inside a warp that is a shuffle by 8 lanes; the first row of a
-      // warp takes the last row of the warp above through the warpgroup's shared scratch (double-buffered per slice; one
-      // named barrier per slice).  The tile's first row (lane row 0) is a scratch row: it only feeds row 1.
-      const int lane = c.m & 31, q = c.m >> 5;
-      const uint32_t scratch = vec + (uint32_t)(VEC_MAX + c.wg * p.wg_scratch) * 4u;
-#pragma unroll 1
-      for (int j = 0; j < NJ; ++j) {
-        float v0[16], v1[16];
-        tmem_ld16x2(taddr + j * 16, taddr + CG + j * 16, v0, v1);
-        const uint32_t buf = scratch + (uint32_t)((j & 1) * 512 + q * 128) * 4u;
-        if (lane >= 24) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + (uint32_t)((lane - 24) * 16 + 4 * i) * 4u), "f"(v1[4 * i]),
-                         "f"(v1[4 * i + 1]), "f"(v1[4 * i + 2]), "f"(v1[4 * i + 3]) : "memory");
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + c.wg) : "memory");
-        float up[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) up[i] = __shfl_up_sync(0xffffffffu, v1[i], 8);
-        if (lane < 8) {
-          if (q > 0) vec16(buf - 128u * 4u, lane * 16, up); else zero16(up);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v0[i] += up[i];
-        tmem_st16(taddr + j * 16, v0);
-      }
-      tmem_st_wait();
-    }
     float mean, rstd;
     ln_stats<CG>(taddr, mean, rstd);
     if constexpr (EPI == SF_EPI_LNGELU) {
@@ -764,6 +779,10 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
       if (elect_one()) {
         for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
         tma_prefetch_desc(&p.wmap);
+        if (p.resident_b) {               // the stage's own weights: resident for the whole launch
+          mbar_expect_tx(b_full0, (uint32_t)p.resident_b);
+          for (int q = 0; q * 64 * ROW_BYTES < p.resident_b; ++q) tma_load_2d(b_smem0 + q * 64 * ROW_BYTES, &p.wmap, b_full0, 0, q * 64);
+        }
         if (epi_has_b2b(EPI)) {          // the follow-up conv's weights: resident for the whole launch
           mbar_expect_tx(smem_u32(b2b_full), (uint32_t)p.b2b_bytes);
           for (int q = 0; q * 64 * ROW_BYTES < p.b2b_bytes; ++q)
@@ -796,6 +815,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
           const int tap_rows = ck.n * ck.nrep;                  // weight rows of one tap
           const int ngrp = (R + ck.tb - 1) / ck.tb;             // B tiles per dx column; the last one may hold fewer taps
           int dx = rem % R, g0 = (ck.tb == 1) ? (rem / R) % R : 0;     // tap rotation (same formula in the MMA warp)
+          if (p.resident_b) continue;                                  // weights already in shared memory
           for (int i = 0; i < R; ++i) {
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
@@ -824,6 +844,11 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
     {
       // ===================== MMA issuer (converged warp, one elected lane issues) =====================
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 1;   // parities to wait for on the FULL barriers / acc EMPTY
+      const bool resident = p.resident_b != 0;
+      if (resident && blockIdx.x < (unsigned)nwork) {              // the one-time weight load
+        mbar_wait(b_full0, 0, p.err, 5);
+        tc_fence_after();
+      }
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         uint32_t mtmask;
         const int tile = work_tile(w, mtmask);
@@ -850,14 +875,18 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
           for (int i = 0; i < R; ++i) {
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
-              mbar_wait(b_full0 + sb * 8, pb, p.err, 5);
-              tc_fence_after();
-              uint32_t b_lo = ((b_smem0 + sb * p.b_slot_bytes) & 0x3FFFFu) >> 4;
+              if (!resident) {
+                mbar_wait(b_full0 + sb * 8, pb, p.err, 5);
+                tc_fence_after();
+              }
+              // streamed: the ring slot holds this group's rows; resident: the group starts at its row of the packed matrix
+              uint32_t b_lo = resident ? ((b_smem0 + (uint32_t)(ck.wrow + (dx * R + gi * ck.tb) * ck.n * ck.nrep) * ROW_BYTES) & 0x3FFFFu) >> 4
+                                       : ((b_smem0 + sb * p.b_slot_bytes) & 0x3FFFFu) >> 4;
               // first tap of this group: dy = gi*tb; one pixel row = 128 B = 8 descriptor units
               uint32_t a_lo = a_lo0 + ((uint32_t)(gi * ck.tb) * WP + (uint32_t)dx) * (ROW_BYTES >> 4);
               const int ntap = min(ck.tb, R - gi * ck.tb);
               if (p.debug & 2) {
-                if (elect_one()) umma_commit(b_empty0 + sb * 8);
+                if (!resident && elect_one()) umma_commit(b_empty0 + sb * 8);
               } else if (p.pair_rows) {
                 // Row-paired taps.  This B tile holds the taps dy = gi*tb .. gi*tb + ntap - 1 of column dx as ONE operand of
                 // n * ntap rows per rep, ordered [dy_hi | dy_lo]; a single MMA per K step, on the window of dy_hi, produces the
@@ -883,7 +912,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
                       acc = 1u;
                     }
                   }
-                  umma_commit(b_empty0 + sb * 8);
+                  if (!resident) umma_commit(b_empty0 + sb * 8);
                 }
               } else if (elect_one()) {
                 uint32_t acc = accumulate;
@@ -903,7 +932,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
                     acc = 1u;
                   }
                 }
-                umma_commit(b_empty0 + sb * 8);        // frees the weight tile once these MMAs retire
+                if (!resident) umma_commit(b_empty0 + sb * 8);        // frees the weight tile once these MMAs retire
               }
               __syncwarp();
               accumulate = 1u;

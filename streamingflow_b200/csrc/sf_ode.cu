@@ -333,7 +333,9 @@ int build_cell(TensorTable& T, const std::string& p, bool x3, int options, sf_pa
     p2.add(SS, x_of(wt2), 0, 1);
     p2.add(SF_BUF_G2, s_of(wt2), 0, 0);
   }
-  stage("decode", SF_EPI_DECODE, bias("conv_decoder_2"), {SF_BUF_B}).add(SF_BUF_HH, g3("conv_decoder_2", C), 0, 1);
+  // 64 channels: the 3x3 stages with ONE 64-column accumulator block pair their vertically adjacent taps too (N = 128 MMAs)
+  const bool pair3 = C == 64 && (options & SF_PACK_PAIR_3X3);
+  stage("decode", SF_EPI_DECODE, bias("conv_decoder_2"), {SF_BUF_B}, pair3 ? FLAG_PAIR_ROWS : 0).add(SF_BUF_HH, g3("conv_decoder_2", C), 0, 1);
   const std::string t = "trusting_gate.0.";
   const W4 w7 = T.conv(p + t + "layers.0.weight", C, 2 * C, 7);
   auto ln = [&](int i, const char* wb) { return T.vec(p + t + "layers." + std::to_string(i) + "." + wb, C); };
@@ -390,7 +392,7 @@ int build_prior(TensorTable& T, const std::string& p, bool x3, int options, sf_p
   V1 b1, b2, b3, b4;
   bn_fold(T, m + "0.layers.conv_1", C, C, 3, w1, b1);
   bn_fold(T, m + "0.layers.conv_2", 2 * C, C, 3, w2, b2);
-  stage("q1", SF_EPI_BIAS_LRELU, b1, {SF_BUF_Q1}, {0}).add(SO, w1, 0, 1);
+  stage("q1", SF_EPI_BIAS_LRELU, b1, {SF_BUF_Q1}, {0}, (C == 64 && (options & SF_PACK_PAIR_3X3)) ? FLAG_PAIR_ROWS : 0).add(SO, w1, 0, 1);
   const W4 wpj = T.conv(m + "0.projection.weight", 2 * C, C, 1);
   const V1 bpj = T.vec(m + "0.projection.bias", 2 * C);
   for (int h = 0; h < halves; ++h) {
@@ -587,7 +589,7 @@ struct ZeroWeights {                 // a complete, zero-valued parameter set of
 
 sf_ode_options default_options(const sf_ode_options* o) {
   sf_ode_options r;
-  r.path_slots = 1; r.obs_images = 1; r.eps_slots = 1; r.pack_options = SF_PACK_PAIR_ROWS | SF_PACK_B2B | SF_PACK_FOLD_SE;
+  r.path_slots = 1; r.obs_images = 1; r.eps_slots = 1; r.pack_options = SF_PACK_DEFAULT;
   if (o) r = *o;
   return r;
 }

@@ -62,6 +62,8 @@ struct Stage {
   int a_slot = 0, b_slot = 0, nA = 0, nB = 0, smem = 0;
   std::vector<int> tb;     // per chunk: taps per B tile (1 or R)
   int b2b_wrow = 0, b2b_bytes = 0;   // fused 1x1 follow-up conv of a lngelu stage (flag 1024): its weights are the last rows of w
+  int fixed_smem = 0;                // shared memory outside the operand rings
+  int resident_b = 0;                // > 0: bytes of packed weights kept in shared memory for the whole launch instead of streamed per tile
   int mt_epi = 0;                    // epilogue id that decides the CTA tile shape (the fused pointwise pair, flag 8192, runs one M-tile)
   // SE layer folded into this stage's weights (sf_plan_define_stage_fold)
   int fold_se = -1;
@@ -228,6 +230,7 @@ int launch_stage(sf_plan* p, int sidx, const sf_event* ev, const int32_t* table,
   sp.nA = st.nA;
   sp.nB = st.nB;
   sp.w_rows_per_sample = st.fold_se >= 0 ? st.w_rows : 0;
+  sp.resident_b = st.resident_b;
   sp.b2b_wrow = st.b2b_wrow;
   sp.b2b_bytes = st.b2b_bytes;
   static const int debug_stage = [] { const char* v = getenv("SF_DEBUG_STAGE"); return v ? atoi(v) : 0; }();    // read once, not per launch
@@ -460,6 +463,54 @@ int launch_se(sf_plan* p, int which, const sf_event* ev, const int32_t* table, c
   return launch_se_apply(p, which, ev, table, 0, 1.0f / (float)hw, stream);
 }
 
+// Shared-memory layout of a stage's operand rings.
+// Weight tiles: as many taps of a dx column per tile as the cap allows (fewer producer <-> issuer barrier round trips per MMA;
+// measured: 48 KB tiles are worth 4 % of the rollout over 24 KB ones), shrunk until at least two weight slots fit next to
+// the activation ring.  Activation ring: one slot = one chunk's tile + halo, 3 slots when they leave room, up to 4.
+// Resident weights: when the whole packed matrix fits next to two activation slots it is loaded ONCE per CTA and stays for the
+// launch (no per-tile weight stream from L2, no weight-ring handshakes): the dilated ASPP branches, the 64 -> 64 3x3 stages, mix,
+// q1, q2.  Not for per-sample weights (SE layer folded in: the rows change with the tile's sample).  SF_RESIDENT_B=0 turns it off.
+int layout_operand_rings(sf_plan* p, Stage& st, bool allow_resident) {
+  static const bool resident_on = [] { const char* v = getenv("SF_RESIDENT_B"); return !(v && v[0] == '0'); }();
+  const int fixed = st.fixed_smem, flags = st.flags;
+  int a_slot = 0, b_slot = 0, nA = 0, nB = 0;
+  for (int cap = B_TILE_MAX;; cap -= 8 * 1024) {
+    st.tb.clear();
+    a_slot = b_slot = 0;
+    for (const sf_chunk& c : st.chunks) {
+      const int tap_bytes = c.n * c.nrep * ROW_BYTES;
+      int tb = cap / tap_bytes;
+      if (tb < 1) tb = 1;
+      if (tb > c.R) tb = c.R;
+      if (flags & 512) tb = tb < 2 ? 2 : (tb & ~1);          // row-paired taps: a B tile = whole pairs of vertically adjacent taps
+      st.tb.push_back(tb);
+      const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(st.mt_epi, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
+      a_slot = a > a_slot ? a : a_slot;
+      b_slot = b > b_slot ? b : b_slot;
+    }
+    const int res_bytes = st.b2b_wrow * ROW_BYTES;           // every row of the chunks (a fused follow-up conv's rows have their own region)
+    const int res_slot = (res_bytes + 1023) & ~1023;
+    if (allow_resident && resident_on && cap == B_TILE_MAX && res_bytes > 0 && fixed + res_slot + 2 * a_slot <= SMEM_BUDGET) {
+      nA = (SMEM_BUDGET - fixed - res_slot) / a_slot;
+      if (nA > 4) nA = 4;
+      st.a_slot = a_slot; st.b_slot = res_slot; st.nA = nA; st.nB = 1;
+      st.resident_b = res_bytes;
+      st.smem = fixed + nA * a_slot + st.b_slot;
+      return SF_OK;
+    }
+    nA = (fixed + 3 * a_slot + 2 * b_slot <= SMEM_BUDGET) ? 3 : 2;
+    nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
+    if (nB > sf::MAX_RING) nB = sf::MAX_RING;
+    if (nB >= 2) break;
+    if (cap <= 8 * 1024) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
+  }
+  while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
+  st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
+  st.resident_b = 0;
+  st.smem = fixed + nA * a_slot + nB * b_slot;
+  return SF_OK;
+}
+
 int run_item(sf_plan* p, int item, const sf_event* ev, const int32_t* table, cudaStream_t stream) {
   if (item >= 2000) return launch_se_fold(p, item - 2000, ev, table, stream);
   if (item >= 1000) return launch_se(p, item - 1000, ev, table, stream);
@@ -545,8 +596,10 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
     if (c.n % 64 || c.n <= 0 || c.n > 256 || c.col < 0 || c.col + c.n > sf::TMEM_COLS / sf::ACC_STAGES / sf::mtiles_for(st.mt_epi, p->g.C)) return fail(SF_ERR_INVALID, "bad chunk N / column range");
     if (c.nrep < 1 || c.nrep > 2) return fail(SF_ERR_INVALID, "nrep must be 1 or 2");
     if (c.wrow < 0 || c.wrow + c.R * c.R * c.nrep * c.n > w_rows) return fail(SF_ERR_INVALID, "chunk weight rows exceed the packed matrix");
-    if ((flags & 512) && (epilogue != SF_EPI_LNGELU || p->g.C != 64 || c.n != 64 || c.col != 0 || c.R < 2))
-      return fail(SF_ERR_INVALID, "row-paired taps need the lngelu epilogue, 64 channels and n = 64 chunks at column 0");
+    if ((flags & 512) && (!sf::epi_can_pair(epilogue) || (flags & (128 | 8192)) || p->g.C != 64 ||
+                          c.n != 64 || c.col != 0 || c.R < 2 || c.ox || c.oy))
+      return fail(SF_ERR_INVALID, "row-paired taps need an epilogue with ONE 64-column accumulator block (lngelu, decode, bias_act, res_id), a 64-channel "
+                                  "plan and undilated n = 64 chunks at column 0");
   }
   if (epilogue < 0 || epilogue > SF_EPI_SAMPLE) return fail(SF_ERR_INVALID, "unknown epilogue");
   // flag 1024: a 1x1 convolution + LayerNorm + GELU fused behind a lngelu stage (back-to-back GEMM in the epilogue); its
@@ -558,44 +611,20 @@ int sf_plan_define_stage(sf_plan* p, int stage, int epilogue, int n_chunks, cons
   for (const sf_chunk& c : st.chunks)
     if ((b2b || pw) && c.wrow + c.R * c.R * c.nrep * c.n > w_rows - b2b_rows) return fail(SF_ERR_INVALID, "chunk weight rows overlap the follow-up conv's rows");
   const int fixed = 1024 + (sf::VEC_MAX + 4 * ((flags & 512) ? sf::WG_SCRATCH_PAIR : sf::WG_SCRATCH)) * 4 + BAR_AREA + b2b_rows * ROW_BYTES;
-  // Weight tiles: as many taps of a dx column per tile as the cap allows (fewer producer <-> issuer barrier round trips per MMA;
-  // measured: 48 KB tiles are worth 4 % of the rollout over 24 KB ones), shrunk until at least two weight slots fit next to
-  // the activation ring.  Activation ring: one slot = one chunk's tile + halo, 3 slots when they leave room, up to 4.
-  int a_slot = 0, b_slot = 0, nA = 0, nB = 0;
-  for (int cap = B_TILE_MAX;; cap -= 8 * 1024) {
-    st.tb.clear();
-    a_slot = b_slot = 0;
-    for (const sf_chunk& c : st.chunks) {
-      const int tap_bytes = c.n * c.nrep * ROW_BYTES;
-      int tb = cap / tap_bytes;
-      if (tb < 1) tb = 1;
-      if (tb > c.R) tb = c.R;
-      if (flags & 512) tb = tb < 2 ? 2 : (tb & ~1);          // row-paired taps: a B tile = whole pairs of vertically adjacent taps
-      st.tb.push_back(tb);
-      const int a = (sf::a_box_bytes(c.R, sf::mtiles_for(st.mt_epi, p->g.C)) + 1023) & ~1023, b = tb * tap_bytes;
-      a_slot = a > a_slot ? a : a_slot;
-      b_slot = b > b_slot ? b : b_slot;
-    }
-    nA = (fixed + 3 * a_slot + 2 * b_slot <= SMEM_BUDGET) ? 3 : 2;
-    nB = (SMEM_BUDGET - fixed - nA * a_slot) / b_slot;
-    if (nB > sf::MAX_RING) nB = sf::MAX_RING;
-    if (nB >= 2) break;
-    if (cap <= 8 * 1024) return fail(SF_ERR_INVALID, "stage does not fit in shared memory");
-  }
-  while (nA < 4 && fixed + (nA + 1) * a_slot + nB * b_slot <= SMEM_BUDGET) ++nA;
+  st.flags = flags;
+  st.w_rows = w_rows;
+  st.fixed_smem = fixed;
+  st.b2b_bytes = b2b_rows * ROW_BYTES;
+  st.b2b_wrow = w_rows - b2b_rows;
+  if (int rc = layout_operand_rings(p, st, true)) return rc;
   st.w = w_packed;
   st.w_rows = w_rows;
   st.vec = vec;
   st.n_vec = n_vec;
   st.io.assign(io_bufs, io_bufs + n_io);
   if (io_choff) st.io_off.assign(io_choff, io_choff + n_io); else st.io_off.assign(n_io, 0);
-  st.flags = flags;
   st.n_out = 0;
   for (const sf_chunk& c : st.chunks) if (c.col == 0 && c.n > st.n_out) st.n_out = c.n;
-  st.a_slot = a_slot; st.b_slot = b_slot; st.nA = nA; st.nB = nB;
-  st.b2b_bytes = b2b_rows * ROW_BYTES;
-  st.b2b_wrow = w_rows - b2b_rows;
-  st.smem = fixed + nA * a_slot + nB * b_slot;
   int rc = encode_weight_map(w_packed, w_rows, &st.wmap);
   if (rc) return rc;
   st.defined = true;
@@ -608,6 +637,7 @@ int sf_plan_define_stage_fold(sf_plan* p, int stage, int which_se, const float* 
   if (which_se < 0 || which_se > 1 || !w32 || !row_meta || !w_scaled) return fail(SF_ERR_INVALID, "bad fold arguments");
   Stage& st = p->stage[stage];
   st.fold_se = which_se;
+  if (int rc = layout_operand_rings(p, st, false)) return rc;      // per-sample weights are streamed, never resident
   st.w32 = w32;
   st.row_meta = row_meta;
   st.w_scaled = w_scaled;

@@ -70,7 +70,7 @@ class StageDef:
         return self
 
 
-def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True, b2b: bool = True) -> List[StageDef]:
+def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True, b2b: bool = True, pair3: bool = False) -> List[StageDef]:
     """The conv stages of one dual-GRU cell (derivative or jump) from the reference's parameters; C = 64 or 128.
     b2b (C = 64): the Bottleblock's 7x7 conv + LN + GELU + 1x1 conv + LN + GELU run as ONE stage ("trunk")."""
     g = lambda k: sd[f"{p}.{k}"].float()
@@ -99,7 +99,8 @@ def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True,
                    .add(SX, wt1[:, :C_], 0, 1).add(BUF_G1, wt1[:, C_:], 0, 0))
         out.append(StageDef("propose_2", L.EPI_PROPOSE, g("conv_state_tilde_2.bias"), [BUF_U2, BUF_HH])
                    .add(SS, wt2[:, :C_], 0, 1).add(BUF_G2, wt2[:, C_:], 0, 0))
-    out.append(StageDef("decode", L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B]).add(BUF_HH, g("conv_decoder_2.weight"), 0, 1))
+    out.append(StageDef("decode", L.EPI_DECODE, g("conv_decoder_2.bias"), [BUF_B], flags=L.FLAG_PAIR_ROWS if (C_ == 64 and pair3) else 0)
+               .add(BUF_HH, g("conv_decoder_2.weight"), 0, 1))
     t = "trusting_gate.0."
     w7 = g(t + "layers.0.weight")
     # 64 channels: vertically adjacent taps of the 7x7 conv are paired into N = 128 MMAs (the MMA issue cost is ~41 + N/2 cycles)
@@ -123,7 +124,7 @@ def cell_stage_defs(sd: Dict[str, torch.Tensor], p: str, pair_rows: bool = True,
     return out
 
 
-def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str, fold_se: bool = False) -> List[object]:
+def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str, fold_se: bool = False, pair3: bool = False) -> List[object]:
     """p_model = ConvNet(C, 2C) with BatchNorm folded (res_models.py:168-180), as a list of StageDefs and the two SE markers
     'se0' / 'se1'.  Outputs wider than 128 channels are produced 128 channels per launch.
 
@@ -136,7 +137,7 @@ def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str, fold_se: bool = False)
     C_ = w1.shape[0]
     halves = (2 * C_) // 128
     SO = L.SRC_STATE_OUT
-    items: List[object] = [StageDef("q1", L.EPI_BIAS_LRELU, b1, [BUF_Q1]).add(SO, w1, 0, 1)]
+    items: List[object] = [StageDef("q1", L.EPI_BIAS_LRELU, b1, [BUF_Q1], flags=L.FLAG_PAIR_ROWS if (C_ == 64 and pair3) else 0).add(SO, w1, 0, 1)]
     wpj, bpj = sd[m + "0.projection.weight"].float(), sd[m + "0.projection.bias"].float()
     for h in range(halves):
         r = slice(128 * h, 128 * h + 128)
@@ -157,6 +158,30 @@ def prior_stage_defs(sd: Dict[str, torch.Tensor], p: str, fold_se: bool = False)
     items.append(StageDef("q5", L.EPI_SAMPLE, sd[m + "4.conv.bias"].float(), [BUF_X]).add(Y2, sd[m + "4.conv.weight"].float(), 0, 1))
     items[-1].fold_se = 1 if fold_se else None
     return items
+
+
+_PAIRABLE = None
+
+
+def pair_rows_if_eligible(sdef: StageDef, C_hidden: int = 64) -> StageDef:
+    """Sets FLAG_PAIR_ROWS on a stage of a 64-channel plan whose accumulator is ONE 64-column block produced by undilated 3x3 (or 7x7)
+    chunks only -- the N = 64 stages that sit at the 44 % issue ceiling of an MMA with both operands in shared memory: their
+    vertically adjacent taps then issue as N = 128 MMAs and the epilogue folds the second column block back one row (sf_conv.cuh
+    fold_paired_rows).  Measured on B200 (profiles/r02_ab_pair3_resident.txt): a LOSS for these light-epilogue stages -- decode 37.8 ->
+    45.5 us, q1 37.8 -> 41.9 us, forward 16.26 -> 16.54 ms: the fold roughly doubles their epilogue and tiles shrink to 15 rows, which
+    costs more than the 19 % fewer MMA issue cycles buy (the 7x7 trunk, whose epilogue is heavy anyway, keeps its pairing).  So this
+    is OFF unless SF_PAIR_3X3=1."""
+    global _PAIRABLE
+    if _PAIRABLE is None:
+        _PAIRABLE = (L.EPI_LNGELU, L.EPI_DECODE, L.EPI_BIAS_LRELU, L.EPI_RES_ID)
+    if os.environ.get("SF_PAIR_3X3", "0") != "1" or C_hidden != 64 or sdef.epilogue not in _PAIRABLE:
+        return sdef
+    if sdef.flags & (L.FLAG_PAIR_ROWS | L.FLAG_RES_SE_SCALE | L.FLAG_PW_B2B):
+        return sdef
+    if not sdef.chunks or any(w.shape[0] != 64 or w.shape[2] < 3 or col != 0 or ox or oy for _, _, w, col, _, ox, oy in sdef.chunks):
+        return sdef
+    sdef.flags |= L.FLAG_PAIR_ROWS
+    return sdef
 
 
 def pack_stage_master(sdef: StageDef, x3: bool):
@@ -429,10 +454,11 @@ class OdeEngine:
         self.stage_names: Dict[int, str] = {}
         pair = os.environ.get("SF_PAIR_ROWS", "1") != "0"
         b2b = os.environ.get("SF_B2B", "1") != "0"
+        pair3 = os.environ.get("SF_PAIR_3X3", "0") == "1"        # measured slower (decode 38 -> 45 us): off unless asked for
         # BatchNorm / cat[state, state] folding, tap order and the hi / lo split happen in the library (sf_pack_cell_weights,
         # sf_pack_pmodel_weights: csrc/sf_ode.cu) -- the same bytes a C host gets; cell_stage_defs / prior_stage_defs / pack_stage
         # above restate them in torch and are pinned to the library's output by tests/test_c_host.py
-        cells = [cpack.pack_cell(sd, pre + "gru_c.", self.x3, pair, b2b), cpack.pack_cell(sd, pre + "gru_obs.gru_d.", self.x3, pair, b2b)]
+        cells = [cpack.pack_cell(sd, pre + "gru_c.", self.x3, pair, b2b, pair3), cpack.pack_cell(sd, pre + "gru_obs.gru_d.", self.x3, pair, b2b, pair3)]
         n_cell = len(cells[0])
         cell_slots = [list(range(ws * n_cell, (ws + 1) * n_cell)) for ws in range(2)]
         for ws in range(2):
@@ -441,7 +467,7 @@ class OdeEngine:
                 if ws == 0:
                     self.stage_names[slot] = item.name
         prior_items, slot, se_items = [], 2 * n_cell, []
-        for it in cpack.pack_pmodel(sd, pre + "p_model.", self.x3, self.se_fold):
+        for it in cpack.pack_pmodel(sd, pre + "p_model.", self.x3, self.se_fold, pair3):
             if it.se_layer >= 0:
                 prior_items.append((L.SE_FOLD_ITEM_BASE if self.se_fold else L.SE_ITEM_BASE) + it.se_layer)
                 self.stage_names[prior_items[-1]] = "se" + str(it.se_layer + 1)

@@ -84,7 +84,7 @@ int main(int argc, char** argv) {
   }
 
   sf_geometry geo = {B, h, w, C, SF_PREC_BF16, 0};
-  sf_ode_options opt = {info.n_path, B * n_obs, info.n_eps, SF_PACK_PAIR_ROWS | SF_PACK_B2B | SF_PACK_FOLD_SE};
+  sf_ode_options opt = {info.n_path, B * n_obs, info.n_eps, SF_PACK_DEFAULT};
   size_t ws_bytes = 0;
   SF(sf_ode_query_workspace(&geo, &opt, &ws_bytes));
   void* ws = NULL;

@@ -51,18 +51,20 @@ def test_c_weight_packers_equal_the_torch_restatement_bit_for_bit(Cc, monkeypatc
     byte of the packed bf16 matrices (cat[state, state] fold, BatchNorm fold, tap order, row pairing, fused 1x1, hi / lo split)."""
     monkeypatch.setattr(en, "_bn_fold", _bn_fold_ieee)
     sd = _weights(Cc)
-    options = ((True, True), (False, True), (True, False), (False, False)) if Cc == 64 else ((True, True),)
+    options = ((True, True, True), (False, True, False), (True, False, True), (False, False, False), (True, True, False)) if Cc == 64 else ((True, True, True),)
     for x3 in (False, True):
-        for pair, b2b in options:
+        for pair, b2b, pair3 in options:
             for pre in ("gru_c", "gru_obs.gru_d"):
-                want = en.cell_stage_defs(sd, pre, pair, b2b)
-                got = cpack.pack_cell(sd, pre + ".", x3, pair, b2b)
+                want = en.cell_stage_defs(sd, pre, pair, b2b, pair3)
+                got = cpack.pack_cell(sd, pre + ".", x3, pair, b2b, pair3)
+                if Cc == 64:
+                    assert bool(next(g for g in got if g.name == "decode").flags & L.FLAG_PAIR_ROWS) == pair3
                 assert [d.name for d in want] == [g.name for g in got]
                 for d, g in zip(want, got):
                     _same_stage(g, d, x3)
-        for fold in (False, True):
-            want = en.prior_stage_defs(sd, "p_model", fold_se=fold)
-            got = cpack.pack_pmodel(sd, "p_model.", x3, fold)
+        for fold, pair3 in ((False, True), (True, True), (True, False)):
+            want = en.prior_stage_defs(sd, "p_model", fold_se=fold, pair3=pair3)
+            got = cpack.pack_pmodel(sd, "p_model.", x3, fold, pair3)
             assert len(want) == len(got)
             for d, g in zip(want, got):
                 if isinstance(d, str):
@@ -174,7 +176,7 @@ def test_ode_workspace_query_is_pure_host_and_accounts_for_every_buffer(Cc, x3):
     tensors and the packed weights, and grows with each of them."""
     lib = L.load()
 
-    def query(B=2, H=24, W=20, path=5, obs=7, eps=11, opts=L.PACK_PAIR_ROWS | L.PACK_B2B | L.PACK_FOLD_SE):
+    def query(B=2, H=24, W=20, path=5, obs=7, eps=11, opts=L.PACK_DEFAULT):
         g = L.Geometry(B, H, W, Cc, L.PREC_BF16X3 if x3 else L.PREC_BF16, 0)
         o = L.OdeOptions(path, obs, eps, opts)
         n = C.c_size_t()

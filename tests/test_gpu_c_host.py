@@ -43,7 +43,7 @@ class COde:
     def __init__(self, sd, Cc, h, w, B, precision, n_path, n_obs, n_eps, dev):
         self.lib = lib = L.load()
         self.geo = L.Geometry(B, h, w, Cc, L.PREC_BF16X3 if precision == "bf16x3" else L.PREC_BF16, dev.index or 0)
-        self.opt = L.OdeOptions(n_path, n_obs, n_eps, L.PACK_PAIR_ROWS | L.PACK_B2B | L.PACK_FOLD_SE)
+        self.opt = L.OdeOptions(n_path, n_obs, n_eps, L.PACK_DEFAULT)     # the engine's defaults
         nbytes = C.c_size_t()
         L.check(lib.sf_ode_query_workspace(C.byref(self.geo), C.byref(self.opt), C.byref(nbytes)), "sf_ode_query_workspace")
         self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)          # the caller owns the device memory

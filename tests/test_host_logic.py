@@ -704,3 +704,31 @@ def test_inner_api_is_registered_as_torch_custom_ops(golden_dir):
     with FakeTensorMode():                                   # shapes without running anything (tracing / torch.compile)
         y, params = torch.ops.sf_b200.infer_state(torch.empty(2, C, 4, 4), m._op_handle)
     assert y.shape == (2, C, 4, 4) and params.shape == (2, 2 * C, 4, 4)
+
+
+@pytest.mark.parametrize("x3", [False, True])
+def test_row_paired_taps_of_a_generic_3x3_stage_replay_to_the_same_accumulator(x3, monkeypatch):
+    """engine.pair_rows_if_eligible marks 64 -> 64 3x3 stages (decoder / encoder convs, SpatialGRU proposal, decode, q1) for row-paired
+    taps; the packed plan replayed the way the kernel runs it ([dy_hi | dy_lo] operands, block 1 folded one row down, a virtual
+    row above the image) gives the accumulator of the plain plan; ineligible stages are left alone."""
+    from streamingflow_b200 import _lib as L, engine as en
+
+    assert not en.pair_rows_if_eligible(en.StageDef("c", L.EPI_BIAS_LRELU, torch.zeros(64), [3]).add(7, torch.zeros(64, 64, 3, 3), 0, 1)).flags & L.FLAG_PAIR_ROWS
+    monkeypatch.setenv("SF_PAIR_3X3", "1")          # off by default (measured slower on B200); the mechanism stays tested
+    g = torch.Generator().manual_seed(4)
+    wa, wb = torch.randn(64, 64, 3, 3, generator=g) * 0.1, torch.randn(64, 64, 3, 3, generator=g) * 0.1
+    src = {7: torch.randn(1, 64, 21, 13, generator=g), 9: torch.randn(1, 128, 21, 13, generator=g)}
+    mk = lambda: en.StageDef("conv", L.EPI_RES_ID, torch.zeros(64), [3, 4]).add(7, wa, 0, 1).add(9, wb, 0, 0, c0=64)
+    plain, paired = mk(), en.pair_rows_if_eligible(mk())
+    assert paired.flags & L.FLAG_PAIR_ROWS and not plain.flags & L.FLAG_PAIR_ROWS
+    a, b = en.emulate_stage(plain, x3, src), en.emulate_stage(paired, x3, src)
+    assert (a[:64] - b[:64]).abs().max().item() < 1e-9 * a.abs().max().item()
+    assert en.pack_stage(paired, x3)[1].shape == en.pack_stage(plain, x3)[1].shape
+    # not eligible: 128 output columns, a 1x1 chunk, a dilated tap, the dual proposal, a 128-channel plan
+    wide = en.StageDef("w", L.EPI_BIAS_LRELU, torch.zeros(128), [3]).add(7, torch.randn(128, 64, 3, 3), 0, 1)
+    one = en.StageDef("o", L.EPI_BIAS_LRELU, torch.zeros(64), [3]).add(7, wa, 0, 1).add(7, torch.randn(64, 64, 1, 1), 0, 0)
+    dil = en.StageDef("d", L.EPI_BIAS_LRELU, torch.zeros(64), [3]).add(7, wa, 0, 1, ox=2)
+    dual = en.StageDef("p", L.EPI_PROPOSE, torch.zeros(128), [1, 2, 3, 4]).add(7, wa, 0, 1)
+    for sdef in (wide, one, dil, dual):
+        assert not en.pair_rows_if_eligible(sdef).flags & L.FLAG_PAIR_ROWS
+    assert not en.pair_rows_if_eligible(mk(), C_hidden=128).flags & L.FLAG_PAIR_ROWS
