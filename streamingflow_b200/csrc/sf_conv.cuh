@@ -272,6 +272,12 @@ __device__ __forceinline__ void fold_paired_rows(const StageParams& p, uint32_t 
   }
   tmem_st_wait();
 }
+// epilogues whose stage may keep its weights resident in shared memory (StageParams::resident_b).  The register-bound gates /
+// propose / sample instantiations and the fused trunk (their weights never fit anyway) compile the path out: with it in, ptxas
+// spilled 28 instead of 8 bytes in propose and the stage ran ~5 % slower.
+__host__ __device__ constexpr bool epi_can_be_resident(int epi) {
+  return !(epi == SF_EPI_GATES || epi == SF_EPI_PROPOSE || epi == SF_EPI_SAMPLE || epi == SF_EPI_LNGELU_B2B);
+}
 // epilogues that accept row-paired taps: one 64-column accumulator block at column 0 (the register-bound propose / mix / sample
 // epilogues stay out: the extra code costs them spills)
 __host__ __device__ constexpr bool epi_can_pair(int epi) {
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
       if (elect_one()) {
         for (int c = 0; c < p.nchunk; ++c) tma_prefetch_desc(&p.amap[c]);
         tma_prefetch_desc(&p.wmap);
-        if (p.resident_b) {               // the stage's own weights: resident for the whole launch
+        if (epi_can_be_resident(EPI) && p.resident_b) {               // the stage's own weights: resident for the whole launch
           mbar_expect_tx(b_full0, (uint32_t)p.resident_b);
           for (int q = 0; q * 64 * ROW_BYTES < p.resident_b; ++q) tma_load_2d(b_smem0 + q * 64 * ROW_BYTES, &p.wmap, b_full0, 0, q * 64);
         }
@@ -815,7 +821,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
           const int tap_rows = ck.n * ck.nrep;                  // weight rows of one tap
           const int ngrp = (R + ck.tb - 1) / ck.tb;             // B tiles per dx column; the last one may hold fewer taps
           int dx = rem % R, g0 = (ck.tb == 1) ? (rem / R) % R : 0;     // tap rotation (same formula in the MMA warp)
-          if (p.resident_b) continue;                                  // weights already in shared memory
+          if (epi_can_be_resident(EPI) && p.resident_b) continue;      // weights already in shared memory
           for (int i = 0; i < R; ++i) {
             int gi = g0;
             for (int j = 0; j < ngrp; ++j) {
@@ -844,7 +850,7 @@ __global__ void __launch_bounds__(128 + 128 * ACC_STAGES * mtiles_for(EPI, CG) *
     {
       // ===================== MMA issuer (converged warp, one elected lane issues) =====================
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 1;   // parities to wait for on the FULL barriers / acc EMPTY
-      const bool resident = p.resident_b != 0;
+      const bool resident = epi_can_be_resident(EPI) && p.resident_b != 0;
       if (resident && blockIdx.x < (unsigned)nwork) {              // the one-time weight load
         mbar_wait(b_full0, 0, p.err, 5);
         tc_fence_after();

@@ -490,7 +490,8 @@ int layout_operand_rings(sf_plan* p, Stage& st, bool allow_resident) {
     }
     const int res_bytes = st.b2b_wrow * ROW_BYTES;           // every row of the chunks (a fused follow-up conv's rows have their own region)
     const int res_slot = (res_bytes + 1023) & ~1023;
-    if (allow_resident && resident_on && cap == B_TILE_MAX && res_bytes > 0 && fixed + res_slot + 2 * a_slot <= SMEM_BUDGET) {
+    const int kepi_static = (st.epi == SF_EPI_LNGELU && st.b2b_bytes) ? sf::SF_EPI_LNGELU_B2B : st.epi;      // (the launch-time variants of bias_act / res_id can all be resident)
+    if (allow_resident && resident_on && sf::epi_can_be_resident(kepi_static) && cap == B_TILE_MAX && res_bytes > 0 && fixed + res_slot + 2 * a_slot <= SMEM_BUDGET) {
       nA = (SMEM_BUDGET - fixed - res_slot) / a_slot;
       if (nA > 4) nA = 4;
       st.a_slot = a_slot; st.b_slot = res_slot; st.nA = nA; st.nB = 1;
