@@ -390,7 +390,11 @@ int sf_ode_tensor(sf_ode* ode, int which, void** ptr, size_t* bytes);
 int sf_ode_set_observations(sf_ode* ode, const float* obs_nchw, int first_image, int n_images, void* stream);
 /* state buffers (fp32 masters and bf16 mirrors) of the first n_images samples back to zero (temporal_ode_bayes.py:505)  */
 int sf_ode_reset_state(sf_ode* ode, void* stream);
-/* ONE event (cell + state update + prior net + sampling) / a whole event list; `table` is the device copy of the event table */
+/* ONE event (cell + state update + prior net + sampling) / a whole event list; `table` is the device copy of the event table.
+   SURVEY 8b's finer-grained proposals are events with flags: sf_dual_gru_cell(mode = DERIV | JUMP) = kind 0 / 1 with run_prior = 0
+   (DualGRUODECell.forward / GRUObservationCell.forward; the derivative itself is the update from a zero base buffer with dt = 1:
+   s_base = a zeroed state buffer, s_in = the state, dt = 1 -> s_out = f(x, s)), sf_infer_state = run_cell = 0, run_prior = 1,
+   want_f32 = 1 (fills SF_ODE_X32 / SF_ODE_PARAMS32), sf_event = one full event, sf_rollout = the list. */
 int sf_ode_event(sf_ode* ode, const sf_event* ev, const int32_t* table, void* stream);
 int sf_ode_rollout(sf_ode* ode, const sf_event* evs, int n_events, const int32_t* table, void* stream);
 /* recorded states `slots` (device int32 [n]) -> fp32 NCHW [n][C][H][W] on the device */
@@ -401,6 +405,10 @@ int sf_ode_read_path(sf_ode* ode, const int32_t* slots, int n, float* out_nchw, 
    steps in float32, see schedule.py).  solver: 0 euler, 1 midpoint.  flags: bit 0 keep the dead prior-net evaluations (the
    reference's literal schedule), bit 1 keep the input sampled after the last op alive (streaming).
    obs image index of sample b's k-th observation = b * n_obs + k. */
+/* Processing order of ONE sample's observations (future_prediction_ode.py:37-45: the camera frames go into a dict, then the LiDAR
+   frames, then a STABLE sort by time -- camera wins ties, duplicates are all kept).  Writes n_cam + n_lidar entries: times[i] and
+   source[i] = sensor * 65536 + index (sensor 0 = camera, 1 = LiDAR); returns the count.  lidar_t may be NULL (n_lidar = 0). */
+int sf_merge_observations(const double* camera_t, int n_cam, const double* lidar_t, int n_lidar, double* times, int32_t* source);
 typedef struct sf_rollout_plan sf_rollout_plan;
 typedef struct {
   int32_t n_events, n_table, n_eps, n_path, n_state_steps, n_jumps, n_cell_evals, n_prior_evals;

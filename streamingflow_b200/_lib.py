@@ -130,6 +130,7 @@ EXPORTS = {
     "sf_ode_event": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_void_p, C.c_void_p]),
     "sf_ode_rollout": (C.c_int, [C.c_void_p, C.POINTER(Event), C.c_int, C.c_void_p, C.c_void_p]),
     "sf_ode_read_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_merge_observations": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "sf_rollout_plan_create": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sf_rollout_plan_info": (C.c_int, [C.c_void_p, C.POINTER(RolloutInfo)]),

@@ -12,6 +12,7 @@
 //   q1..q5   p_model = ConvNet with eval-mode BatchNorm folded                              res_models.py:168-180
 //   schedule start time :508, advance-to-observation :539-553, jump / record :562-581, advance-to-target :585-604,
 //            output selection :606-622
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -900,6 +901,17 @@ struct SampleEvent {
 using namespace sfo;
 
 extern "C" {
+
+int sf_merge_observations(const double* camera_t, int n_cam, const double* lidar_t, int n_lidar, double* times, int32_t* source) {
+  if ((!camera_t && n_cam > 0) || (!lidar_t && n_lidar > 0) || n_cam < 0 || n_lidar < 0 || !times || !source)
+    return ofail(SF_ERR_INVALID, "sf_merge_observations: bad argument");
+  std::vector<std::pair<double, int32_t>> items;
+  for (int i = 0; i < n_cam; ++i) items.push_back(std::make_pair(camera_t[i], (int32_t)i));
+  for (int i = 0; i < n_lidar; ++i) items.push_back(std::make_pair(lidar_t[i], (int32_t)(65536 + i)));
+  std::stable_sort(items.begin(), items.end(), [](const std::pair<double, int32_t>& a, const std::pair<double, int32_t>& b) { return a.first < b.first; });
+  for (size_t i = 0; i < items.size(); ++i) { times[i] = items[i].first; source[i] = items[i].second; }
+  return (int)items.size();
+}
 
 int sf_rollout_plan_create(const double* obs_times, int n_obs, const double* targets, int n_targets, int B, double delta_t, int variable_step,
                            int solver, int impute, int obs_f32, int target_f32, int flags, sf_rollout_plan** out) {

@@ -198,3 +198,45 @@ def test_ode_workspace_query_is_pure_host_and_accounts_for_every_buffer(Cc, x3):
     g = L.Geometry(2, 24, 20, 96, 0, 0)
     n = C.c_size_t()
     assert lib.sf_ode_query_workspace(C.byref(g), None, C.byref(n)) == -1 and b"64 or 128" in lib.sf_last_error()
+
+
+def test_ode_create_fails_loudly_without_a_b200():
+    """sf_ode_create on a host without the GPU: the weights pack (pure host), then the plan refuses -- a negative status and a message,
+    no silent CPU path (the size query and the packers are the only entry points that work here)."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without a GPU")
+    lib = L.load()
+    sd = _weights(64)
+    hot = {k: v for k, v in sd.items() if k.startswith(("gru_c.", "gru_obs.", "p_model."))}
+    arr, n, keep = cpack.tensor_table(hot)
+    g = L.Geometry(1, 12, 12, 64, L.PREC_BF16, 0)
+    o = L.OdeOptions(4, 3, 9, L.PACK_DEFAULT)
+    h = C.c_void_p()
+    fake_ws = C.c_void_p(1 << 20)          # never dereferenced: creation fails before the first device call on it
+    rc = lib.sf_ode_create(C.byref(g), C.byref(o), arr, n, b"", fake_ws, C.c_size_t(1 << 40), C.byref(h))
+    assert rc < 0 and not h.value and len(lib.sf_last_error()) > 0
+    bad = lib.sf_ode_create(C.byref(g), C.byref(o), arr, n, b"", C.c_void_p((1 << 20) + 8), C.c_size_t(1 << 40), C.byref(h))
+    assert bad == -1 and b"aligned" in lib.sf_last_error()
+    assert lib.sf_ode_create(C.byref(g), C.byref(o), arr, n, b"nope.", fake_ws, C.c_size_t(1 << 40), C.byref(h)) == -1      # prefix strips every tensor
+
+
+def test_c_merge_of_camera_and_lidar_stamps_equals_the_reference_order():
+    """sf_merge_observations == schedule.merge_observations (the reference's dict fill + stable sort, future_prediction_ode.py:37-45):
+    camera wins ties, duplicates stay, LiDAR may be absent."""
+    from streamingflow_b200.schedule import merge_observations
+
+    lib = L.load()
+    rng = random.Random(5)
+    cases = [([-1.0, -0.5, 0.0], [-0.8, -0.5, 0.0, 0.0]), ([-1.0, -0.5, 0.0], None), ([0.0], [0.0, 0.0])]
+    for _ in range(50):
+        cases.append(([round(rng.uniform(-1, 0), 1) for _ in range(rng.randint(1, 4))], [round(rng.uniform(-1, 0), 1) for _ in range(rng.randint(0, 6))]))
+    for cam, lid in cases:
+        n_l = len(lid) if lid else 0
+        ct = (C.c_double * len(cam))(*cam)
+        lt = (C.c_double * max(1, n_l))(*(lid or [0.0]))
+        times = (C.c_double * (len(cam) + n_l))()
+        src = (C.c_int32 * (len(cam) + n_l))()
+        n = lib.sf_merge_observations(ct, len(cam), lt if n_l else None, n_l, times, src)
+        want = merge_observations(cam, lid if n_l else None)
+        assert n == len(want)
+        assert [(times[i], src[i] >> 16, src[i] & 0xFFFF) for i in range(n)] == [(t, s, i) for t, s, i in want]
