@@ -732,3 +732,30 @@ def test_row_paired_taps_of_a_generic_3x3_stage_replay_to_the_same_accumulator(x
     for sdef in (wide, one, dil, dual):
         assert not en.pair_rows_if_eligible(sdef).flags & L.FLAG_PAIR_ROWS
     assert not en.pair_rows_if_eligible(mk(), C_hidden=128).flags & L.FLAG_PAIR_ROWS
+
+
+def test_live_noise_slots_are_exactly_the_slots_prior_net_evaluations_read():
+    """Rollout.live_eps (what sf_normal_fill_slot_list draws): the noise slots of the events that run the prior net -- every slot when
+    the dead evaluations are kept, the slots before a step (and inside a midpoint step) otherwise; slot numbering itself never changes."""
+    times = sorted([-1.0, -0.5, 0.0, -0.8, -0.6, -0.4, -0.2, 0.0])
+    targets = [-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+    for solver in ("euler", "midpoint"):
+        plans = [sc.plan_sample(times, targets, 0.05, True, solver), sc.plan_sample([t + 0.01 for t in times], targets, 0.05, True, solver)]
+        full = compile_rollout(plans, [0, 8], solver, True, skip_dead_prior=False)
+        live = compile_rollout(plans, [0, 8], solver, True, skip_dead_prior=True)
+        assert full.n_eps == live.n_eps and full.live_eps == list(range(full.n_eps))
+        want = sorted(s for e in live.events if e["run_prior"] for s in e["eps"])
+        assert live.live_eps == want and len(want) == live.n_prior_evals < live.n_eps
+        # a slot is live iff the NEXT op of its sample is a step (or it sits inside a midpoint step)
+        off = 0
+        for plan in plans:
+            per = 2 if solver == "midpoint" else 1
+            for i, op in enumerate(plan.ops):
+                n = per if op.kind == sc.STEP else 1
+                nxt_step = i + 1 < len(plan.ops) and plan.ops[i + 1].kind == sc.STEP
+                for k in range(n):
+                    inside_midpoint = op.kind == sc.STEP and per == 2 and k == 0
+                    assert ((off + k) in live.live_eps) == (nxt_step or inside_midpoint)
+                off += n
+    none = compile_rollout([sc.plan_sample(times, targets, 0.05, True)], [0], "euler", False)
+    assert none.live_eps == [] and none.n_eps > 0          # IMPUTE off: the reference still draws, nothing reads
